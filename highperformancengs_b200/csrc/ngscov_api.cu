@@ -1,0 +1,803 @@
+/* csrc/ngscov_api.cu -- C ABI of libngscov_cuda (see include/ngscov.h for the contract and the
+ * reference code each entry point replaces).  Host-side orchestration only: memory, streams, launch
+ * order, the (rare) verify/repair loop and the per-stage CUDA-event timers.  All arithmetic on the
+ * data runs in the kernels of ngscov_kernels.cuh.
+ */
+#include "../../include/ngscov.h"
+#include "ngscov_kernels.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#define NGS_HEADROOM (NGS_CARRY_MAX + 256)
+
+struct ngscov {
+	ngscov_cfg cfg;
+	int n_ref;
+	std::vector<uint32_t> ref_len;
+	std::vector<std::string> ref_name;
+	int device;
+	cudaStream_t s_main, s_copy;
+	cudaEvent_t ev_h2d[2], ev_verified, ev_finalized, ev_t0, ev_t1;
+	char cuda_err[256];
+
+	/* geometry */
+	std::vector<ngs_seg> seg;
+	std::vector<int32_t> ctg2seg;
+	uint64_t n_tiles, n_elems, n_bins;
+	std::vector<uint64_t> win_base;          /* [n_ref+1] */
+	ngs_seg *d_seg; int32_t *d_ctg2seg; uint32_t *d_tile2seg; uint32_t *d_ref_len;
+	unsigned long long *d_win_base;
+	int *d_diff; bool diff_dirty;
+	unsigned long long *d_bins;
+
+	/* names */
+	char *d_names; uint32_t *d_name_off; uint32_t max_name_tab;   /* "name\t" */
+	char *d_wighdr; uint32_t *d_wighdr_off; uint32_t max_wighdr;
+
+	/* staging + chunk buffers */
+	size_t stage_cap;
+	uint8_t *h_stage[2]; uint8_t *d_chunk[2]; uint8_t *d_carry;
+	bool stage_busy[2];
+
+	/* sub-chunk walk */
+	int shift;
+	long long *d_entry, *d_exit, *d_bmax; size_t sub_cap, bmax_cap;
+	ngs_dev_state *d_st, *h_st;
+
+	/* pending (unverified) chunk */
+	bool pending; const uint8_t *p_base; int64_t p_n; int64_t p_nsub; bool p_from_state; long long p_fixed0;
+	bool last_pushed; int last_flags;
+	int sticky_err;
+
+	/* runs */
+	uint32_t *d_run_start, *d_run_end; int *d_run_depth; size_t run_cap;
+	unsigned long long *d_rec_base, *d_stA, *d_stB, *d_fmt_status; size_t fmt_status_cap;
+	std::vector<unsigned long long> h_rec_base;
+	bool runs_done, formatted;
+	unsigned long long drop_idx, mod_idx; uint32_t mod_end;
+	ngscov_halo halo;
+
+	/* text */
+	char *d_text[4]; size_t d_text_cap[4]; size_t text_len[4]; bool text_ready[4];
+	char *h_text[4]; size_t h_text_cap[4]; bool h_text_valid[4];
+	std::string chromsize;
+
+	ngscov_stats_t stats;
+	int sm_count;
+	/* per-push timing events (start/end pairs), reused across inputs */
+	std::vector<cudaEvent_t> ev_ing, ev_cp; size_t n_ing, n_cp;
+};
+
+static cudaEvent_t next_event(std::vector<cudaEvent_t> &pool, size_t &used)
+{
+	if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+	return pool[used++];
+}
+static float sum_events(std::vector<cudaEvent_t> &pool, size_t &used)
+{
+	float tot = 0;
+	for (size_t i = 0; i + 1 < used; i += 2) { float ms = 0; if (cudaEventElapsedTime(&ms, pool[i], pool[i + 1]) == cudaSuccess) tot += ms; }
+	used = 0;
+	return tot;
+}
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+	snprintf(h->cuda_err, sizeof h->cuda_err, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	return e__ == cudaErrorMemoryAllocation ? NGSCOV_ENOMEM : NGSCOV_ECUDA; } } while (0)
+
+static void tic(ngscov *h) { cudaEventRecord(h->ev_t0, h->s_main); }
+static float toc(ngscov *h)
+{
+	float ms = 0;
+	cudaEventRecord(h->ev_t1, h->s_main);
+	cudaEventSynchronize(h->ev_t1);
+	cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
+	return ms;
+}
+
+extern "C" int ngscov_abi_version(void) { return NGSCOV_ABI_VERSION; }
+
+extern "C" const char *ngscov_strerror(int code)
+{
+	switch (code) {
+	case NGSCOV_OK: return "ok";
+	case NGSCOV_EINVAL: return "invalid argument";
+	case NGSCOV_ECUDA: return "CUDA error";
+	case NGSCOV_ENOMEM: return "out of device or pinned memory";
+	case NGSCOV_EFORMAT: return "malformed or truncated BAM record stream";
+	case NGSCOV_ERANGE: return "alignment reaches beyond contig end + overhang pad";
+	case NGSCOV_ESTATE: return "call sequence violated";
+	case NGSCOV_ETOOBIG: return "record header larger than the carry area";
+	default: return "unknown error";
+	}
+}
+
+extern "C" const char *ngscov_last_cuda_error(const ngscov_t *h) { return h ? h->cuda_err : ""; }
+
+template <class T>
+static int dev_upload(ngscov *h, T **dst, const std::vector<T> &src)
+{
+	CK(cudaMalloc((void **)dst, std::max<size_t>(1, src.size()) * sizeof(T)));
+	if (!src.empty()) CK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+static int build_geometry(ngscov *h)
+{
+	const ngscov_cfg &c = h->cfg;
+	const uint32_t W = c.window;
+	h->ctg2seg.assign(h->n_ref, -1);
+	h->win_base.assign((size_t)h->n_ref + 1, 0);
+	uint64_t g0 = 0, elems = 0, tiles = 0;
+	for (int i = 0; i < h->n_ref; ++i) {
+		const uint32_t L = h->ref_len[i];
+		const uint64_t g1 = g0 + L;
+		h->win_base[i + 1] = h->win_base[i] + (uint64_t)(L / W) + 1;
+		bool in; uint32_t lo = 0, hi = L;
+		if (c.slice_end == 0) in = true;
+		else {
+			in = (c.slice_beg < g1 && c.slice_end > g0) || (L == 0 && c.slice_beg <= g0 && g0 < c.slice_end);
+			if (in) {
+				lo = c.slice_beg > g0 ? (uint32_t)(c.slice_beg - g0) : 0;
+				hi = c.slice_end < g1 ? (uint32_t)(c.slice_end - g0) : L;
+			}
+		}
+		if (in) {
+			ngs_seg s; memset(&s, 0, sizeof s);
+			s.contig = (uint32_t)i; s.clip_lo = lo; s.ref_len = L; s.n_win = L / W + 1;
+			s.hard_end = hi == L;
+			if (s.hard_end) { uint64_t lim = (uint64_t)L + NGSCOV_OVERHANG_PAD; s.lim = (uint32_t)std::min<uint64_t>(lim, NGS_POS_MASK); }
+			else s.lim = hi;
+			if (s.lim < lo) s.lim = lo;
+			const uint64_t n = (uint64_t)s.lim - lo + 1, nt = (n + NGS_TILE - 1) / NGS_TILE;
+			s.base = elems; s.tile0 = tiles; s.bins0 = h->win_base[i];
+			elems += nt * NGS_TILE; tiles += nt;
+			h->ctg2seg[i] = (int32_t)h->seg.size();
+			h->seg.push_back(s);
+		}
+		g0 = g1;
+	}
+	h->n_elems = elems; h->n_tiles = tiles; h->n_bins = h->win_base[h->n_ref];
+	return 0;
+}
+
+static int create_impl(ngscov_t **out, const ngscov_cfg *cfg);
+extern "C" int ngscov_create(ngscov_t **out, const ngscov_cfg *cfg)
+{
+	if (!out) return NGSCOV_EINVAL;
+	*out = nullptr;
+	const int r = create_impl(out, cfg);
+	if (r && *out) {
+		static char last_err[256];
+		snprintf(last_err, sizeof last_err, "%s", (*out)->cuda_err);
+		if (getenv("NGSCOV_DEBUG")) fprintf(stderr, "ngscov_create: %s: %s\n", ngscov_strerror(r), last_err);
+		ngscov_destroy(*out); *out = nullptr;
+	}
+	return r;
+}
+static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
+{
+	if (!out || !cfg || cfg->n_ref < 0 || (cfg->n_ref && (!cfg->ref_len || !cfg->ref_name))) return NGSCOV_EINVAL;
+	if (cfg->window < 1 || cfg->window > (1u << 30)) return NGSCOV_EINVAL;
+	if (cfg->mode != NGSCOV_MODE_DEPTH && cfg->mode != NGSCOV_MODE_WIG) return NGSCOV_EINVAL;
+	if (cfg->slice_end && cfg->slice_end <= cfg->slice_beg) return NGSCOV_EINVAL;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) return NGSCOV_ECUDA;
+	ngscov *h = new ngscov();
+	h->cfg = *cfg; h->n_ref = cfg->n_ref; h->device = cfg->device; h->cuda_err[0] = 0;
+	h->ref_len.assign(cfg->ref_len, cfg->ref_len + cfg->n_ref);
+	for (int i = 0; i < cfg->n_ref; ++i) h->ref_name.push_back(cfg->ref_name[i] ? cfg->ref_name[i] : "");
+	h->cfg.ref_len = nullptr; h->cfg.ref_name = nullptr;
+	*out = h;
+#define CKC(call) do { int r__ = (call); if (r__) { return r__; } } while (0)
+	CK(cudaSetDevice(h->device));
+	cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, h->device));
+	h->sm_count = prop.multiProcessorCount;
+	CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_verified, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_finalized, cudaEventDisableTiming));
+	CK(cudaEventCreate(&h->ev_t0)); CK(cudaEventCreate(&h->ev_t1));
+	build_geometry(h);
+	CKC(dev_upload(h, &h->d_seg, h->seg));
+	CKC(dev_upload(h, &h->d_ctg2seg, h->ctg2seg));
+	CKC(dev_upload(h, &h->d_ref_len, h->ref_len));
+	{
+		std::vector<unsigned long long> wb(h->win_base.begin(), h->win_base.end());
+		CKC(dev_upload(h, &h->d_win_base, wb));
+		std::vector<uint32_t> t2s(h->n_tiles);
+		for (size_t s = 0; s < h->seg.size(); ++s) {
+			const uint64_t t1 = s + 1 < h->seg.size() ? h->seg[s + 1].tile0 : h->n_tiles;
+			for (uint64_t t = h->seg[s].tile0; t < t1; ++t) t2s[t] = (uint32_t)s;
+		}
+		CKC(dev_upload(h, &h->d_tile2seg, t2s));
+		/* name tables */
+		std::vector<char> names, wh; std::vector<uint32_t> noff(1, 0), whoff(1, 0);
+		h->max_name_tab = 0; h->max_wighdr = 0;
+		for (int i = 0; i < h->n_ref; ++i) {
+			const std::string &nm = h->ref_name[i];
+			names.insert(names.end(), nm.begin(), nm.end()); names.push_back('\t');
+			noff.push_back((uint32_t)names.size());
+			h->max_name_tab = std::max<uint32_t>(h->max_name_tab, (uint32_t)nm.size() + 1);
+			char tmp[64]; snprintf(tmp, sizeof tmp, " span=%d\n", (int)h->cfg.window);
+			std::string hd = "variableStep chrom=" + nm + tmp;
+			wh.insert(wh.end(), hd.begin(), hd.end());
+			whoff.push_back((uint32_t)wh.size());
+			h->max_wighdr = std::max<uint32_t>(h->max_wighdr, (uint32_t)hd.size());
+			char cs[64]; snprintf(cs, sizeof cs, "\t%d\n", (int)h->ref_len[i]);
+			h->chromsize += nm + cs;
+		}
+		CKC(dev_upload(h, &h->d_names, names)); CKC(dev_upload(h, &h->d_name_off, noff));
+		CKC(dev_upload(h, &h->d_wighdr, wh)); CKC(dev_upload(h, &h->d_wighdr_off, whoff));
+	}
+	CK(cudaMalloc((void **)&h->d_diff, std::max<uint64_t>(1, h->n_elems) * sizeof(int)));
+	tic(h);
+	CK(cudaMemsetAsync(h->d_diff, 0, h->n_elems * sizeof(int), h->s_main));
+	h->stats.ms_zero += toc(h);
+	CK(cudaMalloc((void **)&h->d_bins, std::max<uint64_t>(1, h->n_bins) * 8));
+	CK(cudaMalloc((void **)&h->d_stA, std::max<uint64_t>(1, h->n_tiles) * 8));
+	CK(cudaMalloc((void **)&h->d_stB, std::max<uint64_t>(1, h->n_tiles) * 8));
+	CK(cudaMalloc((void **)&h->d_rec_base, (h->seg.size() + 2) * 8));
+	CK(cudaMalloc((void **)&h->d_carry, NGS_CARRY_MAX));
+	CK(cudaMalloc((void **)&h->d_st, sizeof(ngs_dev_state)));
+	CK(cudaHostAlloc((void **)&h->h_st, sizeof(ngs_dev_state), cudaHostAllocDefault));
+	h->stage_cap = cfg->staging_bytes ? (size_t)cfg->staging_bytes : (size_t)256 << 20;
+	h->shift = 0;
+	const char *env = getenv("NGSCOV_SUBCHUNK");
+	if (env && atoi(env) >= 64) { int v = atoi(env), s = 6; while ((1 << (s + 1)) <= v) ++s; h->shift = s; }
+	return ngscov_reset(h);
+}
+
+extern "C" void ngscov_destroy(ngscov_t *h)
+{
+	if (!h) return;
+	cudaSetDevice(h->device);
+	cudaDeviceSynchronize();
+	void *dev[] = { h->d_seg, h->d_ctg2seg, h->d_tile2seg, h->d_ref_len, h->d_win_base, h->d_diff, h->d_bins, h->d_names,
+	                h->d_name_off, h->d_wighdr, h->d_wighdr_off, h->d_chunk[0], h->d_chunk[1], h->d_carry, h->d_entry, h->d_exit,
+	                h->d_bmax, h->d_st, h->d_run_start, h->d_run_end, h->d_run_depth, h->d_rec_base, h->d_stA, h->d_stB,
+	                h->d_fmt_status, h->d_text[0], h->d_text[1], h->d_text[2], h->d_text[3] };
+	for (void *p : dev) if (p) cudaFree(p);
+	for (int i = 0; i < 2; ++i) if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
+	for (int i = 0; i < 4; ++i) if (h->h_text[i]) cudaFreeHost(h->h_text[i]);
+	if (h->h_st) cudaFreeHost(h->h_st);
+	if (h->s_main) cudaStreamDestroy(h->s_main);
+	if (h->s_copy) cudaStreamDestroy(h->s_copy);
+	for (int i = 0; i < 2; ++i) if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+	if (h->ev_verified) cudaEventDestroy(h->ev_verified);
+	if (h->ev_finalized) cudaEventDestroy(h->ev_finalized);
+	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+	for (cudaEvent_t e : h->ev_ing) cudaEventDestroy(e);
+	for (cudaEvent_t e : h->ev_cp) cudaEventDestroy(e);
+	delete h;
+}
+
+extern "C" int ngscov_reset(ngscov_t *h)
+{
+	if (!h) return NGSCOV_EINVAL;
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->s_main)); CK(cudaStreamSynchronize(h->s_copy));
+	if (h->diff_dirty) {            /* pushes were made but the scan (which re-zeroes) never ran */
+		tic(h);
+		CK(cudaMemsetAsync(h->d_diff, 0, h->n_elems * sizeof(int), h->s_main));
+		h->stats.ms_zero = toc(h);
+		h->diff_dirty = false;
+	}
+	const float keep_zero = h->stats.ms_zero;
+	memset(&h->stats, 0, sizeof h->stats);
+	h->stats.ms_zero = keep_zero;
+	CK(cudaMemsetAsync(h->d_st, 0, sizeof(ngs_dev_state), h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	h->pending = false; h->last_pushed = false; h->last_flags = 0; h->sticky_err = 0;
+	h->runs_done = false; h->formatted = false;
+	h->drop_idx = ~0ull; h->mod_idx = ~0ull; h->mod_end = 0;
+	memset(&h->halo, 0, sizeof h->halo); h->halo.first.contig = h->halo.last.contig = -1;
+	for (int i = 0; i < 4; ++i) { h->text_len[i] = 0; h->text_ready[i] = false; h->h_text_valid[i] = false; }
+	h->stage_busy[0] = h->stage_busy[1] = false;
+	h->n_ing = 0; h->n_cp = 0;
+	return 0;
+}
+
+extern "C" int ngscov_sync(ngscov_t *h)
+{
+	if (!h) return NGSCOV_EINVAL;
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->s_copy)); CK(cudaStreamSynchronize(h->s_main));
+	return 0;
+}
+
+extern "C" void *ngscov_stream(ngscov_t *h) { return h ? (void *)h->s_main : nullptr; }
+
+extern "C" int ngscov_staging(ngscov_t *h, int idx, void **pinned, size_t *cap)
+{
+	if (!h || idx < 0 || idx > 1 || !pinned || !cap) return NGSCOV_EINVAL;
+	CK(cudaSetDevice(h->device));
+	if (!h->h_stage[idx]) {
+		CK(cudaHostAlloc((void **)&h->h_stage[idx], h->stage_cap, cudaHostAllocDefault));
+		CK(cudaMalloc((void **)&h->d_chunk[idx], NGS_HEADROOM + h->stage_cap + 256));
+	}
+	*pinned = h->h_stage[idx]; *cap = h->stage_cap;
+	return 0;
+}
+
+extern "C" int ngscov_staging_wait(ngscov_t *h, int idx)
+{
+	if (!h || idx < 0 || idx > 1) return NGSCOV_EINVAL;
+	if (h->stage_busy[idx]) { CK(cudaEventSynchronize(h->ev_h2d[idx])); h->stage_busy[idx] = false; }
+	return 0;
+}
+
+static int ensure_sub(ngscov *h, int64_t n_sub)
+{
+	if ((size_t)n_sub > h->sub_cap) {
+		CK(cudaStreamSynchronize(h->s_main));
+		if (h->d_entry) cudaFree(h->d_entry);
+		if (h->d_exit) cudaFree(h->d_exit);
+		h->d_entry = h->d_exit = nullptr; h->sub_cap = 0;
+		const size_t cap = (size_t)n_sub + (size_t)n_sub / 8 + 1024;
+		CK(cudaMalloc((void **)&h->d_entry, cap * 8));
+		CK(cudaMalloc((void **)&h->d_exit, cap * 8));
+		h->sub_cap = cap;
+	}
+	const size_t nb = ((size_t)n_sub + NGS_VER_PER_BLOCK - 1) / NGS_VER_PER_BLOCK;
+	if (nb > h->bmax_cap) {
+		CK(cudaStreamSynchronize(h->s_main));
+		if (h->d_bmax) cudaFree(h->d_bmax);
+		h->d_bmax = nullptr; h->bmax_cap = 0;
+		CK(cudaMalloc((void **)&h->d_bmax, (nb + 1024) * 8));
+		h->bmax_cap = nb + 1024;
+	}
+	return 0;
+}
+
+static IngestArgs make_ingest_args(ngscov *h, const uint8_t *base, int64_t n, int64_t n_sub, bool from_state, long long fixed0)
+{
+	IngestArgs A;
+	A.base = base; A.n = n; A.shift = h->shift; A.n_sub = n_sub; A.entry = h->d_entry; A.exit = h->d_exit;
+	A.cfg.n_ref = h->n_ref; A.cfg.flag_mask = h->cfg.mode == NGSCOV_MODE_DEPTH ? 0x704u : 0x4u;
+	A.cfg.ctg2seg = h->d_ctg2seg; A.cfg.seg = h->d_seg;
+	A.ref_len = h->d_ref_len; A.diff = h->d_diff; A.st = h->d_st;
+	A.fixed_entry0 = fixed0; A.entry0_from_state = from_state ? 1 : 0;
+	return A;
+}
+
+static int launch_verify(ngscov *h)
+{
+	const int64_t n_sub = h->p_nsub;
+	const unsigned nb = (unsigned)((n_sub + NGS_VER_PER_BLOCK - 1) / NGS_VER_PER_BLOCK);
+	k_verify_blockmax<<<nb, 256, 0, h->s_main>>>(h->d_exit, n_sub, h->d_bmax);
+	k_verify_scan<<<1, 1024, 0, h->s_main>>>(h->d_bmax, nb, h->d_st, h->p_fixed0, h->p_from_state ? 1 : 0);
+	k_verify_check<<<nb, 256, 0, h->s_main>>>(h->d_entry, h->d_exit, n_sub, h->d_bmax, h->shift, h->p_n, h->d_st);
+	h->stats.launches += 3;
+	CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaEventRecord(h->ev_verified, h->s_main));
+	CK(cudaGetLastError());
+	return 0;
+}
+
+/* wait for the verification of the chunk in flight; repair mis-speculated sub-chunks; fix the carry */
+static int resolve_pending(ngscov *h)
+{
+	if (!h->pending) return 0;
+	for (int iter = 0; ; ++iter) {
+		CK(cudaEventSynchronize(h->ev_verified));
+		if (h->h_st->n_bad == 0) break;
+		const unsigned long long key = h->h_st->first_bad_key;
+		if ((key & 1) || iter > 100000) { h->sticky_err = NGSCOV_EFORMAT; h->pending = false; return NGSCOV_EFORMAT; }
+		IngestArgs A = make_ingest_args(h, h->p_base, h->p_n, h->p_nsub, h->p_from_state, h->p_fixed0);
+		k_repair<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
+		h->stats.launches += 1;
+		int r = launch_verify(h);
+		if (r) return r;
+	}
+	k_finalize_chunk<<<1, 256, 0, h->s_main>>>(h->p_base, h->p_n, h->d_st, h->d_carry);
+	h->stats.launches += 1;
+	CK(cudaEventRecord(h->ev_finalized, h->s_main));
+	CK(cudaGetLastError());
+	h->pending = false;
+	return 0;
+}
+
+static int pick_shift(ngscov *h, int32_t first_block_size)
+{
+	if (h->shift) return 0;
+	int64_t rec = (int64_t)first_block_size + 4;
+	if (rec < 36) rec = 36;
+	if (rec > 4096) rec = 4096;
+	int64_t want = rec * 10; int s = 9;                       /* ~10 records per sub-chunk, 512 B .. 32 KiB */
+	while (((int64_t)1 << s) < want && s < 15) ++s;
+	h->shift = s;
+	return 0;
+}
+
+static int submit_chunk(ngscov *h, const uint8_t *base, int64_t n, bool from_state, long long fixed0)
+{
+	const int64_t n_sub = (n + ((int64_t)1 << h->shift) - 1) >> h->shift;
+	int r = ensure_sub(h, n_sub);
+	if (r) return r;
+	IngestArgs A = make_ingest_args(h, base, n, n_sub, from_state, fixed0);
+	const unsigned nb = (unsigned)((n_sub + 255) / 256);
+	CK(cudaEventRecord(next_event(h->ev_ing, h->n_ing), h->s_main));
+	k_ingest_walk<<<nb, 256, 0, h->s_main>>>(A);
+	h->stats.launches += 1;
+	CK(cudaGetLastError());
+	h->pending = true; h->p_base = base; h->p_n = n; h->p_nsub = n_sub; h->p_from_state = from_state; h->p_fixed0 = fixed0;
+	h->diff_dirty = true;
+	r = launch_verify(h);
+	CK(cudaEventRecord(next_event(h->ev_ing, h->n_ing), h->s_main));
+	return r;
+}
+
+extern "C" int ngscov_push(ngscov_t *h, int idx, size_t nbytes, int flags)
+{
+	if (!h || idx < 0 || idx > 1 || !h->h_stage[idx] || nbytes > h->stage_cap) return NGSCOV_EINVAL;
+	if (h->runs_done || h->last_pushed) return NGSCOV_ESTATE;
+	if (h->sticky_err) return h->sticky_err;
+	CK(cudaSetDevice(h->device));
+	int r = resolve_pending(h);
+	if (r) return r;
+	if (flags & NGSCOV_PUSH_LAST) { h->last_pushed = true; h->last_flags = flags; }
+	h->stats.stream_bytes += nbytes;
+	if (nbytes == 0) return 0;
+	if (!h->shift) pick_shift(h, *(const int32_t *)h->h_stage[idx]);
+	uint8_t *data = h->d_chunk[idx] + NGS_HEADROOM;
+	CK(cudaStreamWaitEvent(h->s_copy, h->ev_finalized, 0));
+	CK(cudaEventRecord(next_event(h->ev_cp, h->n_cp), h->s_copy));
+	CK(cudaMemcpyAsync(data, h->h_stage[idx], nbytes, cudaMemcpyHostToDevice, h->s_copy));
+	CK(cudaEventRecord(next_event(h->ev_cp, h->n_cp), h->s_copy));
+	CK(cudaEventRecord(h->ev_h2d[idx], h->s_copy));
+	h->stage_busy[idx] = true;
+	CK(cudaStreamWaitEvent(h->s_main, h->ev_h2d[idx], 0));
+	k_place_carry<<<1, 256, 0, h->s_main>>>(data, h->d_st, h->d_carry);
+	h->stats.launches += 1;
+	return submit_chunk(h, data, (int64_t)nbytes, true, 0);
+}
+
+extern "C" int ngscov_push_device(ngscov_t *h, const void *dev_records, size_t nbytes, int flags)
+{
+	if (!h || (!dev_records && nbytes)) return NGSCOV_EINVAL;
+	if (h->runs_done || h->last_pushed) return NGSCOV_ESTATE;
+	if (h->sticky_err) return h->sticky_err;
+	CK(cudaSetDevice(h->device));
+	int r = resolve_pending(h);
+	if (r) return r;
+	/* whole records only: the previous push must have ended on a record boundary */
+	if (h->stats.stream_bytes) {
+		CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
+		CK(cudaStreamSynchronize(h->s_main));
+		if (h->h_st->entry_next != 0 || h->h_st->carry_len != 0) { h->sticky_err = NGSCOV_EFORMAT; return NGSCOV_EFORMAT; }
+	}
+	if (flags & NGSCOV_PUSH_LAST) { h->last_pushed = true; h->last_flags = flags; }
+	h->stats.stream_bytes += nbytes;
+	if (nbytes == 0) return 0;
+	if (!h->shift) {
+		int32_t bs = 0;
+		CK(cudaMemcpy(&bs, dev_records, 4, cudaMemcpyDeviceToHost));
+		pick_shift(h, bs);
+	}
+	return submit_chunk(h, (const uint8_t *)dev_records, (int64_t)nbytes, false, 0);
+}
+
+template <class T>
+static int ensure_buf(ngscov *h, T **p, size_t *cap, size_t need)
+{
+	if (need <= *cap && *p) return 0;
+	CK(cudaStreamSynchronize(h->s_main));
+	if (*p) cudaFree(*p);
+	*p = nullptr; *cap = 0;
+	const size_t want = need + need / 16 + 1024;
+	CK(cudaMalloc((void **)p, want * sizeof(T)));
+	*cap = want;
+	return 0;
+}
+
+extern "C" int ngscov_finish_runs(ngscov_t *h)
+{
+	if (!h) return NGSCOV_EINVAL;
+	if (h->runs_done) return NGSCOV_ESTATE;
+	if (h->sticky_err) return h->sticky_err;
+	CK(cudaSetDevice(h->device));
+	int r = resolve_pending(h);
+	if (r) return r;
+	CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	CK(cudaStreamSynchronize(h->s_copy));
+	h->stats.ms_ingest += sum_events(h->ev_ing, h->n_ing);
+	h->stats.ms_h2d += sum_events(h->ev_cp, h->n_cp);
+	const ngs_dev_state st = *h->h_st;
+	h->stats.records = st.records; h->stats.kept = st.kept; h->stats.m_ops = st.m_ops; h->stats.cigar_words = st.cigar_words;
+	h->stats.spec_subchunks = st.spec_walks; h->stats.spec_repaired = st.spec_repaired;
+	if (st.flags & NGS_FLAG_EFORMAT) return h->sticky_err = NGSCOV_EFORMAT;
+	if ((st.entry_next != 0 || st.carry_len != 0) && !(h->last_flags & NGSCOV_PUSH_TRUNCATED_OK)) return h->sticky_err = NGSCOV_EFORMAT;
+	if (st.flags & NGS_FLAG_ERANGE) return h->sticky_err = NGSCOV_ERANGE;
+
+	/* boundary records: at most two per accumulated M interval, never more than tracked positions */
+	size_t need = (size_t)std::min<unsigned long long>(2ull * st.m_ops, h->n_elems) + 16;
+	{
+		size_t cap0 = h->run_cap, cap1 = h->run_cap, cap2 = h->run_cap;
+		if ((r = ensure_buf(h, &h->d_run_start, &cap0, need))) return r;
+		if ((r = ensure_buf(h, &h->d_run_end, &cap1, need))) return r;
+		if ((r = ensure_buf(h, &h->d_run_depth, &cap2, need))) return r;
+		h->run_cap = std::min(cap0, std::min(cap1, cap2));
+	}
+	tic(h);
+	CK(cudaMemsetAsync(h->d_stA, 0, h->n_tiles * 8, h->s_main));
+	CK(cudaMemsetAsync(h->d_stB, 0, h->n_tiles * 8, h->s_main));
+	CK(cudaMemsetAsync(h->d_bins, 0, h->n_bins * 8, h->s_main));
+	{
+		ngs_dev_state init = st;
+		init.scan_ticket = 0; init.n_boundaries = 0; init.n_runs = 0; init.first_run = ~0ull; init.last_run = 0;
+		init.max_depth = 0; init.min_depth = 0;
+		*h->h_st = init;
+		CK(cudaMemcpyAsync(h->d_st, h->h_st, sizeof(ngs_dev_state), cudaMemcpyHostToDevice, h->s_main));
+	}
+	if (h->n_tiles) {
+		ScanArgs A;
+		A.diff = h->d_diff; A.n_tiles = h->n_tiles; A.tile2seg = h->d_tile2seg; A.seg = h->d_seg;
+		A.stA = h->d_stA; A.stB = h->d_stB;
+		A.run_start = h->d_run_start; A.run_end = h->d_run_end; A.run_depth = h->d_run_depth; A.run_cap = h->run_cap;
+		A.rec_base = h->d_rec_base; A.n_seg = (uint32_t)h->seg.size();
+		A.bins = h->d_bins; A.window = h->cfg.window; A.variant = h->cfg.mode == NGSCOV_MODE_WIG ? 1 : 0;
+		A.rezero = 1; A.st = h->d_st;
+		k_scan_runs<<<(unsigned)h->n_tiles, NGS_SCAN_THREADS, 0, h->s_main>>>(A);
+		h->stats.launches += 1;
+		CK(cudaGetLastError());
+	}
+	h->diff_dirty = false;
+	CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
+	h->h_rec_base.assign(h->seg.size() + 1, 0);
+	if (h->n_tiles) CK(cudaMemcpyAsync(h->h_rec_base.data(), h->d_rec_base, (h->seg.size() + 1) * 8, cudaMemcpyDeviceToHost, h->s_main));
+	h->stats.ms_scan += toc(h);
+	const ngs_dev_state s2 = *h->h_st;
+	h->stats.boundaries = s2.n_boundaries; h->stats.runs = s2.n_runs; h->stats.positions = h->n_elems;
+	if (s2.n_boundaries > h->run_cap) return h->sticky_err = NGSCOV_ENOMEM;
+	/* halo */
+	h->halo.n_runs = s2.n_runs;
+	if (s2.n_runs) {
+		const unsigned long long idx[2] = { s2.first_run, s2.last_run };
+		ngscov_run *dst[2] = { &h->halo.first, &h->halo.last };
+		for (int k = 0; k < 2; ++k) {
+			CK(cudaMemcpy(&dst[k]->start, h->d_run_start + idx[k], 4, cudaMemcpyDeviceToHost));
+			CK(cudaMemcpy(&dst[k]->end, h->d_run_end + idx[k], 4, cudaMemcpyDeviceToHost));
+			CK(cudaMemcpy(&dst[k]->depth, h->d_run_depth + idx[k], 4, cudaMemcpyDeviceToHost));
+			size_t s = std::upper_bound(h->h_rec_base.begin(), h->h_rec_base.begin() + h->seg.size(), idx[k]) - h->h_rec_base.begin() - 1;
+			dst[k]->contig = (int32_t)h->seg[s].contig;
+		}
+	}
+	h->runs_done = true;
+	return 0;
+}
+
+extern "C" int ngscov_halo_get(ngscov_t *h, ngscov_halo *halo)
+{
+	if (!h || !halo) return NGSCOV_EINVAL;
+	if (!h->runs_done) return NGSCOV_ESTATE;
+	*halo = h->halo;
+	return 0;
+}
+
+extern "C" int ngscov_halo_put(ngscov_t *h, int drop_first, uint32_t new_last_end)
+{
+	if (!h) return NGSCOV_EINVAL;
+	if (!h->runs_done || h->formatted) return NGSCOV_ESTATE;
+	if (h->halo.n_runs == 0) return drop_first || new_last_end ? NGSCOV_EINVAL : 0;
+	h->drop_idx = drop_first ? h->h_st->first_run : ~0ull;
+	if (new_last_end) { h->mod_idx = h->h_st->last_run; h->mod_end = new_last_end; } else h->mod_idx = ~0ull;
+	return 0;
+}
+
+extern "C" int ngscov_bins_count(ngscov_t *h, uint64_t *n)
+{
+	if (!h || !n) return NGSCOV_EINVAL;
+	*n = h->n_bins;
+	return 0;
+}
+
+extern "C" int ngscov_bins_get(ngscov_t *h, uint64_t *bins, uint64_t n)
+{
+	if (!h || !bins || n != h->n_bins) return NGSCOV_EINVAL;
+	if (!h->runs_done) return NGSCOV_ESTATE;
+	CK(cudaSetDevice(h->device));
+	CK(cudaMemcpyAsync(bins, h->d_bins, n * 8, cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	return 0;
+}
+
+extern "C" int ngscov_bins_put(ngscov_t *h, const uint64_t *bins, uint64_t n)
+{
+	if (!h || !bins || n != h->n_bins) return NGSCOV_EINVAL;
+	if (!h->runs_done || h->formatted) return NGSCOV_ESTATE;
+	CK(cudaSetDevice(h->device));
+	CK(cudaMemcpyAsync(h->d_bins, bins, n * 8, cudaMemcpyHostToDevice, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	return 0;
+}
+
+struct HostBinAdd { uint64_t *bins; int sign; __host__ __device__ void operator()(uint32_t k, int64_t v) const { bins[k] += (uint64_t)(sign * v); } };
+
+extern "C" int ngscov_bins_apply_run(ngscov_t *h, const ngscov_run *run, int sign, uint64_t *bins, uint64_t n)
+{
+	if (!h || !run || !bins || n != h->n_bins || run->contig < 0 || run->contig >= h->n_ref) return NGSCOV_EINVAL;
+	const uint32_t L = h->ref_len[run->contig];
+	HostBinAdd add = { bins + h->win_base[run->contig], sign < 0 ? -1 : 1 };
+	ngs_bin_run(h->cfg.mode == NGSCOV_MODE_WIG ? 1 : 0, run->start, run->end, (int64_t)run->depth, h->cfg.window, L, L / h->cfg.window + 1, add);
+	return 0;
+}
+
+template <class Producer>
+static int run_format(ngscov *h, int which, unsigned long long n_items, const Producer &P, uint32_t max_line, size_t bound)
+{
+	int r;
+	size_t cap = h->d_text_cap[which];
+	if ((r = ensure_buf(h, &h->d_text[which], &cap, bound + 64))) return r;
+	h->d_text_cap[which] = cap;
+	int ipt = 4;
+	const uint32_t smem_max = 96 * 1024;
+	while (ipt > 1 && (size_t)NGS_FMT_THREADS * ipt * max_line + 32 > smem_max) ipt >>= 1;
+	uint32_t stage = (uint32_t)std::min<size_t>((size_t)NGS_FMT_THREADS * ipt * max_line + 32, smem_max);
+	const unsigned long long per = (unsigned long long)NGS_FMT_THREADS * ipt;
+	const unsigned long long n_tiles = (n_items + per - 1) / per;
+	h->text_len[which] = 0; h->text_ready[which] = true; h->h_text_valid[which] = false;
+	if (n_tiles == 0) return 0;
+	size_t scap = h->fmt_status_cap;
+	if ((r = ensure_buf(h, &h->d_fmt_status, &scap, (size_t)n_tiles))) return r;
+	h->fmt_status_cap = scap;
+	CK(cudaMemsetAsync(h->d_fmt_status, 0, n_tiles * 8, h->s_main));
+	CK(cudaMemsetAsync(&h->d_st->fmt_ticket, 0, 16, h->s_main));      /* fmt_ticket + fmt_bytes */
+	FmtArgs A;
+	A.n_items = n_items; A.n_tiles = n_tiles; A.status = h->d_fmt_status; A.out = h->d_text[which];
+	A.out_cap = h->d_text_cap[which]; A.st = h->d_st; A.stage_bytes = stage;
+	if (ipt == 4) {
+		CK(cudaFuncSetAttribute(k_format_lines<Producer, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+		k_format_lines<Producer, 4><<<(unsigned)n_tiles, NGS_FMT_THREADS, stage, h->s_main>>>(A, P);
+	} else if (ipt == 2) {
+		CK(cudaFuncSetAttribute(k_format_lines<Producer, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+		k_format_lines<Producer, 2><<<(unsigned)n_tiles, NGS_FMT_THREADS, stage, h->s_main>>>(A, P);
+	} else {
+		CK(cudaFuncSetAttribute(k_format_lines<Producer, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+		k_format_lines<Producer, 1><<<(unsigned)n_tiles, NGS_FMT_THREADS, stage, h->s_main>>>(A, P);
+	}
+	h->stats.launches += 1;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	if (h->h_st->fmt_bytes > h->d_text_cap[which]) return NGSCOV_ENOMEM;
+	h->text_len[which] = (size_t)h->h_st->fmt_bytes;
+	h->stats.out_bytes[which] = h->text_len[which];
+	return 0;
+}
+
+static uint32_t dig(uint64_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n; } return n; }
+
+extern "C" int ngscov_format(ngscov_t *h, uint32_t which_mask)
+{
+	if (!h) return NGSCOV_EINVAL;
+	if (!h->runs_done) return NGSCOV_ESTATE;
+	CK(cudaSetDevice(h->device));
+	int r = 0;
+	tic(h);
+	NameTable nt = { h->d_names, h->d_name_off };
+	const ngs_dev_state st = *h->h_st;
+	if (which_mask & (1u << NGSCOV_OUT_BEDGRAPH)) {
+		BedProducer P;
+		P.run_start = h->d_run_start; P.run_end = h->d_run_end; P.run_depth = h->d_run_depth;
+		P.rec_base = h->d_rec_base; P.seg = h->d_seg; P.n_seg = (uint32_t)h->seg.size(); P.nt = nt;
+		P.drop_idx = h->drop_idx; P.mod_idx = h->mod_idx; P.mod_end = h->mod_end;
+		const uint32_t dd = std::max(dig((uint64_t)std::max(st.max_depth, 0)), 1 + dig((uint64_t)(-(int64_t)std::min(st.min_depth, 0))));
+		size_t bound = 0;
+		for (size_t s = 0; s < h->seg.size(); ++s) {
+			const unsigned long long k = h->h_rec_base[s + 1] - h->h_rec_base[s];
+			const uint32_t pd = dig(std::max<uint64_t>(h->seg[s].lim, h->mod_end));
+			bound += (size_t)k * (h->ref_name[h->seg[s].contig].size() + 1 + 2 * pd + 2 + dd + 1);
+		}
+		r = run_format(h, NGSCOV_OUT_BEDGRAPH, st.n_boundaries, P, h->max_name_tab + 10 + 1 + 10 + 1 + 11 + 1, bound);
+		if (r) return r;
+	}
+	if (which_mask & (1u << NGSCOV_OUT_DEPTH)) {
+		DepthProducer P;
+		P.bins = h->d_bins; P.win_base = h->d_win_base; P.ref_len = h->d_ref_len; P.n_ref = (uint32_t)h->n_ref;
+		P.window = h->cfg.window; P.nt = nt;
+		const size_t bound = (size_t)h->n_bins * (h->max_name_tab + 10 + 1 + 10 + 1 + 24);
+		r = run_format(h, NGSCOV_OUT_DEPTH, h->n_bins, P, h->max_name_tab + 10 + 1 + 10 + 1 + 24, bound);
+		if (r) return r;
+	}
+	if (which_mask & (1u << NGSCOV_OUT_WIG)) {
+		WigProducer P;
+		P.bins = h->d_bins; P.win_base = h->d_win_base; P.n_ref = (uint32_t)h->n_ref; P.window = h->cfg.window;
+		P.hdr = h->d_wighdr; P.hdr_off = h->d_wighdr_off;
+		const uint32_t ml = std::max<uint32_t>(h->max_wighdr, 10 + 1 + 24);
+		size_t bound = (size_t)h->n_bins * (10 + 1 + 24);
+		for (int i = 0; i < h->n_ref; ++i) bound += h->ref_name[i].size() + 48;
+		r = run_format(h, NGSCOV_OUT_WIG, h->n_bins + (unsigned long long)h->n_ref, P, ml, bound);
+		if (r) return r;
+	}
+	if (which_mask & (1u << NGSCOV_OUT_CHROMSIZE)) {
+		/* static header information only (reference bam2depth.c:337): no computed data, kept on the host */
+		h->text_len[NGSCOV_OUT_CHROMSIZE] = h->chromsize.size();
+		h->text_ready[NGSCOV_OUT_CHROMSIZE] = true;
+		h->stats.out_bytes[NGSCOV_OUT_CHROMSIZE] = h->chromsize.size();
+	}
+	h->stats.ms_format += toc(h);
+	h->formatted = true;
+	return 0;
+}
+
+extern "C" int ngscov_finish(ngscov_t *h)
+{
+	if (!h) return NGSCOV_EINVAL;
+	int r = ngscov_finish_runs(h);
+	if (r) return r;
+	uint32_t mask;
+	if (h->cfg.mode == NGSCOV_MODE_DEPTH) {
+		mask = (1u << NGSCOV_OUT_BEDGRAPH) | (1u << NGSCOV_OUT_DEPTH);
+		if (h->cfg.emit_wig) mask |= (1u << NGSCOV_OUT_WIG) | (1u << NGSCOV_OUT_CHROMSIZE);
+	} else mask = (1u << NGSCOV_OUT_WIG) | (1u << NGSCOV_OUT_CHROMSIZE);
+	return ngscov_format(h, mask);
+}
+
+extern "C" int ngscov_output_device(ngscov_t *h, int which, const void **dev_buf, size_t *len)
+{
+	if (!h || which < 0 || which > 2 || !dev_buf || !len) return NGSCOV_EINVAL;
+	if (!h->text_ready[which]) return NGSCOV_ESTATE;
+	*dev_buf = h->d_text[which]; *len = h->text_len[which];
+	return 0;
+}
+
+extern "C" int ngscov_output(ngscov_t *h, int which, const char **buf, size_t *len)
+{
+	if (!h || which < 0 || which > 3 || !buf || !len) return NGSCOV_EINVAL;
+	if (!h->text_ready[which]) return NGSCOV_ESTATE;
+	if (which == NGSCOV_OUT_CHROMSIZE) { *buf = h->chromsize.data(); *len = h->chromsize.size(); return 0; }
+	CK(cudaSetDevice(h->device));
+	if (!h->h_text_valid[which]) {
+		const size_t n = h->text_len[which];
+		if (n > h->h_text_cap[which] || !h->h_text[which]) {
+			if (h->h_text[which]) cudaFreeHost(h->h_text[which]);
+			h->h_text[which] = nullptr; h->h_text_cap[which] = 0;
+			const size_t want = n + n / 16 + 4096;
+			CK(cudaHostAlloc((void **)&h->h_text[which], want, cudaHostAllocDefault));
+			h->h_text_cap[which] = want;
+		}
+		tic(h);
+		if (n) CK(cudaMemcpyAsync(h->h_text[which], h->d_text[which], n, cudaMemcpyDeviceToHost, h->s_main));
+		h->stats.ms_d2h += toc(h);
+		h->h_text_valid[which] = true;
+	}
+	*buf = h->h_text[which]; *len = h->text_len[which];
+	return 0;
+}
+
+extern "C" int ngscov_runs_get(ngscov_t *h, ngscov_run *runs, uint64_t cap, uint64_t *n)
+{
+	if (!h || !n) return NGSCOV_EINVAL;
+	if (!h->runs_done) return NGSCOV_ESTATE;
+	CK(cudaSetDevice(h->device));
+	const uint64_t nb = h->stats.boundaries;
+	*n = h->stats.runs;
+	if (!runs || cap == 0 || nb == 0) return 0;
+	std::vector<uint32_t> s(nb), e(nb); std::vector<int> d(nb);
+	CK(cudaMemcpy(s.data(), h->d_run_start, nb * 4, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(e.data(), h->d_run_end, nb * 4, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(d.data(), h->d_run_depth, nb * 4, cudaMemcpyDeviceToHost));
+	uint64_t k = 0; size_t sg = 0;
+	for (uint64_t i = 0; i < nb && k < cap; ++i) {
+		while (sg + 1 < h->seg.size() && h->h_rec_base[sg + 1] <= i) ++sg;
+		if (d[i] == 0) continue;
+		runs[k].contig = (int32_t)h->seg[sg].contig; runs[k].start = s[i]; runs[k].end = e[i]; runs[k].depth = d[i];
+		++k;
+	}
+	return 0;
+}
+
+extern "C" int ngscov_stats(ngscov_t *h, ngscov_stats_t *st)
+{
+	if (!h || !st) return NGSCOV_EINVAL;
+	*st = h->stats;
+	return 0;
+}

@@ -1,0 +1,285 @@
+/* csrc/ngscov_hd.h -- record-level logic shared by every kernel of libngscov_cuda.
+ *
+ * Everything here is `NGS_HD` (__host__ __device__) and free of CUDA intrinsics so that the exact code
+ * the kernels run can also be compiled with g++ and unit-tested on a CPU-only machine
+ * (tests/hd_check.cpp).  It is NOT a CPU fallback: the library itself only ever calls it from device
+ * code, plus ngscov_bins_apply_run for the few boundary runs of the shard stitcher.
+ *
+ * Semantics restated (reference file:line):
+ *   record layout            samtools-0.1.19 bam.h:178-187 (bam1_core_t), bam.c:191-223 (bam_read1)
+ *   flag filter, CIGAR walk  bam2depth.c:86-110 (mask 0x704), bam2wig.c:84-109 (mask 0x4)
+ *   28-bit position keys     hashtbl.c:243-259 (int2char / char2int)
+ *   window bins, variant A   bam2depth.c:132-176 ; variant B bam2wig.c:131-175
+ *   "%.2f" of bins/window    bam2depth.c:243,253 (glibc printf, round-half-even on the exact double)
+ */
+#ifndef NGSCOV_HD_H
+#define NGSCOV_HD_H
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NGS_HD __host__ __device__ __forceinline__
+#else
+#define NGS_HD static inline
+#endif
+
+#define NGS_POS_MASK   0x0FFFFFFFu        /* 4 x 7 bit key of the reference */
+#define NGS_MAX_BS     (1u << 26)         /* block_size plausibility bound used only by speculation */
+#define NGS_CARRY_MAX  (512u * 1024u)     /* > 36 + 255 + 4*65535: any header+CIGAR fits */
+
+/* exit codes of a sub-chunk walk, stored in the per-sub-chunk exit slot */
+#define NGS_NONE       (-(1ll << 62))                   /* entry: no record start found / none expected */
+#define NGS_EXIT_INF   (1ll << 60)                  /* exit >= INF: chain ended inside this chunk */
+#define NGS_EXIT_PARTIAL(o) (NGS_EXIT_INF + (o) + (1ll << 40))   /* header of record at o is cut by chunk end */
+#define NGS_EXIT_INVALID (-(1ll << 62) - 1)                  /* a walked record failed structural validation */
+
+typedef struct {
+	int32_t  block_size;
+	int32_t  ref_id;
+	int32_t  pos;
+	uint32_t l_qname;      /* byte  */
+	uint32_t n_cigar;      /* u16   */
+	uint32_t flag;         /* u16   */
+	int32_t  l_seq;
+	int32_t  next_ref_id;
+	int32_t  next_pos;
+} ngs_hdr;
+
+/* Per-segment geometry.  A segment is the tracked part of one contig on this shard. */
+typedef struct {
+	uint32_t contig;       /* index into the header's contig list */
+	uint32_t clip_lo;      /* first tracked position (contig coordinates) */
+	uint32_t lim;          /* last index that may receive a delta (the -1 of an interval ending here) */
+	uint32_t hard_end;     /* 1: lim is contig end + pad (going beyond is ERANGE); 0: lim is a shard cut (clip) */
+	uint64_t base;         /* element offset of clip_lo in the difference array */
+	uint64_t tile0;        /* first scan tile of the segment */
+	uint64_t bins0;        /* first bin of the contig in the concatenated bins array */
+	uint32_t ref_len;      /* contig length */
+	uint32_t n_win;        /* ref_len / window + 1 */
+} ngs_seg;
+
+/* structural validation applied to EVERY walked record (a real chain never fails it on a well-formed
+ * BAM; a mis-speculated chain almost always does, quickly) */
+NGS_HD int ngs_hdr_valid(const ngs_hdr &h, int32_t n_ref)
+{
+	if (h.block_size < 32) return 0;
+	if (h.ref_id < -1 || h.ref_id >= n_ref) return 0;
+	if (h.l_seq < 0) return 0;
+	uint64_t need = 32ull + h.l_qname + 4ull * h.n_cigar + ((uint64_t)h.l_seq + 1) / 2 + (uint64_t)h.l_seq;
+	return need <= (uint64_t)(uint32_t)h.block_size;
+}
+
+/* stricter test used only to pick a speculative entry point */
+NGS_HD int ngs_hdr_plausible(const ngs_hdr &h, int32_t n_ref, const uint32_t *ref_len)
+{
+	if (!ngs_hdr_valid(h, n_ref)) return 0;
+	if ((uint32_t)h.block_size > NGS_MAX_BS) return 0;
+	if (h.l_qname < 1) return 0;
+	if (h.pos < -1) return 0;
+	if (h.ref_id >= 0 && (uint32_t)h.pos != 0xFFFFFFFFu && (uint32_t)h.pos > ref_len[h.ref_id]) return 0;
+	if (h.next_ref_id < -1 || h.next_ref_id >= n_ref) return 0;
+	if (h.next_pos < -1) return 0;
+	return 1;
+}
+
+/* ---- window bins ---------------------------------------------------------------------------------
+ * Adds the contribution of run [s,e) with depth d to bins[0..n_win) through add(k, value).
+ * variant 0 = bam2depth (half-open windows): exact sum of depth over the bases of each window.
+ * variant 1 = bam2wig  (inclusive window ends): restates the reference loop, off-by-one terms and all,
+ *             starting at the first window whose end is >= s (the reference's persistent cursor only
+ *             skips windows that cannot contribute). */
+template <class Add>
+NGS_HD void ngs_bin_run(int variant, uint32_t s, uint32_t e, int64_t d, uint32_t W, uint32_t L, uint32_t n_win, Add &add)
+{
+	if (e <= s) return;
+	uint64_t k = s / W;
+	if (variant == 0) {
+		for (; k < n_win; ++k) {
+			uint64_t ws = k * (uint64_t)W, we = ws + W;
+			if (we > L) we = L;
+			if (e <= ws) break;
+			uint64_t lo = s > ws ? s : ws, hi = e < we ? e : we;
+			if (hi > lo) add((uint32_t)k, (int64_t)(hi - lo) * d);
+			if (e <= we) break;
+		}
+	} else {
+		for (; k <= n_win; ++k) {
+			uint64_t ws = k * (uint64_t)W, we = ws + W - 1;
+			if (we > L) we = L;
+			if (e < ws) break;
+			int64_t c; int stop;
+			if (s < ws) {
+				if (e < we) { c = (int64_t)(e - ws); stop = 1; }
+				else { c = (int64_t)(we - ws + 1); stop = 0; }
+			} else if (s <= we) {
+				if (e <= we) { c = (int64_t)(e - s); stop = 1; }
+				else { c = (int64_t)(we - s); stop = 0; }
+			} else continue;
+			if (k < n_win && c != 0) add((uint32_t)k, c * d);   /* k == n_win is out of bounds in the reference too */
+			if (stop) break;
+		}
+	}
+}
+
+/* ---- decimal formatting --------------------------------------------------------------------------*/
+NGS_HD uint32_t ngs_ndigits(uint32_t v)
+{
+	return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 :
+	       v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+NGS_HD uint32_t ngs_ndigits64(uint64_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n; } return n; }
+/* printf("%d") length */
+NGS_HD uint32_t ngs_len_i32(int32_t v) { return v < 0 ? 1 + ngs_ndigits((uint32_t)(-(int64_t)v)) : ngs_ndigits((uint32_t)v); }
+/* writes printf("%d") of v at dst, returns bytes written */
+template <class Ptr>
+NGS_HD uint32_t ngs_put_u64(Ptr dst, uint64_t v)
+{
+	uint32_t n = ngs_ndigits64(v);
+	for (uint32_t i = n; i-- > 0;) { dst[i] = (char)('0' + (uint32_t)(v % 10)); v /= 10; }
+	return n;
+}
+template <class Ptr>
+NGS_HD uint32_t ngs_put_u32(Ptr dst, uint32_t v)
+{
+	uint32_t n = ngs_ndigits(v);
+	for (uint32_t i = n; i-- > 0;) { uint32_t q = v / 10u; dst[i] = (char)('0' + (v - q * 10u)); v = q; }
+	return n;
+}
+template <class Ptr>
+NGS_HD uint32_t ngs_put_i32(Ptr dst, int32_t v)
+{
+	if (v < 0) { dst[0] = '-'; return 1 + ngs_put_u32(dst + 1, (uint32_t)(-(int64_t)v)); }
+	return ngs_put_u32(dst, (uint32_t)v);
+}
+
+/* value of printf("%.2f", (double)bins / (double)window) as an integer number of hundredths, rounded
+ * half-to-even on the EXACT binary value of the IEEE quotient (what glibc does).  `q` must be that
+ * correctly rounded quotient (device: __ddiv_rn; host: plain division).  q >= 0. */
+NGS_HD uint64_t ngs_hundredths(double q)
+{
+	union { double d; uint64_t u; } cv; cv.d = q;
+	uint64_t bits = cv.u;
+	int ex = (int)((bits >> 52) & 0x7ff);
+	uint64_t m = bits & 0xFFFFFFFFFFFFFull;
+	if (ex == 0) { if (m == 0) return 0; ex = 1; } else m |= 1ull << 52;
+	int sh = 1075 - ex;                          /* q = m * 2^-sh */
+	if (sh <= 0) {                               /* integer >= 2^52 (not reachable for bins < 2^53) */
+		uint64_t ip = m << (-sh > 10 ? 10 : -sh);
+		return ip * 100;
+	}
+	if (sh >= 64) return 0;                      /* m*100 < 2^60 <= 2^(sh-1): below one half */
+	uint64_t N = m * 100ull;
+	uint64_t t = N >> sh, rem = N & ((1ull << sh) - 1), half = 1ull << (sh - 1);
+	if (rem > half || (rem == half && (t & 1))) ++t;
+	return t;
+}
+NGS_HD uint32_t ngs_len_f2(uint64_t hundredths) { return ngs_ndigits64(hundredths / 100) + 3; }
+template <class Ptr>
+NGS_HD uint32_t ngs_put_f2(Ptr dst, uint64_t hundredths)
+{
+	uint32_t n = ngs_put_u64(dst, hundredths / 100);
+	uint32_t f = (uint32_t)(hundredths % 100);
+	dst[n] = '.'; dst[n + 1] = (char)('0' + f / 10); dst[n + 2] = (char)('0' + f % 10);
+	return n + 3;
+}
+
+/* ---- the record walk -----------------------------------------------------------------------------
+ * Policy `Mem` supplies the loads:  void hdr_lite(int64 o, ngs_hdr&)  first 24 bytes of the record,
+ *                                   void hdr(int64 o, ngs_hdr&)       all 36 bytes,
+ *                                   uint32 u32(int64 o), uint8 u8(int64 o), int64 size().
+ * Policy `Sink` receives deltas:    void add2(uint64 idx_plus, uint64 idx_minus, int sign),
+ *                                   void flag_range_error().
+ */
+typedef struct {
+	uint64_t records, kept, m_ops, cigar_words;
+} ngs_counts;
+
+typedef struct {
+	int32_t  n_ref;
+	uint32_t flag_mask;
+	const int32_t *ctg2seg;      /* [n_ref] segment index of a contig or -1 (outside the shard) */
+	const ngs_seg *seg;
+} ngs_walk_cfg;
+
+/* decode one (already validated) record at offset o and emit its deltas with weight `sign` */
+template <class Mem, class Sink>
+NGS_HD void ngs_decode_record(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o, const ngs_hdr &h,
+                              Sink &sink, int sign, ngs_counts &cnt)
+{
+	cnt.records += 1; cnt.cigar_words += h.n_cigar;
+	if ((h.flag & cfg.flag_mask) || h.ref_id < 0 || h.pos >= (1 << 29)) return;
+	cnt.kept += 1;
+	const int32_t si = cfg.ctg2seg[h.ref_id];
+	if (si < 0 || h.n_cigar == 0) return;
+	const ngs_seg sg = cfg.seg[si];
+	uint32_t p = (uint32_t)h.pos;
+	int64_t co = o + 36 + (int64_t)h.l_qname;
+	for (uint32_t i = 0; i < h.n_cigar; ++i, co += 4) {
+		const uint32_t w = mem.u32(co), op = w & 0xf, len = w >> 4;
+		if (op == 0) {                                   /* M: Start[p]++, End[p+len]++ */
+			uint32_t a = p & NGS_POS_MASK;
+			p += len;
+			uint32_t b = p & NGS_POS_MASK;
+			if (a == b) continue;                        /* net-zero pair of keys: transparent to the sweep */
+			if (b < a) { sink.flag_range_error(); continue; }
+			if (b > sg.lim) {
+				if (sg.hard_end) { sink.flag_range_error(); continue; }
+				b = sg.lim;
+			}
+			if (a < sg.clip_lo) a = sg.clip_lo;
+			if (a >= b) continue;
+			cnt.m_ops += 1;
+			sink.add2(sg.base + (a - sg.clip_lo), sg.base + (b - sg.clip_lo), sign);
+		} else if (op == 2 || op == 3) p += len;         /* D, N advance; I S H P = X B do not */
+	}
+}
+
+/* Walk the record chain from offset o while records START before `hi`.  Returns the exit code:
+ *   >= hi            offset of the first record start at or beyond hi (may exceed the chunk size)
+ *   NGS_EXIT_PARTIAL the record at that offset has its header/CIGAR cut by the chunk end
+ *   NGS_EXIT_INVALID a record failed validation                                             */
+template <class Mem, class Sink>
+NGS_HD int64_t ngs_walk(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o, int64_t hi,
+                        Sink &sink, int sign, ngs_counts &cnt)
+{
+	const int64_t n = mem.size();
+	while (o < hi) {
+		ngs_hdr h;
+		if (o + 36 > n) return NGS_EXIT_PARTIAL(o);
+		mem.hdr_lite(o, h);
+		if (!ngs_hdr_valid(h, cfg.n_ref)) return NGS_EXIT_INVALID;
+		if (o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar > n) return NGS_EXIT_PARTIAL(o);
+		ngs_decode_record(cfg, mem, o, h, sink, sign, cnt);
+		o += 4 + (int64_t)h.block_size;
+	}
+	return o;
+}
+
+/* Speculative entry search in [lo, hi): first offset whose record and the `depth-1` records chained
+ * after it all look plausible.  NGS_NONE if there is none (or it cannot be checked inside the chunk). */
+template <class Mem>
+NGS_HD int64_t ngs_find_entry(const ngs_walk_cfg &cfg, const Mem &mem, const uint32_t *ref_len, int64_t lo, int64_t hi)
+{
+	const int64_t n = mem.size();
+	for (int64_t o = lo; o < hi; ++o) {
+		if (o + 36 > n) return NGS_NONE;
+		/* cheap prefilter: block_size and refID ranges */
+		const uint32_t bs = mem.u32(o);
+		if (bs - 32u > NGS_MAX_BS - 32u) continue;
+		const uint32_t rid = mem.u32(o + 4);
+		if (rid + 1u > (uint32_t)cfg.n_ref) continue;
+		int64_t c = o; int ok = 1;
+		for (int depth = 0; depth < 3; ++depth) {
+			ngs_hdr h;
+			if (c + 36 > n) break;                                   /* chain leaves the chunk: accept */
+			mem.hdr(c, h);
+			if (!ngs_hdr_plausible(h, cfg.n_ref, ref_len)) { ok = 0; break; }
+			const int64_t nul = c + 36 + (int64_t)h.l_qname - 1;
+			if (nul < n && mem.u8(nul) != 0) { ok = 0; break; }
+			c += 4 + (int64_t)h.block_size;
+		}
+		if (ok) return o;
+	}
+	return NGS_NONE;
+}
+
+#endif

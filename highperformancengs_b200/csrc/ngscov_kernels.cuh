@@ -1,0 +1,790 @@
+/* csrc/ngscov_kernels.cuh -- the sm_100a kernels of libngscov_cuda.
+ *
+ * Stage map (SURVEY.md section 7 / BASELINE.json north_star):
+ *   K1+K2  k_ingest_walk     record-offset discovery (speculative per-sub-chunk block_size chain walk)
+ *                            fused with core/CIGAR decode and +1/-1 scatter into the int32 difference
+ *                            array (REDs, run-length combined per thread)
+ *          k_verify_*        boundary check: each sub-chunk's entry must equal the running max of the
+ *                            exits before it;  k_repair re-walks (undo + redo) the rare misses
+ *          k_finalize_chunk  carry of a record cut by the chunk end
+ *   K3+K4  k_scan_runs       single-pass decoupled-look-back prefix scan over the difference array,
+ *                            run-boundary detection, stream compaction into (start,end,depth) records,
+ *                            window bins; also re-zeroes the array for the next input
+ *   K5     k_format_lines<>  device-side integer -> ASCII formatting with a second look-back scan for
+ *                            byte offsets, shared-memory line staging and 128-bit coalesced stores
+ *
+ * None of this is a dense contraction, so there is no tensor-core path; every stage is bound by HBM
+ * bandwidth or by L2 atomic throughput.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ngscov_hd.h"
+
+#define NGS_SCAN_THREADS 256
+#define NGS_SCAN_ITEMS   16
+#define NGS_TILE         (NGS_SCAN_THREADS * NGS_SCAN_ITEMS)   /* 4096 difference-array elements */
+#define NGS_FMT_THREADS  256
+#define NGS_BAD_CAP      4096
+
+#define NGS_FLAG_ERANGE  1u
+#define NGS_FLAG_EFORMAT 2u
+
+/* ------------------------------------------------------------------------------------------------ */
+/* device-side global state of one handle (lives in device memory, mirrored to pinned host memory) */
+struct ngs_dev_state {
+	unsigned long long records, kept, m_ops, cigar_words;   /* ingest counters */
+	unsigned long long spec_walks, spec_repaired;
+	unsigned long long n_bad;          /* verify: mismatching sub-chunks found this pass */
+	unsigned long long first_bad_key;  /* verify: min over (sub-chunk*2 + kind), kind 1 = broken chain */
+	long long first_bad_expected;
+	long long chunk_exit;              /* verify: max exit of the chunk (entry of the next chunk + n) */
+	long long entry_next;              /* entry offset of the next chunk relative to its data start */
+	unsigned int carry_len;
+	unsigned int flags;                /* NGS_FLAG_* */
+	/* scan */
+	unsigned long long scan_ticket;
+	unsigned long long n_boundaries, n_runs;
+	unsigned long long first_run, last_run;   /* record indices of the first / last non-zero run */
+	int max_depth, min_depth;
+	/* format */
+	unsigned long long fmt_ticket;
+	unsigned long long fmt_bytes;
+};
+
+/* ------------------------------------------------------------------------------------------------ */
+/* memory policy: unaligned little-endian field access on the inflated stream in HBM               */
+struct DevMem {
+	const uint8_t *base;     /* offset 0 of the chunk (carry bytes live just before it) */
+	int64_t n;
+	__device__ __forceinline__ int64_t size() const { return n; }
+	__device__ __forceinline__ uint32_t u32(int64_t o) const
+	{
+		const uintptr_t a = (uintptr_t)(base + o);
+		const uint32_t *p = (const uint32_t *)(a & ~(uintptr_t)3);
+		const uint32_t sh = (uint32_t)(a & 3) * 8;
+		const uint32_t lo = __ldg(p);
+		if (sh == 0) return lo;
+		return __funnelshift_r(lo, __ldg(p + 1), sh);
+	}
+	__device__ __forceinline__ uint32_t u8(int64_t o) const
+	{
+		const uintptr_t a = (uintptr_t)(base + o);
+		return (__ldg((const uint32_t *)(a & ~(uintptr_t)3)) >> ((a & 3) * 8)) & 0xff;
+	}
+	/* first 24 bytes of a record with two (sometimes three) 128-bit loads */
+	__device__ __forceinline__ void hdr_lite(int64_t o, ngs_hdr &h) const
+	{
+		const uintptr_t a = (uintptr_t)(base + o);
+		const uint4 *p = (const uint4 *)(a & ~(uintptr_t)15);
+		const uint32_t bo = (uint32_t)(a & 15);
+		const uint4 q0 = __ldg(p), q1 = __ldg(p + 1);
+		uint4 q2 = make_uint4(0, 0, 0, 0);
+		if (bo > 8) q2 = __ldg(p + 2);
+		uint32_t w[10] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y };
+		if (bo & 8) {
+			#pragma unroll
+			for (int i = 0; i < 8; ++i) w[i] = w[i + 2];
+		}
+		if (bo & 4) {
+			#pragma unroll
+			for (int i = 0; i < 7; ++i) w[i] = w[i + 1];
+		}
+		const uint32_t sh = (bo & 3) * 8;
+		uint32_t f[6];
+		#pragma unroll
+		for (int i = 0; i < 6; ++i) f[i] = __funnelshift_r(w[i], w[i + 1], sh);
+		h.block_size = (int32_t)f[0]; h.ref_id = (int32_t)f[1]; h.pos = (int32_t)f[2];
+		h.l_qname = f[3] & 0xff; h.n_cigar = f[4] & 0xffff; h.flag = f[4] >> 16; h.l_seq = (int32_t)f[5];
+		h.next_ref_id = 0; h.next_pos = 0;
+	}
+	__device__ __forceinline__ void hdr(int64_t o, ngs_hdr &h) const
+	{
+		h.block_size = (int32_t)u32(o); h.ref_id = (int32_t)u32(o + 4); h.pos = (int32_t)u32(o + 8);
+		const uint32_t a = u32(o + 12), b = u32(o + 16);
+		h.l_qname = a & 0xff; h.n_cigar = b & 0xffff; h.flag = b >> 16;
+		h.l_seq = (int32_t)u32(o + 20); h.next_ref_id = (int32_t)u32(o + 24); h.next_pos = (int32_t)u32(o + 28);
+	}
+};
+
+/* delta sink: one pending (address,count) pair for the +1 stream and one for the -1 stream, so that
+ * pile-ups (identical starts / ends in consecutive records) collapse into a single RED */
+struct DevSink {
+	int *diff; unsigned int *flags;
+	unsigned long long pa, pb; int ca, cb;
+	__device__ __forceinline__ void init(int *d, unsigned int *f) { diff = d; flags = f; pa = pb = ~0ull; ca = cb = 0; }
+	__device__ __forceinline__ void add2(uint64_t ia, uint64_t ib, int sign)
+	{
+		if (ia == pa) ca += sign; else { if (ca) atomicAdd(diff + pa, ca); pa = ia; ca = sign; }
+		if (ib == pb) cb -= sign; else { if (cb) atomicAdd(diff + pb, cb); pb = ib; cb = -sign; }
+	}
+	__device__ __forceinline__ void flush()
+	{
+		if (ca) atomicAdd(diff + pa, ca);
+		if (cb) atomicAdd(diff + pb, cb);
+		ca = cb = 0; pa = pb = ~0ull;
+	}
+	__device__ __forceinline__ void flag_range_error() { atomicOr(flags, NGS_FLAG_ERANGE); }
+};
+
+struct IngestArgs {
+	const uint8_t *base; int64_t n;        /* chunk */
+	int shift;                             /* log2(sub-chunk bytes) */
+	int64_t n_sub;
+	long long *entry, *exit;               /* [n_sub] */
+	ngs_walk_cfg cfg;
+	const uint32_t *ref_len;
+	int *diff;
+	ngs_dev_state *st;
+	long long fixed_entry0;                /* used when entry0_from_state == 0 */
+	int entry0_from_state;                 /* 1: first entry = st->entry_next (streamed pushes) */
+};
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+/* K1+K2: one thread per sub-chunk. */
+__global__ void __launch_bounds__(256) k_ingest_walk(IngestArgs A)
+{
+	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	ngs_counts cnt = { 0, 0, 0, 0 };
+	unsigned long long walks = 0;
+	if (c < A.n_sub) {
+		DevMem mem = { A.base, A.n };
+		const int64_t lo = c << A.shift;
+		int64_t hi = lo + ((int64_t)1 << A.shift);
+		if (hi > A.n) hi = A.n;
+		long long entry, ex = 0;
+		if (c == 0) {
+			const long long e0 = A.entry0_from_state ? A.st->entry_next : A.fixed_entry0;
+			entry = e0 < hi ? e0 : NGS_NONE;
+		} else {
+			entry = ngs_find_entry(A.cfg, mem, A.ref_len, lo, hi);
+		}
+		if (entry != NGS_NONE) {
+			DevSink sink; sink.init(A.diff, &A.st->flags);
+			ex = ngs_walk(A.cfg, mem, entry, hi, sink, +1, cnt);
+			sink.flush();
+			walks = 1;
+		}
+		A.entry[c] = entry; A.exit[c] = ex;
+	}
+	/* block-aggregate the counters */
+	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
+	                   v2 = warp_sum_u64(cnt.m_ops), v3 = warp_sum_u64(cnt.cigar_words), v4 = warp_sum_u64(walks);
+	if ((threadIdx.x & 31) == 0) {
+		if (v0) atomicAdd(&A.st->records, v0);
+		if (v1) atomicAdd(&A.st->kept, v1);
+		if (v2) atomicAdd(&A.st->m_ops, v2);
+		if (v3) atomicAdd(&A.st->cigar_words, v3);
+		if (v4) atomicAdd(&A.st->spec_walks, v4);
+	}
+}
+
+/* numeric value of an exit slot for the running max */
+__device__ __forceinline__ long long exit_num(long long x) { return x == NGS_EXIT_INVALID ? 0 : x; }
+
+__device__ __forceinline__ long long block_max_ll(long long v, long long *sm)
+{
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+	const int w = threadIdx.x >> 5;
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) sm[w] = v;
+	__syncthreads();
+	long long r = sm[0];
+	for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = sm[i] > r ? sm[i] : r;
+	return r;
+}
+
+#define NGS_VER_PER_BLOCK 1024   /* sub-chunks per verify block: 256 threads x 4 */
+
+__global__ void __launch_bounds__(256) k_verify_blockmax(const long long *exit, int64_t n_sub, long long *bmax)
+{
+	__shared__ long long sm[8];
+	const int64_t b0 = (int64_t)blockIdx.x * NGS_VER_PER_BLOCK;
+	long long m = 0;
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const int64_t c = b0 + i * 256 + threadIdx.x;
+		if (c < n_sub) { long long x = exit_num(exit[c]); m = x > m ? x : m; }
+	}
+	m = block_max_ll(m, sm);
+	if (threadIdx.x == 0) bmax[blockIdx.x] = m;
+}
+
+/* single block: exclusive running max over the block maxima, seeded with the chunk's first entry */
+__global__ void __launch_bounds__(1024) k_verify_scan(long long *bmax, int64_t n_blocks, ngs_dev_state *st,
+                                                      long long fixed_entry0, int entry0_from_state)
+{
+	__shared__ long long sm[32];
+	__shared__ long long carry_s;
+	if (threadIdx.x == 0) {
+		carry_s = entry0_from_state ? st->entry_next : fixed_entry0;
+		st->n_bad = 0; st->first_bad_key = ~0ull;
+	}
+	__syncthreads();
+	for (int64_t b0 = 0; b0 < n_blocks; b0 += 1024) {
+		const int64_t b = b0 + threadIdx.x;
+		const long long own = b < n_blocks ? bmax[b] : 0;
+		/* inclusive max-scan within the block of 1024 */
+		long long v = own;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o && t > v) v = t; }
+		if ((threadIdx.x & 31) == 31) sm[threadIdx.x >> 5] = v;
+		__syncthreads();
+		long long pre = carry_s;
+		for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) pre = sm[w] > pre ? sm[w] : pre;
+		long long incl = v > pre ? v : pre;
+		/* exclusive value for this block = max(pre, values of earlier lanes) */
+		long long prev = __shfl_up_sync(0xffffffffu, v, 1);
+		long long excl = (threadIdx.x & 31) ? (prev > pre ? prev : pre) : pre;
+		if (b < n_blocks) bmax[b] = excl;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry_s = incl;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) st->chunk_exit = carry_s;
+}
+
+__global__ void __launch_bounds__(256) k_verify_check(const long long *entry, const long long *exit, int64_t n_sub,
+                                                      const long long *bexcl, int shift, int64_t n, ngs_dev_state *st)
+{
+	__shared__ long long sm[8];
+	const int64_t c0 = (int64_t)blockIdx.x * NGS_VER_PER_BLOCK + (int64_t)threadIdx.x * 4;
+	long long ex[4], en[4];
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const int64_t c = c0 + i;
+		ex[i] = c < n_sub ? exit_num(exit[c]) : 0;
+		en[i] = c < n_sub ? entry[c] : NGS_NONE;
+	}
+	long long tmax = ex[0];
+	tmax = ex[1] > tmax ? ex[1] : tmax; tmax = ex[2] > tmax ? ex[2] : tmax; tmax = ex[3] > tmax ? ex[3] : tmax;
+	/* exclusive max-scan of per-thread maxima across the block */
+	long long v = tmax;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o && t > v) v = t; }
+	if ((threadIdx.x & 31) == 31) sm[threadIdx.x >> 5] = v;
+	__syncthreads();
+	long long pre = bexcl[blockIdx.x];
+	for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) pre = sm[w] > pre ? sm[w] : pre;
+	long long prev = __shfl_up_sync(0xffffffffu, v, 1);
+	long long run = (threadIdx.x & 31) ? (prev > pre ? prev : pre) : pre;
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const int64_t c = c0 + i;
+		if (c < n_sub) {
+			const long long expected = run;
+			const int64_t lo = c << shift;
+			int64_t hi = lo + ((int64_t)1 << shift);
+			if (hi > n) hi = n;
+			const bool exp_in = expected < hi;
+			int kind = -1;
+			if (exp_in && c > 0 && expected < lo) kind = 1;                  /* a verified chain ended early */
+			else if (exp_in ? (en[i] != expected) : (en[i] != NGS_NONE)) kind = 0;
+			else if (en[i] != NGS_NONE && exit[c] == NGS_EXIT_INVALID) kind = 1;
+			if (kind >= 0) {
+				atomicAdd(&st->n_bad, 1ull);
+				const unsigned long long key = (unsigned long long)c * 2 + (unsigned)kind;
+				const unsigned long long old = atomicMin(&st->first_bad_key, key);
+				(void)old;
+			}
+			run = ex[i] > run ? ex[i] : run;
+		}
+	}
+}
+
+/* Rare path: single thread zips the true chain forward from the first mismatching sub-chunk until it
+ * re-converges with an already-walked entry, undoing (sign -1) every mis-speculated walk it crosses. */
+__global__ void k_repair(IngestArgs A, long long first_bad, const long long *bexcl)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	/* expected entry of the first bad sub-chunk = running max of the exits before it */
+	long long expected0 = bexcl[first_bad / NGS_VER_PER_BLOCK];
+	for (long long k = (first_bad / NGS_VER_PER_BLOCK) * NGS_VER_PER_BLOCK; k < first_bad; ++k) {
+		const long long x = exit_num(A.exit[k]);
+		expected0 = x > expected0 ? x : expected0;
+	}
+	DevMem mem = { A.base, A.n };
+	DevSink sink; sink.init(A.diff, &A.st->flags);
+	ngs_counts add = { 0, 0, 0, 0 }, sub = { 0, 0, 0, 0 };
+	long long c = first_bad, cur = expected0, repaired = 0;
+	for (;;) {
+		long long cc = cur >= A.n ? A.n_sub : (cur < 0 ? 0 : (cur >> A.shift));
+		if (cc > A.n_sub) cc = A.n_sub;
+		for (long long k = c; k < cc; ++k) {            /* sub-chunks the true chain jumps over */
+			if (A.entry[k] != NGS_NONE) {
+				long long hi = (k + 1) << A.shift; if (hi > A.n) hi = A.n;
+				ngs_walk(A.cfg, mem, A.entry[k], hi, sink, -1, sub);
+				A.entry[k] = NGS_NONE; A.exit[k] = 0; ++repaired;
+			}
+		}
+		if (cc >= A.n_sub) break;
+		if (A.entry[cc] == cur) break;                  /* converged */
+		long long hi = (cc + 1) << A.shift; if (hi > A.n) hi = A.n;
+		if (A.entry[cc] != NGS_NONE) ngs_walk(A.cfg, mem, A.entry[cc], hi, sink, -1, sub);
+		A.entry[cc] = cur;
+		const long long x = ngs_walk(A.cfg, mem, cur, hi, sink, +1, add);
+		A.exit[cc] = x; ++repaired;
+		c = cc + 1;
+		if (x == NGS_EXIT_INVALID || x >= NGS_EXIT_INF) cur = A.n;   /* chain ends in this chunk */
+		else cur = x;
+	}
+	sink.flush();
+	atomicAdd(&A.st->records, add.records - sub.records);
+	atomicAdd(&A.st->kept, add.kept - sub.kept);
+	atomicAdd(&A.st->m_ops, add.m_ops - sub.m_ops);
+	atomicAdd(&A.st->cigar_words, add.cigar_words - sub.cigar_words);
+	atomicAdd(&A.st->spec_repaired, (unsigned long long)repaired);
+}
+
+/* after a clean verify: derive the next chunk's entry and save the bytes of a cut record */
+__global__ void __launch_bounds__(256) k_finalize_chunk(const uint8_t *base, int64_t n, ngs_dev_state *st, uint8_t *carry)
+{
+	const long long ce = st->chunk_exit;
+	__shared__ long long s_o;
+	if (threadIdx.x == 0) {
+		if (ce >= NGS_EXIT_INF) {
+			const long long o = ce - NGS_EXIT_INF - (1ll << 40);
+			if (n - o > (long long)NGS_CARRY_MAX || n - o < 0) { atomicOr(&st->flags, NGS_FLAG_EFORMAT); s_o = n; }
+			else s_o = o;
+		} else s_o = n;
+	}
+	__syncthreads();
+	const long long o = s_o;
+	const unsigned int len = (unsigned int)(n - o);
+	for (unsigned int i = threadIdx.x; i < len; i += blockDim.x) carry[i] = base[o + i];
+	if (threadIdx.x == 0) {
+		st->carry_len = len;
+		st->entry_next = len ? -(long long)len : (ce >= NGS_EXIT_INF ? 0 : ce - n);
+	}
+}
+
+/* place the saved carry bytes right before the data start of the next chunk buffer */
+__global__ void __launch_bounds__(256) k_place_carry(uint8_t *data_start, const ngs_dev_state *st, const uint8_t *carry)
+{
+	const unsigned int len = st->carry_len;
+	for (unsigned int i = threadIdx.x; i < len; i += blockDim.x) data_start[(long long)i - (long long)len] = carry[i];
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* K3+K4: decoupled look-back scan + run compaction + window bins                                    */
+
+#define NGS_ST_EMPTY 0ull
+#define NGS_ST_AGG   1ull
+#define NGS_ST_INC   2ull
+
+struct ScanArgs {
+	int *diff;                       /* difference array, zeroed again on the way through */
+	uint64_t n_tiles;
+	const uint32_t *tile2seg;        /* [n_tiles] */
+	const ngs_seg *seg;
+	unsigned long long *stA, *stB;   /* [n_tiles] look-back words: A = status:2|count:62, B = status:2|lastb:30|sum:32 */
+	uint32_t *run_start, *run_end; int *run_depth;   /* boundary records */
+	uint64_t run_cap;
+	unsigned long long *rec_base;    /* [n_seg+1] first record index of each segment */
+	uint32_t n_seg;
+	unsigned long long *bins;        /* window bins (concatenated contigs) */
+	uint32_t window; int variant;
+	int rezero;
+	ngs_dev_state *st;
+};
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+struct BinAcc {   /* per-thread pending (bin, value): consecutive runs of a thread share a window */
+	unsigned long long *bins; long long k; long long acc;
+	__device__ __forceinline__ void operator()(uint32_t kk, int64_t v)
+	{
+		if ((long long)kk == k) acc += v;
+		else { if (k >= 0 && acc) atomicAdd(bins + k, (unsigned long long)acc); k = kk; acc = v; }
+	}
+};
+
+__global__ void __launch_bounds__(NGS_SCAN_THREADS) k_scan_runs(ScanArgs A)
+{
+	__shared__ int s_tile[NGS_SCAN_THREADS * 20];        /* 16 ints + 4 pad per thread: conflict-free 128-bit reads */
+	__shared__ long long s_wsum[8]; __shared__ unsigned int s_wcnt[8]; __shared__ unsigned int s_wlast[8];
+	__shared__ unsigned long long s_tile_id;
+	__shared__ long long s_ex_sum; __shared__ unsigned long long s_ex_cnt; __shared__ unsigned int s_ex_last;
+	__shared__ unsigned long long s_nruns; __shared__ int s_maxd, s_mind;
+	__shared__ unsigned long long s_firstrun, s_lastrun;
+
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	if (t == 0) {
+		s_tile_id = atomicAdd(&A.st->scan_ticket, 1ull);
+		s_nruns = 0; s_maxd = 0; s_mind = 0; s_firstrun = ~0ull; s_lastrun = 0;
+	}
+	__syncthreads();
+	const uint64_t tile = s_tile_id;
+	if (tile >= A.n_tiles) return;
+	const uint32_t si = A.tile2seg[tile];
+	const ngs_seg sg = A.seg[si];
+
+	/* coalesced 128-bit loads (striped), transpose through shared memory to 16 consecutive per thread */
+	int4 *gp = reinterpret_cast<int4 *>(A.diff + tile * (uint64_t)NGS_TILE);
+	#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int q = j * NGS_SCAN_THREADS + t;              /* int4 index within the tile */
+		const int4 v = gp[q];
+		*reinterpret_cast<int4 *>(&s_tile[(q >> 2) * 20 + (q & 3) * 4]) = v;
+		if (A.rezero) gp[q] = make_int4(0, 0, 0, 0);
+	}
+	__syncthreads();
+	int d[16];
+	#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int4 v = *reinterpret_cast<const int4 *>(&s_tile[t * 20 + j * 4]);
+		d[4 * j] = v.x; d[4 * j + 1] = v.y; d[4 * j + 2] = v.z; d[4 * j + 3] = v.w;
+	}
+	/* thread-local aggregate */
+	int tsum = 0; unsigned int tcnt = 0, tlast = 0;         /* tlast: 1 + tile-relative index of last boundary */
+	#pragma unroll
+	for (int i = 0; i < 16; ++i) { tsum += d[i]; if (d[i] != 0) { ++tcnt; tlast = (unsigned)(t * 16 + i + 1); } }
+	/* warp inclusive scans */
+	int isum = tsum; unsigned int icnt = tcnt, ilast = tlast;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const int a = __shfl_up_sync(0xffffffffu, isum, o);
+		const unsigned int b = __shfl_up_sync(0xffffffffu, icnt, o);
+		const unsigned int c = __shfl_up_sync(0xffffffffu, ilast, o);
+		if (lane >= o) { isum += a; icnt += b; ilast = ilast > c ? ilast : c; }
+	}
+	if (lane == 31) { s_wsum[warp] = isum; s_wcnt[warp] = icnt; s_wlast[warp] = ilast; }
+	__syncthreads();
+	long long wpre_sum = 0; unsigned int wpre_cnt = 0, wpre_last = 0;
+	long long tot_sum = 0; unsigned int tot_cnt = 0, tot_last = 0;
+	#pragma unroll
+	for (int w = 0; w < 8; ++w) {
+		if (w < warp) { wpre_sum += s_wsum[w]; wpre_cnt += s_wcnt[w]; wpre_last = s_wlast[w] > wpre_last ? s_wlast[w] : wpre_last; }
+		tot_sum += s_wsum[w]; tot_cnt += s_wcnt[w]; tot_last = s_wlast[w] > tot_last ? s_wlast[w] : tot_last;
+	}
+	/* exclusive prefix of this thread within the tile */
+	const int psum = __shfl_up_sync(0xffffffffu, isum, 1);
+	const unsigned int pcnt = __shfl_up_sync(0xffffffffu, icnt, 1), plast = __shfl_up_sync(0xffffffffu, ilast, 1);
+	long long ex_sum = wpre_sum + (lane ? psum : 0);
+	unsigned int ex_cnt = wpre_cnt + (lane ? pcnt : 0);
+	unsigned int ex_last = lane ? (plast > wpre_last ? plast : wpre_last) : wpre_last;
+
+	/* tile-relative -> contig position of element 0 of this tile */
+	const uint32_t pos0 = sg.clip_lo + (uint32_t)((tile - sg.tile0) * NGS_TILE);
+	const uint32_t agg_lastb = tot_last ? pos0 + tot_last : 0;     /* 1 + contig position, 0 = none */
+
+	/* ---- decoupled look-back (warp 0) */
+	if (warp == 0) {
+		long long run_sum = 0; unsigned long long run_cnt = 0; unsigned int run_last = 0;
+		if (tile == 0) {
+			if (lane == 0) {
+				st_relaxed_u64(&A.stA[0], (NGS_ST_INC << 62) | (unsigned long long)tot_cnt);
+				st_relaxed_u64(&A.stB[0], (NGS_ST_INC << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
+			}
+		} else {
+			if (lane == 0) {
+				st_relaxed_u64(&A.stA[tile], (NGS_ST_AGG << 62) | (unsigned long long)tot_cnt);
+				st_relaxed_u64(&A.stB[tile], (NGS_ST_AGG << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
+			}
+			long long base = (long long)tile - 1;
+			for (;;) {
+				const long long idx = base - lane;
+				unsigned long long a = NGS_ST_INC << 62, b = NGS_ST_INC << 62;   /* virtual tiles before 0: inclusive zero */
+				if (idx >= 0) {
+					do {
+						a = ld_relaxed_u64(&A.stA[idx]);
+						b = ld_relaxed_u64(&A.stB[idx]);
+					} while ((a >> 62) == NGS_ST_EMPTY || (a >> 62) != (b >> 62));
+				}
+				const unsigned int incl_mask = __ballot_sync(0xffffffffu, (a >> 62) == NGS_ST_INC);
+				const int first_inc = incl_mask ? __ffs(incl_mask) - 1 : 32;        /* nearest inclusive predecessor */
+				/* combine lanes 0..first_inc (nearest first) */
+				long long vs = lane <= first_inc ? (long long)(int)(uint32_t)b : 0;
+				unsigned long long vc = lane <= first_inc ? (a & 0x3FFFFFFFFFFFFFFFull) : 0;
+				unsigned int vl = lane <= first_inc ? (unsigned int)((b >> 32) & 0x3FFFFFFFu) : 0;
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) {
+					vs += __shfl_xor_sync(0xffffffffu, vs, o);
+					vc += __shfl_xor_sync(0xffffffffu, vc, o);
+				}
+				/* nearest (lowest lane) non-zero lastb wins */
+				const unsigned int has = __ballot_sync(0xffffffffu, vl != 0);
+				unsigned int near_l = 0;
+				if (has) near_l = __shfl_sync(0xffffffffu, vl, __ffs(has) - 1);
+				run_sum += vs; run_cnt += vc; if (run_last == 0) run_last = near_l;
+				if (first_inc < 32) break;
+				base -= 32;
+			}
+			if (lane == 0) {
+				const unsigned int inc_last = agg_lastb ? agg_lastb : run_last;
+				st_relaxed_u64(&A.stA[tile], (NGS_ST_INC << 62) | (run_cnt + tot_cnt));
+				st_relaxed_u64(&A.stB[tile], (NGS_ST_INC << 62) | ((unsigned long long)inc_last << 32) | (uint32_t)(int)(run_sum + tot_sum));
+			}
+		}
+		if (lane == 0) { s_ex_sum = run_sum; s_ex_cnt = run_cnt; s_ex_last = run_last; }
+	}
+	__syncthreads();
+	const long long tile_sum = s_ex_sum; const unsigned long long tile_cnt = s_ex_cnt; const unsigned int tile_last = s_ex_last;
+	if (t == 0) {
+		if (tile == sg.tile0) A.rec_base[si] = tile_cnt;
+		if (tile == A.n_tiles - 1) {
+			for (uint32_t s2 = si + 1; s2 <= A.n_seg; ++s2) A.rec_base[s2] = tile_cnt + tot_cnt;
+			A.st->n_boundaries = tile_cnt + tot_cnt;
+		}
+	}
+	if (tot_cnt == 0) return;
+
+	/* ---- emit boundary records + bins */
+	int depth = (int)(tile_sum + ex_sum);
+	unsigned long long rec = tile_cnt + ex_cnt;
+	unsigned int last = ex_last ? pos0 + ex_last : tile_last;     /* 1 + contig position of previous boundary */
+	BinAcc bacc; bacc.bins = A.bins + sg.bins0; bacc.k = -1; bacc.acc = 0;
+	unsigned int my_runs = 0; int my_max = 0, my_min = 0;
+	unsigned long long my_first = ~0ull, my_last = 0;
+	if (tcnt) {
+		#pragma unroll
+		for (int i = 0; i < 16; ++i) {
+			if (d[i] != 0) {
+				const uint32_t pos = pos0 + (uint32_t)(t * 16 + i);
+				if (rec < A.run_cap) {
+					A.run_start[rec] = last ? last - 1 : 0;
+					A.run_end[rec] = pos;
+					A.run_depth[rec] = depth;
+				}
+				if (depth != 0) {
+					const uint32_t s = last ? last - 1 : 0;
+					ngs_bin_run(A.variant, s, pos, (int64_t)depth, A.window, sg.ref_len, sg.n_win, bacc);
+					++my_runs; my_max = depth > my_max ? depth : my_max; my_min = depth < my_min ? depth : my_min;
+					if (my_first == ~0ull) my_first = rec;
+					my_last = rec;
+				}
+				depth += d[i]; last = pos + 1; ++rec;
+			}
+		}
+		if (bacc.k >= 0 && bacc.acc) atomicAdd(bacc.bins + bacc.k, (unsigned long long)bacc.acc);
+	}
+	/* block-aggregate the statistics */
+	if (my_runs) {
+		atomicAdd(&s_nruns, (unsigned long long)my_runs);
+		atomicMax(&s_maxd, my_max); atomicMin(&s_mind, my_min);
+		atomicMin(&s_firstrun, my_first); atomicMax(&s_lastrun, my_last);
+	}
+	__syncthreads();
+	if (t == 0 && s_nruns) {
+		atomicAdd(&A.st->n_runs, s_nruns);
+		atomicMax(&A.st->max_depth, s_maxd); atomicMin(&A.st->min_depth, s_mind);
+		atomicMin(&A.st->first_run, s_firstrun); atomicMax(&A.st->last_run, s_lastrun);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* K5: line formatting.  A "producer" maps an item index to (length, bytes).  One look-back scan over
+ * tile byte counts gives each tile its output offset; lines are assembled in shared memory and copied
+ * out with aligned 128-bit stores.                                                                   */
+
+struct NameTable {
+	const char *names;               /* concatenated "name\t" strings */
+	const uint32_t *name_off;        /* [n_ref+1] */
+};
+
+/* bedGraph: item = boundary record; gap records (depth 0) and the dropped halo run have length 0 */
+struct BedProducer {
+	const uint32_t *run_start, *run_end; const int *run_depth;
+	const unsigned long long *rec_base; const ngs_seg *seg; uint32_t n_seg;
+	NameTable nt;
+	unsigned long long drop_idx, mod_idx; uint32_t mod_end;
+	struct Item { uint32_t s, e; int d; uint32_t ctg; };
+	__device__ __forceinline__ uint32_t seg_of(unsigned long long r) const
+	{
+		uint32_t lo = 0, hi = n_seg;                          /* last segment with rec_base <= r */
+		while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (rec_base[mid] <= r) lo = mid; else hi = mid; }
+		return lo;
+	}
+	__device__ __forceinline__ uint32_t length(unsigned long long r, Item &it) const
+	{
+		it.d = run_depth[r];
+		if (it.d == 0 || r == drop_idx) { it.d = 0; return 0; }
+		it.s = run_start[r]; it.e = (r == mod_idx) ? mod_end : run_end[r];
+		it.ctg = seg[seg_of(r)].contig;
+		return (nt.name_off[it.ctg + 1] - nt.name_off[it.ctg]) + ngs_ndigits(it.s) + 1 + ngs_ndigits(it.e) + 1 + ngs_len_i32(it.d) + 1;
+	}
+	__device__ __forceinline__ void write(char *dst, const Item &it) const
+	{
+		const uint32_t a = nt.name_off[it.ctg], nl = nt.name_off[it.ctg + 1] - a;
+		for (uint32_t i = 0; i < nl; ++i) dst[i] = nt.names[a + i];
+		dst += nl;
+		dst += ngs_put_u32(dst, it.s); *dst++ = '\t';
+		dst += ngs_put_u32(dst, it.e); *dst++ = '\t';
+		dst += ngs_put_i32(dst, it.d); *dst = '\n';
+	}
+};
+
+/* .depth: item = window (every window of every contig) */
+struct DepthProducer {
+	const unsigned long long *bins; const unsigned long long *win_base;   /* [n_ref+1] first item of contig */
+	const uint32_t *ref_len; uint32_t n_ref; uint32_t window; NameTable nt;
+	struct Item { uint32_t ws, we, ctg; unsigned long long h; };
+	__device__ __forceinline__ uint32_t ctg_of(unsigned long long r) const
+	{
+		uint32_t lo = 0, hi = n_ref;
+		while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (win_base[mid] <= r) lo = mid; else hi = mid; }
+		return lo;
+	}
+	__device__ __forceinline__ uint32_t length(unsigned long long r, Item &it) const
+	{
+		it.ctg = ctg_of(r);
+		const unsigned long long k = r - win_base[it.ctg];
+		const unsigned long long ws = k * window, we = ws + window;
+		it.ws = (uint32_t)ws; it.we = we > ref_len[it.ctg] ? ref_len[it.ctg] : (uint32_t)we;
+		it.h = ngs_hundredths(__ddiv_rn((double)(long long)bins[r], (double)window));
+		return (nt.name_off[it.ctg + 1] - nt.name_off[it.ctg]) + ngs_ndigits(it.ws) + 1 + ngs_ndigits(it.we) + 1 + ngs_len_f2(it.h) + 1;
+	}
+	__device__ __forceinline__ void write(char *dst, const Item &it) const
+	{
+		const uint32_t a = nt.name_off[it.ctg], nl = nt.name_off[it.ctg + 1] - a;
+		for (uint32_t i = 0; i < nl; ++i) dst[i] = nt.names[a + i];
+		dst += nl;
+		dst += ngs_put_u32(dst, it.ws); *dst++ = '\t';
+		dst += ngs_put_u32(dst, it.we); *dst++ = '\t';
+		dst += ngs_put_f2(dst, it.h); *dst = '\n';
+	}
+};
+
+/* wig: per contig one header item followed by one item per window (length 0 when the bin is empty) */
+struct WigProducer {
+	const unsigned long long *bins; const unsigned long long *win_base;   /* [n_ref+1] first BIN of contig */
+	uint32_t n_ref; uint32_t window;
+	const char *hdr; const uint32_t *hdr_off;                             /* "variableStep chrom=%s span=%d\n" per contig */
+	struct Item { uint32_t ws, ctg; int is_hdr; unsigned long long h; };
+	__device__ __forceinline__ uint32_t length(unsigned long long r, Item &it) const
+	{
+		/* item space: contig c owns items [win_base[c] + c, win_base[c+1] + c + 1) */
+		uint32_t lo = 0, hi = n_ref;
+		while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (win_base[mid] + mid <= r) lo = mid; else hi = mid; }
+		it.ctg = lo;
+		const unsigned long long k = r - (win_base[lo] + lo);
+		if (k == 0) { it.is_hdr = 1; return hdr_off[lo + 1] - hdr_off[lo]; }
+		it.is_hdr = 0;
+		const unsigned long long b = bins[win_base[lo] + k - 1];
+		if (b == 0) { it.h = ~0ull; return 0; }
+		it.ws = (uint32_t)((k - 1) * window);
+		it.h = ngs_hundredths(__ddiv_rn((double)(long long)b, (double)window));
+		return ngs_ndigits(it.ws) + 1 + ngs_len_f2(it.h) + 1;
+	}
+	__device__ __forceinline__ void write(char *dst, const Item &it) const
+	{
+		if (it.is_hdr) {
+			const uint32_t a = hdr_off[it.ctg], nl = hdr_off[it.ctg + 1] - a;
+			for (uint32_t i = 0; i < nl; ++i) dst[i] = hdr[a + i];
+			return;
+		}
+		dst += ngs_put_u32(dst, it.ws); *dst++ = '\t';
+		dst += ngs_put_f2(dst, it.h); *dst = '\n';
+	}
+};
+
+struct FmtArgs {
+	unsigned long long n_items;
+	unsigned long long n_tiles;
+	unsigned long long *status;        /* [n_tiles] status:2 | bytes:62 */
+	char *out; unsigned long long out_cap;
+	ngs_dev_state *st;
+	uint32_t stage_bytes;              /* dynamic shared memory for line staging */
+};
+
+template <class Producer, int IPT>
+__global__ void __launch_bounds__(NGS_FMT_THREADS) k_format_lines(FmtArgs A, Producer P)
+{
+	extern __shared__ __align__(16) char s_stage[];
+	__shared__ unsigned int s_w[8];
+	__shared__ unsigned long long s_tile_id, s_off;
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	if (t == 0) s_tile_id = atomicAdd(&A.st->fmt_ticket, 1ull);
+	__syncthreads();
+	const unsigned long long tile = s_tile_id;
+	if (tile >= A.n_tiles) return;
+	const unsigned long long r0 = tile * (unsigned long long)(NGS_FMT_THREADS * IPT) + (unsigned long long)t * IPT;
+	typename Producer::Item it[IPT];
+	uint32_t len[IPT], tlen = 0;
+	#pragma unroll
+	for (int i = 0; i < IPT; ++i) {
+		len[i] = (r0 + i < A.n_items) ? P.length(r0 + i, it[i]) : 0;
+		tlen += len[i];
+	}
+	/* block exclusive scan of tlen */
+	uint32_t inc = tlen;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+	if (lane == 31) s_w[warp] = inc;
+	__syncthreads();
+	uint32_t wpre = 0, total = 0;
+	#pragma unroll
+	for (int w = 0; w < 8; ++w) { if (w < warp) wpre += s_w[w]; total += s_w[w]; }
+	uint32_t off = wpre + inc - tlen;
+	/* look-back over tile byte totals */
+	if (warp == 0) {
+		unsigned long long run = 0;
+		if (tile == 0) { if (lane == 0) st_relaxed_u64(&A.status[0], (NGS_ST_INC << 62) | total); }
+		else {
+			if (lane == 0) st_relaxed_u64(&A.status[tile], (NGS_ST_AGG << 62) | total);
+			long long base = (long long)tile - 1;
+			for (;;) {
+				const long long idx = base - lane;
+				unsigned long long a = NGS_ST_INC << 62;
+				if (idx >= 0) { do { a = ld_relaxed_u64(&A.status[idx]); } while ((a >> 62) == NGS_ST_EMPTY); }
+				const unsigned int incl_mask = __ballot_sync(0xffffffffu, (a >> 62) == NGS_ST_INC);
+				const int first_inc = incl_mask ? __ffs(incl_mask) - 1 : 32;
+				unsigned long long v = lane <= first_inc ? (a & 0x3FFFFFFFFFFFFFFFull) : 0;
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+				run += v;
+				if (first_inc < 32) break;
+				base -= 32;
+			}
+			if (lane == 0) st_relaxed_u64(&A.status[tile], (NGS_ST_INC << 62) | (run + total));
+		}
+		if (lane == 0) { s_off = run; if (tile == A.n_tiles - 1) A.st->fmt_bytes = run + total; }
+	}
+	__syncthreads();
+	const unsigned long long goff = s_off;
+	if (total == 0 || goff + total > A.out_cap) return;
+	/* assemble lines in shared memory, shifted so that 16-byte alignment matches the global address */
+	const uint32_t mis = (uint32_t)((uintptr_t)(A.out + goff) & 15);
+	if (total + mis <= A.stage_bytes) {
+		#pragma unroll
+		for (int i = 0; i < IPT; ++i) { if (len[i]) P.write(s_stage + mis + off, it[i]); off += len[i]; }
+		__syncthreads();
+		char *g = A.out + goff - mis;                       /* 16-byte aligned */
+		const uint32_t end = mis + total;
+		uint32_t a0 = (mis + 15u) & ~15u;                   /* head bytes [mis,a0), 128-bit body [a0,a1), tail [a1,end) */
+		if (a0 > end) a0 = end;
+		uint32_t a1 = end & ~15u;
+		if (a1 < a0) a1 = a0;
+		for (uint32_t i = mis + t; i < a0; i += NGS_FMT_THREADS) g[i] = s_stage[i];
+		for (uint32_t i = a0 + (uint32_t)t * 16; i < a1; i += NGS_FMT_THREADS * 16)
+			*reinterpret_cast<int4 *>(g + i) = *reinterpret_cast<const int4 *>(s_stage + i);
+		for (uint32_t i = a1 + t; i < end; i += NGS_FMT_THREADS) g[i] = s_stage[i];
+	} else {
+		/* lines too long for the staging area (very long contig names): write straight to global */
+		#pragma unroll
+		for (int i = 0; i < IPT; ++i) { if (len[i]) P.write(A.out + goff + off, it[i]); off += len[i]; }
+	}
+}
+
+/* reset of look-back status words and tickets before a scan / format launch */
+__global__ void k_clear_u64(unsigned long long *p, unsigned long long n)
+{
+	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) p[i] = 0;
+}

@@ -1,0 +1,177 @@
+/* tests/hd_check.cpp -- CPU-only check of the record-level logic the kernels run (csrc/ngscov_hd.h).
+ *
+ * TEST INFRASTRUCTURE.  Compiles the NGS_HD functions with g++ and drives them with a sequential model
+ * of the kernel orchestration (speculative sub-chunk walk, running-max verification, zipper repair,
+ * prefix scan, run emission, window bins, decimal formatting), then compares every output byte with
+ * the oracle (oracle/ngscov_oracle.c).  It lets the semantics be validated on a machine without a GPU;
+ * the GPU tests then only have to prove that the parallel orchestration matches this model.
+ *
+ *   hd_check <bam> depth|wig <window> <subchunk_bytes> <chunk_bytes>
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../highperformancengs_b200/csrc/ngscov_hd.h"
+#include "../include/ngscov.h"
+#include "../oracle/ngscov_oracle.h"
+
+struct HostMem {
+	const uint8_t *base; int64_t n;
+	int64_t size() const { return n; }
+	uint32_t u32(int64_t o) const { uint32_t v; memcpy(&v, base + o, 4); return v; }
+	uint32_t u8(int64_t o) const { return base[o]; }
+	void hdr(int64_t o, ngs_hdr &h) const
+	{
+		h.block_size = (int32_t)u32(o); h.ref_id = (int32_t)u32(o + 4); h.pos = (int32_t)u32(o + 8);
+		uint32_t a = u32(o + 12), b = u32(o + 16);
+		h.l_qname = a & 0xff; h.n_cigar = b & 0xffff; h.flag = b >> 16;
+		h.l_seq = (int32_t)u32(o + 20); h.next_ref_id = (int32_t)u32(o + 24); h.next_pos = (int32_t)u32(o + 28);
+	}
+	void hdr_lite(int64_t o, ngs_hdr &h) const { hdr(o, h); h.next_ref_id = h.next_pos = 0; }
+};
+struct HostSink {
+	std::vector<int> *diff; int *range_err;
+	void add2(uint64_t a, uint64_t b, int sign) { (*diff)[a] += sign; (*diff)[b] -= sign; }
+	void flag_range_error() { *range_err = 1; }
+};
+static long long exit_num(long long x) { return x == NGS_EXIT_INVALID ? 0 : x; }
+
+int main(int argc, char **argv)
+{
+	if (argc < 6) { fprintf(stderr, "usage: hd_check bam depth|wig window subchunk chunk\n"); return 2; }
+	const int mode = !strcmp(argv[2], "wig") ? 1 : 0;
+	const uint32_t W = (uint32_t)atoi(argv[3]);
+	int shift = 0; while ((1 << (shift + 1)) <= atoi(argv[4])) ++shift;
+	const int64_t chunk = atoll(argv[5]);
+	ora_bam bam;
+	if (ngscov_oracle_load_bam(argv[1], &bam)) { fprintf(stderr, "cannot load %s\n", argv[1]); return 2; }
+	ora_result ora;
+	if (ngscov_oracle_run(bam.records, bam.records_len, bam.n_ref, bam.ref_len, (const char *const *)bam.ref_name, mode, W, 1, &ora)) { fprintf(stderr, "oracle failed\n"); return 2; }
+
+	/* geometry (whole genome) */
+	std::vector<ngs_seg> seg; std::vector<int32_t> c2s(bam.n_ref); std::vector<uint64_t> wb(bam.n_ref + 1, 0);
+	uint64_t elems = 0;
+	for (int i = 0; i < bam.n_ref; ++i) {
+		ngs_seg s; memset(&s, 0, sizeof s);
+		s.contig = i; s.clip_lo = 0; s.ref_len = bam.ref_len[i]; s.n_win = bam.ref_len[i] / W + 1; s.hard_end = 1;
+		s.lim = (uint32_t)std::min<uint64_t>((uint64_t)bam.ref_len[i] + NGSCOV_OVERHANG_PAD, NGS_POS_MASK);
+		s.base = elems; s.bins0 = wb[i]; wb[i + 1] = wb[i] + s.n_win;
+		elems += (uint64_t)s.lim + 1;
+		c2s[i] = i; seg.push_back(s);
+	}
+	std::vector<int> diff(elems, 0);
+	int range_err = 0;
+	ngs_walk_cfg cfg = { bam.n_ref, mode ? 0x4u : 0x704u, c2s.data(), seg.data() };
+	ngs_counts cnt = { 0, 0, 0, 0 };
+	long long mismatches = 0, walks = 0;
+
+	/* streamed pushes with carry, exactly as the library does it */
+	std::vector<uint8_t> buf(NGS_CARRY_MAX + chunk + 64);
+	uint8_t *data = buf.data() + NGS_CARRY_MAX;
+	long long entry_next = 0; std::vector<uint8_t> carry;
+	for (int64_t off = 0; off < (int64_t)bam.records_len || off == 0; off += chunk) {
+		const int64_t n = std::min<int64_t>(chunk, (int64_t)bam.records_len - off);
+		if (n <= 0) break;
+		memcpy(data, bam.records + off, n);
+		memcpy(data - carry.size(), carry.data(), carry.size());
+		HostMem mem = { data, n };
+		HostSink sink = { &diff, &range_err };
+		const int64_t n_sub = (n + (1ll << shift) - 1) >> shift;
+		std::vector<long long> entry(n_sub), ex(n_sub, 0);
+		for (int64_t c = 0; c < n_sub; ++c) {
+			const int64_t lo = c << shift, hi = std::min<int64_t>(lo + (1ll << shift), n);
+			entry[c] = c == 0 ? (entry_next < hi ? entry_next : NGS_NONE) : ngs_find_entry(cfg, mem, bam.ref_len, lo, hi);
+			if (entry[c] != NGS_NONE) { ex[c] = ngs_walk(cfg, mem, entry[c], hi, sink, +1, cnt); ++walks; }
+		}
+		/* verify + zipper repair */
+		for (;;) {
+			long long run = entry_next, bad = -1, expected = 0; int kind = 0;
+			for (int64_t c = 0; c < n_sub; ++c) {
+				const int64_t lo = c << shift, hi = std::min<int64_t>(lo + (1ll << shift), n);
+				const bool exp_in = run < hi;
+				int k = -1;
+				if (exp_in && c > 0 && run < lo) k = 1;
+				else if (exp_in ? entry[c] != run : entry[c] != NGS_NONE) k = 0;
+				else if (entry[c] != NGS_NONE && ex[c] == NGS_EXIT_INVALID) k = 1;
+				if (k >= 0) { bad = c; kind = k; expected = run; break; }
+				run = std::max(run, exit_num(ex[c]));
+			}
+			if (bad < 0) { entry_next = run; break; }
+			if (kind == 1) { fprintf(stderr, "hd_check: broken chain at sub-chunk %lld (chunk off %lld n %lld expected %lld entry %lld exit %lld e0 %lld)\n", bad, (long long)off, (long long)n, expected, entry[bad], ex[bad], entry_next); for (int64_t c=0;c<std::min<int64_t>(n_sub,6);++c) fprintf(stderr,"  c=%lld entry=%lld exit=%lld\n",(long long)c,entry[c],ex[c]); return 1; }
+			++mismatches;
+			ngs_counts sub = { 0, 0, 0, 0 };
+			long long c = bad, cur = expected;
+			for (;;) {
+				long long cc = cur >= n ? n_sub : (cur < 0 ? 0 : cur >> shift);
+				for (long long k = c; k < cc; ++k) if (entry[k] != NGS_NONE) {
+					ngs_walk(cfg, mem, entry[k], std::min<int64_t>((k + 1) << shift, n), sink, -1, sub); entry[k] = NGS_NONE; ex[k] = 0; }
+				if (cc >= n_sub || entry[cc] == cur) break;
+				const int64_t hi = std::min<int64_t>((cc + 1) << shift, n);
+				if (entry[cc] != NGS_NONE) ngs_walk(cfg, mem, entry[cc], hi, sink, -1, sub);
+				entry[cc] = cur; ex[cc] = ngs_walk(cfg, mem, cur, hi, sink, +1, cnt);
+				c = cc + 1; cur = (ex[cc] == NGS_EXIT_INVALID || ex[cc] >= NGS_EXIT_INF) ? n : ex[cc];
+			}
+			cnt.records -= sub.records; cnt.kept -= sub.kept; cnt.m_ops -= sub.m_ops; cnt.cigar_words -= sub.cigar_words;
+		}
+		/* finalize */
+		carry.clear();
+		if (entry_next >= NGS_EXIT_INF) {
+			const long long o = entry_next - NGS_EXIT_INF - (1ll << 40);
+			carry.assign(data + o, data + n);
+			entry_next = -(long long)carry.size();
+		} else entry_next -= n;
+	}
+	if (entry_next != 0 || range_err) { fprintf(stderr, "hd_check: truncated (%lld) or range error (%d)\n", entry_next, range_err); return 1; }
+
+	/* scan + runs + bins + text */
+	std::string bed, dep, wig, chs;
+	char tmp[512];
+	std::vector<uint64_t> bins(wb[bam.n_ref], 0);
+	for (int i = 0; i < bam.n_ref; ++i) {
+		const ngs_seg &s = seg[i];
+		const std::string nm = bam.ref_name[i];
+		int depth = 0; uint32_t last = 0;
+		uint64_t *b = bins.data() + s.bins0;
+		auto add = [b](uint32_t k, int64_t v) { b[k] += (uint64_t)v; };
+		for (uint64_t p = 0; p <= s.lim; ++p) {
+			const int d = diff[s.base + p];
+			if (!d) continue;
+			if (depth != 0) {
+				char *q = tmp; memcpy(q, nm.data(), nm.size()); q += nm.size(); *q++ = '\t';
+				q += ngs_put_u32(q, last); *q++ = '\t'; q += ngs_put_u32(q, (uint32_t)p); *q++ = '\t'; q += ngs_put_i32(q, depth); *q++ = '\n';
+				bed.append(tmp, q - tmp);
+				ngs_bin_run(mode, last, (uint32_t)p, depth, W, s.ref_len, s.n_win, add);
+			}
+			depth += d; last = (uint32_t)p;
+		}
+		if (depth != 0) { fprintf(stderr, "hd_check: depth does not return to zero on %s\n", nm.c_str()); return 1; }
+		wig += "variableStep chrom=" + nm + " span=" + std::to_string((int)W) + "\n";
+		for (uint32_t k = 0; k < s.n_win; ++k) {
+			const uint64_t h = ngs_hundredths((double)(long long)b[k] / (double)W);
+			const uint64_t ws = (uint64_t)k * W, we = std::min<uint64_t>(ws + W, s.ref_len);
+			char *q = tmp; memcpy(q, nm.data(), nm.size()); q += nm.size(); *q++ = '\t';
+			q += ngs_put_u32(q, (uint32_t)ws); *q++ = '\t'; q += ngs_put_u32(q, (uint32_t)we); *q++ = '\t'; q += ngs_put_f2(q, h); *q++ = '\n';
+			dep.append(tmp, q - tmp);
+			if (b[k]) { q = tmp; q += ngs_put_u32(q, (uint32_t)ws); *q++ = '\t'; q += ngs_put_f2(q, h); *q++ = '\n'; wig.append(tmp, q - tmp); }
+		}
+		chs += nm + "\t" + std::to_string((int)s.ref_len) + "\n";
+	}
+	int fail = 0;
+	auto cmp = [&](const char *what, const std::string &got, const char *ref, size_t len) {
+		if (got.size() != len || memcmp(got.data(), ref, len)) { fprintf(stderr, "hd_check: %s differs (%zu vs %zu bytes)\n", what, got.size(), len); fail = 1; }
+	};
+	if (mode == 0) { cmp("bedGraph", bed, ora.bedgraph, ora.bedgraph_len); cmp("depth", dep, ora.depth, ora.depth_len); }
+	cmp("wig", wig, ora.wig, ora.wig_len); cmp("chromSize", chs, ora.chromsize, ora.chromsize_len);
+	if (cnt.records != ora.n_records || cnt.kept != ora.n_kept || cnt.m_ops != ora.n_mops) {
+		fprintf(stderr, "hd_check: counters differ: records %llu/%llu kept %llu/%llu mops %llu/%llu\n",
+		        (unsigned long long)cnt.records, (unsigned long long)ora.n_records, (unsigned long long)cnt.kept, (unsigned long long)ora.n_kept,
+		        (unsigned long long)cnt.m_ops, (unsigned long long)ora.n_mops);
+		fail = 1;
+	}
+	printf("hd_check %s mode=%d W=%u S=%d chunk=%lld: records=%llu walks=%lld repaired=%lld %s\n", argv[1], mode, W, 1 << shift,
+	       (long long)chunk, (unsigned long long)cnt.records, walks, mismatches, fail ? "FAIL" : "ok");
+	return fail;
+}

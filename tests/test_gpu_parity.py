@@ -1,0 +1,124 @@
+"""GPU parity tests: libngscov_cuda (through the C ABI) against the CPU oracle, bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import bamutil
+
+pytestmark = pytest.mark.gpu
+
+MODES = [(0, "depth"), (1, "wig")]
+
+
+def run_engine(names, lens, recs, mode, window, emit_wig=True, staging_bytes=0, chunk=None, device_resident=False):
+    from highperformancengs_b200 import CoverageEngine
+    eng = CoverageEngine(names, lens, mode=mode, window=window, emit_wig=emit_wig, staging_bytes=staging_bytes)
+    try:
+        if device_resident:
+            import torch
+            t = torch.from_numpy(np.ascontiguousarray(recs)).cuda()
+            torch.cuda.synchronize()
+            eng.push_device(t.data_ptr(), t.numel(), last=True)
+        else:
+            eng.push_host(recs, last=True)
+        eng.finish()
+        out = {"bedgraph": eng.output(0) if mode == 0 else b"", "depth": eng.output(1) if mode == 0 else b"",
+               "wig": eng.output(2) if (mode == 1 or emit_wig) else b"", "chromsize": eng.output(3) if (mode == 1 or emit_wig) else b""}
+        out["stats"] = eng.stats()
+        out["runs"] = eng.runs()
+        return out
+    finally:
+        eng.close()
+
+
+def check(got, exp, mode, what):
+    for k in (("bedgraph", "depth", "wig", "chromsize") if mode == 0 else ("wig", "chromsize")):
+        assert got[k] == exp[k], f"{what}: {k} differs ({len(got[k])} vs {len(exp[k])} bytes)"
+    assert got["stats"]["records"] == exp["n_records"], what
+    assert got["stats"]["kept"] == exp["n_kept"], what
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+@pytest.mark.parametrize("case", ["toy", "quirk"])
+@pytest.mark.parametrize("window", [1, 7, 10, 25, 20000])
+def test_small_cases(oracle, mode, mname, case, window):
+    names, lens, reads = bamutil.toy_case() if case == "toy" else bamutil.quirk_case()
+    recs = bamutil.records(reads)
+    exp = oracle.run(recs, names, lens, mode, window)
+    got = run_engine(names, lens, recs, mode, window)
+    check(got, exp, mode, f"{case} {mname} w={window}")
+
+
+@pytest.mark.parametrize("mode,mname", MODES)
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("window", [150, 999, 1000, 20000])
+def test_random_cases(oracle, mode, mname, seed, window):
+    names, lens, reads = bamutil.random_case(seed)
+    recs = bamutil.records(reads, seq=(seed != 2))
+    exp = oracle.run(recs, names, lens, mode, window)
+    got = run_engine(names, lens, recs, mode, window)
+    check(got, exp, mode, f"random{seed} {mname} w={window}")
+
+
+@pytest.mark.parametrize("staging", [4096, 70000])
+@pytest.mark.parametrize("sub", ["64", "512"])
+def test_straddling_pushes(oracle, monkeypatch, staging, sub):
+    """records cut by push boundaries (carry path) and tiny sub-chunks (speculation + repair path)"""
+    monkeypatch.setenv("NGSCOV_SUBCHUNK", sub)
+    names, lens, reads = bamutil.random_case(7, n_reads=4000)
+    recs = bamutil.records(reads)
+    exp = oracle.run(recs, names, lens, 0, 500)
+    got = run_engine(names, lens, recs, 0, 500, staging_bytes=staging)
+    check(got, exp, 0, f"straddle staging={staging} sub={sub}")
+
+
+def test_empty_input(oracle):
+    names, lens = [b"chrA", b"chrB"], [1000, 20000]
+    recs = np.zeros(0, dtype=np.uint8)
+    for mode, _ in MODES:
+        exp = oracle.run(recs, names, lens, mode, 300)
+        got = run_engine(names, lens, recs, mode, 300)
+        check(got, exp, mode, "empty")
+
+
+@pytest.mark.parametrize("config,scale,window", [(1, 0.05, 20000), (2, 0.0005, 20000), (4, 0.01, 100), (4, 0.01, 20000), (5, 0.002, 20000)])
+@pytest.mark.parametrize("resident", [False, True])
+def test_generator_configs(oracle, config, scale, window, resident):
+    from highperformancengs_b200.gen import Generator
+    g = Generator(config, scale=scale)
+    recs = g.records()
+    mode = 1 if config == 4 else 0
+    exp = oracle.run(recs, g.names, g.lens, mode, window)
+    got = run_engine(g.names, g.lens, recs, mode, window, device_resident=resident)
+    check(got, exp, mode, f"config{config} scale={scale} w={window} resident={resident}")
+    assert got["stats"]["records"] == g.n_reads
+
+
+def test_truncated_stream_is_an_error(oracle):
+    from highperformancengs_b200 import NgscovError
+    names, lens, reads = bamutil.toy_case()
+    recs = bamutil.records(reads)
+    with pytest.raises(NgscovError) as e:
+        run_engine(names, lens, recs[:-7], 0, 10)
+    assert e.value.code == -4
+
+
+def test_overhang_beyond_pad_is_range_error(oracle):
+    from highperformancengs_b200 import NgscovError
+    names, lens = [b"c"], [1000]
+    recs = bamutil.records([(0, 900, 0, "100M200000N50M")], seq=False)
+    with pytest.raises(NgscovError) as e:
+        run_engine(names, lens, recs, 0, 100)
+    assert e.value.code == -5
+
+
+def test_small_overhang_matches_oracle(oracle):
+    """a read hanging over the contig end by less than a window is defined in the reference: bedGraph
+    coordinates run past the end, bins stop at the end"""
+    names, lens = [b"c"], [1000]
+    recs = bamutil.records([(0, 100, 0, "50M"), (0, 950, 0, "80M"), (0, 960, 16, "60M")], seq=False)
+    for mode, _ in MODES:
+        exp = oracle.run(recs, names, lens, mode, 300)
+        got = run_engine(names, lens, recs, mode, 300)
+        check(got, exp, mode, "overhang")
