@@ -48,6 +48,7 @@ SYMBOLS = {
     "ngscov_staging": (C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "ngscov_push": (C.c_int, [_H, C.c_int, C.c_size_t, C.c_int]),
     "ngscov_staging_wait": (C.c_int, [_H, C.c_int]),
+    "ngscov_push_host": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_int]),
     "ngscov_push_device": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_int]),
     "ngscov_finish_runs": (C.c_int, [_H]),
     "ngscov_halo_get": (C.c_int, [_H, C.POINTER(Halo)]),

@@ -320,7 +320,7 @@ extern "C" int ngscov_staging(ngscov_t *h, int idx, void **pinned, size_t *cap)
 	CK(cudaSetDevice(h->device));
 	if (!h->h_stage[idx]) {
 		CK(cudaHostAlloc((void **)&h->h_stage[idx], h->stage_cap, cudaHostAllocDefault));
-		CK(cudaMalloc((void **)&h->d_chunk[idx], NGS_HEADROOM + h->stage_cap + 256));
+		if (!h->d_chunk[idx]) CK(cudaMalloc((void **)&h->d_chunk[idx], NGS_HEADROOM + h->stage_cap + 256));
 	}
 	*pinned = h->h_stage[idx]; *cap = h->stage_cap;
 	return 0;
@@ -410,7 +410,7 @@ static int pick_shift(ngscov *h, int32_t first_block_size)
 	int64_t rec = (int64_t)first_block_size + 4;
 	if (rec < 36) rec = 36;
 	if (rec > 4096) rec = 4096;
-	int64_t want = rec * 10; int s = 9;                       /* ~10 records per sub-chunk, 512 B .. 32 KiB */
+	int64_t want = rec * 20; int s = 9;                       /* ~20 records per sub-chunk, 512 B .. 32 KiB */
 	while (((int64_t)1 << s) < want && s < 15) ++s;
 	h->shift = s;
 	return 0;
@@ -457,6 +457,55 @@ extern "C" int ngscov_push(ngscov_t *h, int idx, size_t nbytes, int flags)
 	k_place_carry<<<1, 256, 0, h->s_main>>>(data, h->d_st, h->d_carry);
 	h->stats.launches += 1;
 	return submit_chunk(h, data, (int64_t)nbytes, true, 0);
+}
+
+static int ensure_chunk(ngscov *h, int idx)
+{
+	if (!h->d_chunk[idx]) CK(cudaMalloc((void **)&h->d_chunk[idx], NGS_HEADROOM + h->stage_cap + 256));
+	return 0;
+}
+
+static int issue_h2d(ngscov *h, int idx, const uint8_t *src, size_t m)
+{
+	CK(cudaStreamWaitEvent(h->s_copy, h->ev_finalized, 0));
+	CK(cudaEventRecord(next_event(h->ev_cp, h->n_cp), h->s_copy));
+	CK(cudaMemcpyAsync(h->d_chunk[idx] + NGS_HEADROOM, src, m, cudaMemcpyHostToDevice, h->s_copy));
+	CK(cudaEventRecord(next_event(h->ev_cp, h->n_cp), h->s_copy));
+	CK(cudaEventRecord(h->ev_h2d[idx], h->s_copy));
+	return 0;
+}
+
+/* Stream a caller-owned host buffer (ideally pinned) through the two device chunk buffers: the copy of
+ * chunk k+1 overlaps the ingest of chunk k.  Records may straddle chunks and calls. */
+extern "C" int ngscov_push_host(ngscov_t *h, const void *host, size_t nbytes, int flags)
+{
+	if (!h || (!host && nbytes)) return NGSCOV_EINVAL;
+	if (h->runs_done || h->last_pushed) return NGSCOV_ESTATE;
+	if (h->sticky_err) return h->sticky_err;
+	CK(cudaSetDevice(h->device));
+	int r;
+	if ((r = ensure_chunk(h, 0)) || (r = ensure_chunk(h, 1))) return r;
+	if (flags & NGSCOV_PUSH_LAST) { h->last_pushed = true; h->last_flags = flags; }
+	h->stats.stream_bytes += nbytes;
+	if (nbytes == 0) return resolve_pending(h);
+	const uint8_t *src = (const uint8_t *)host;
+	if (!h->shift) pick_shift(h, *(const int32_t *)src);
+	if ((r = resolve_pending(h))) return r;
+	const size_t cap = h->stage_cap;
+	const size_t nchunks = (nbytes + cap - 1) / cap;
+	int idx = 0;
+	if ((r = issue_h2d(h, idx, src, std::min(cap, nbytes)))) return r;
+	for (size_t k = 0; k < nchunks; ++k, idx ^= 1) {
+		const size_t off = k * cap, m = std::min(cap, nbytes - off);
+		if ((r = resolve_pending(h))) return r;                      /* chunk k-1 verified, its buffer is free */
+		if (k + 1 < nchunks && (r = issue_h2d(h, idx ^ 1, src + off + m, std::min(cap, nbytes - off - m)))) return r;
+		uint8_t *data = h->d_chunk[idx] + NGS_HEADROOM;
+		CK(cudaStreamWaitEvent(h->s_main, h->ev_h2d[idx], 0));
+		k_place_carry<<<1, 256, 0, h->s_main>>>(data, h->d_st, h->d_carry);
+		h->stats.launches += 1;
+		if ((r = submit_chunk(h, data, (int64_t)m, true, 0))) return r;
+	}
+	return 0;
 }
 
 extern "C" int ngscov_push_device(ngscov_t *h, const void *dev_records, size_t nbytes, int flags)

@@ -255,18 +255,18 @@ NGS_HD int64_t ngs_walk(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o, int6
 }
 
 /* Speculative entry search in [lo, hi): first offset whose record and the `depth-1` records chained
- * after it all look plausible.  NGS_NONE if there is none (or it cannot be checked inside the chunk). */
+ * after it all look plausible.  NGS_NONE if there is none (or it cannot be checked inside the chunk).
+ * mem.next_candidate(o, end, n_ref) returns the first offset in [o, end) whose block_size and refID
+ * fields are in range (a tight, convergent byte scan), or NGS_NONE. */
 template <class Mem>
 NGS_HD int64_t ngs_find_entry(const ngs_walk_cfg &cfg, const Mem &mem, const uint32_t *ref_len, int64_t lo, int64_t hi)
 {
 	const int64_t n = mem.size();
-	for (int64_t o = lo; o < hi; ++o) {
-		if (o + 36 > n) return NGS_NONE;
-		/* cheap prefilter: block_size and refID ranges */
-		const uint32_t bs = mem.u32(o);
-		if (bs - 32u > NGS_MAX_BS - 32u) continue;
-		const uint32_t rid = mem.u32(o + 4);
-		if (rid + 1u > (uint32_t)cfg.n_ref) continue;
+	const int64_t end = hi < n - 35 ? hi : n - 35;            /* a candidate needs its 36 header bytes inside the chunk */
+	int64_t o = lo;
+	for (;;) {
+		o = mem.next_candidate(o, end, (uint32_t)cfg.n_ref);
+		if (o == NGS_NONE) return NGS_NONE;
 		int64_t c = o; int ok = 1;
 		for (int depth = 0; depth < 3; ++depth) {
 			ngs_hdr h;
@@ -278,8 +278,8 @@ NGS_HD int64_t ngs_find_entry(const ngs_walk_cfg &cfg, const Mem &mem, const uin
 			c += 4 + (int64_t)h.block_size;
 		}
 		if (ok) return o;
+		++o;
 	}
-	return NGS_NONE;
 }
 
 #endif

@@ -72,6 +72,24 @@ struct DevMem {
 		const uintptr_t a = (uintptr_t)(base + o);
 		return (__ldg((const uint32_t *)(a & ~(uintptr_t)3)) >> ((a & 3) * 8)) & 0xff;
 	}
+	/* first offset in [o, end) with 32 <= block_size <= NGS_MAX_BS and -1 <= refID < n_ref: a sliding
+	 * three-word window, one aligned load per four candidate bytes */
+	__device__ __forceinline__ int64_t next_candidate(int64_t o, int64_t end, uint32_t n_ref) const
+	{
+		if (o >= end) return NGS_NONE;
+		const uintptr_t a = (uintptr_t)(base + o);
+		const uint32_t *p = (const uint32_t *)(a & ~(uintptr_t)3);
+		uint32_t sh = (uint32_t)(a & 3) * 8;
+		uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+		p += 3;
+		for (;;) {
+			const uint32_t bs = __funnelshift_r(w0, w1, sh), rid = __funnelshift_r(w1, w2, sh);
+			if (bs - 32u <= NGS_MAX_BS - 32u && rid + 1u <= n_ref) return o;
+			if (++o >= end) return NGS_NONE;
+			sh += 8;
+			if (sh == 32) { sh = 0; w0 = w1; w1 = w2; w2 = __ldg(p++); }
+		}
+	}
 	/* first 24 bytes of a record with two (sometimes three) 128-bit loads */
 	__device__ __forceinline__ void hdr_lite(int64_t o, ngs_hdr &h) const
 	{
@@ -421,13 +439,13 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS) k_scan_runs(ScanArgs A)
 	__shared__ long long s_wsum[8]; __shared__ unsigned int s_wcnt[8]; __shared__ unsigned int s_wlast[8];
 	__shared__ unsigned long long s_tile_id;
 	__shared__ long long s_ex_sum; __shared__ unsigned long long s_ex_cnt; __shared__ unsigned int s_ex_last;
-	__shared__ unsigned long long s_nruns; __shared__ int s_maxd, s_mind;
-	__shared__ unsigned long long s_firstrun, s_lastrun;
+	__shared__ long long s_bk[8], s_bv[8];
+	__shared__ unsigned int s_wr[8]; __shared__ int s_wmax[8], s_wmin[8];
+	__shared__ unsigned long long s_rfirst[8], s_rlast[8];
 
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 	if (t == 0) {
 		s_tile_id = atomicAdd(&A.st->scan_ticket, 1ull);
-		s_nruns = 0; s_maxd = 0; s_mind = 0; s_firstrun = ~0ull; s_lastrun = 0;
 	}
 	__syncthreads();
 	const uint64_t tile = s_tile_id;
@@ -572,19 +590,55 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS) k_scan_runs(ScanArgs A)
 				depth += d[i]; last = pos + 1; ++rec;
 			}
 		}
-		if (bacc.k >= 0 && bacc.acc) atomicAdd(bacc.bins + bacc.k, (unsigned long long)bacc.acc);
 	}
-	/* block-aggregate the statistics */
-	if (my_runs) {
-		atomicAdd(&s_nruns, (unsigned long long)my_runs);
-		atomicMax(&s_maxd, my_max); atomicMin(&s_mind, my_min);
-		atomicMin(&s_firstrun, my_first); atomicMax(&s_lastrun, my_last);
+	/* ---- warp- then block-level aggregation of the pending window contribution and the statistics
+	 * (one global atomic per distinct window per tile instead of one per thread) */
+	{
+		const unsigned full = 0xffffffffu;
+		const bool has = bacc.k >= 0 && bacc.acc != 0;
+		const unsigned hm = __ballot_sync(full, has);
+		long long wk = -1, wv = 0;
+		if (hm) {
+			const int leader = __ffs(hm) - 1;
+			const long long k0 = __shfl_sync(full, bacc.k, leader);
+			if (__all_sync(full, !has || bacc.k == k0)) {
+				long long v = has ? bacc.acc : 0;
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+				wk = k0; wv = v;
+			} else if (has) atomicAdd(bacc.bins + bacc.k, (unsigned long long)bacc.acc);
+		}
+		const unsigned rm = __ballot_sync(full, my_runs != 0);
+		const unsigned wr = __reduce_add_sync(full, my_runs);
+		const int wmax = __reduce_max_sync(full, my_max), wmin = __reduce_min_sync(full, my_min);
+		unsigned long long wfirst = ~0ull, wlast = 0;
+		if (rm) {
+			wfirst = __shfl_sync(full, my_first, __ffs(rm) - 1);
+			wlast = __shfl_sync(full, my_last, 31 - __clz(rm));
+		}
+		if (lane == 0) {
+			s_bk[warp] = wk; s_bv[warp] = wv;
+			s_wr[warp] = wr; s_wmax[warp] = wmax; s_wmin[warp] = wmin; s_rfirst[warp] = wfirst; s_rlast[warp] = wlast;
+		}
 	}
 	__syncthreads();
-	if (t == 0 && s_nruns) {
-		atomicAdd(&A.st->n_runs, s_nruns);
-		atomicMax(&A.st->max_depth, s_maxd); atomicMin(&A.st->min_depth, s_mind);
-		atomicMin(&A.st->first_run, s_firstrun); atomicMax(&A.st->last_run, s_lastrun);
+	if (t == 0) {
+		long long ck = -1, cv = 0;
+		unsigned long long nr = 0, fr = ~0ull, lr = 0; int mx = 0, mn = 0;
+		for (int w = 0; w < 8; ++w) {
+			if (s_bk[w] >= 0) {
+				if (s_bk[w] == ck) cv += s_bv[w];
+				else { if (ck >= 0 && cv) atomicAdd(bacc.bins + ck, (unsigned long long)cv); ck = s_bk[w]; cv = s_bv[w]; }
+			}
+			nr += s_wr[w]; mx = s_wmax[w] > mx ? s_wmax[w] : mx; mn = s_wmin[w] < mn ? s_wmin[w] : mn;
+			fr = s_rfirst[w] < fr ? s_rfirst[w] : fr; lr = s_rlast[w] > lr ? s_rlast[w] : lr;
+		}
+		if (ck >= 0 && cv) atomicAdd(bacc.bins + ck, (unsigned long long)cv);
+		if (nr) {
+			atomicAdd(&A.st->n_runs, nr);
+			atomicMax(&A.st->max_depth, mx); atomicMin(&A.st->min_depth, mn);
+			atomicMin(&A.st->first_run, fr); atomicMax(&A.st->last_run, lr);
+		}
 	}
 }
 

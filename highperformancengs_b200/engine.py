@@ -88,6 +88,11 @@ class CoverageEngine:
             self.push(idx, m, last=last and off >= n, truncated_ok=truncated_ok)
             idx ^= 1
 
+    def push_host_ptr(self, host_ptr, nbytes, last=True, truncated_ok=False):
+        """Stream nbytes at host address host_ptr (pinned memory preferred) -- ngscov_push_host."""
+        flags = (PUSH_LAST if last else 0) | (PUSH_TRUNCATED_OK if truncated_ok else 0)
+        self._check(self.lib.ngscov_push_host(self.h, C.c_void_p(host_ptr), nbytes, flags), "ngscov_push_host")
+
     def push_device(self, dev_ptr, nbytes, last=True):
         self._check(self.lib.ngscov_push_device(self.h, C.c_void_p(dev_ptr), nbytes, PUSH_LAST if last else 0), "ngscov_push_device")
 

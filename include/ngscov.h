@@ -6,7 +6,7 @@
  *
  *   ngscov_create        DataBuf + hashtbl_create x2 + calloc(Bins)   bam2depth.c:15-19,326-330
  *                        globalArgs (window, wig)                     bam2depth.c:21-29,259-297
- *   ngscov_staging/push  bam_fetch -> bam_iter_read -> bam_read1 -> fetch_func callback
+ *   ngscov_staging/push/push_host  bam_fetch -> bam_iter_read -> bam_read1 -> fetch_func callback
  *                        samtools bam_index.c:682-726, bam.c:191-223; bam2depth.c:86-110, bam2wig.c:84-109
  *                        (type bam_fetch_f, samtools bam.h:627) + insertInt2Hash bam2depth.c:72-84
  *   ngscov_finish_runs   union_hashed_keys hashtbl.c:275-297 + the sweep of hash2BedGraph
@@ -131,6 +131,11 @@ int ngscov_staging(ngscov_t *h, int idx, void **pinned, size_t *cap);
  * are queued.  Records may straddle pushes.  The buffer may be refilled after ngscov_staging_wait. */
 int ngscov_push(ngscov_t *h, int idx, size_t nbytes, int flags);
 int ngscov_staging_wait(ngscov_t *h, int idx);
+
+/* Submit a caller-owned host buffer (pinned memory gives full PCIe speed).  The library streams it through
+ * its two device chunk buffers, overlapping the copy of one chunk with the ingest of the previous one.
+ * Records may straddle chunks and calls.  Returns when every chunk has been queued. */
+int ngscov_push_host(ngscov_t *h, const void *host_records, size_t nbytes, int flags);
 
 /* Submit records that already live in device memory (whole records only: the range must start and
  * end on record boundaries).  Used when the inflated stream is resident in HBM. */

@@ -31,6 +31,11 @@ struct HostMem {
 		h.l_seq = (int32_t)u32(o + 20); h.next_ref_id = (int32_t)u32(o + 24); h.next_pos = (int32_t)u32(o + 28);
 	}
 	void hdr_lite(int64_t o, ngs_hdr &h) const { hdr(o, h); h.next_ref_id = h.next_pos = 0; }
+	int64_t next_candidate(int64_t o, int64_t end, uint32_t n_ref) const
+	{
+		for (; o < end; ++o) if (u32(o) - 32u <= NGS_MAX_BS - 32u && u32(o + 4) + 1u <= n_ref) return o;
+		return NGS_NONE;
+	}
 };
 struct HostSink {
 	std::vector<int> *diff; int *range_err;
