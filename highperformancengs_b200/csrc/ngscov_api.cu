@@ -594,6 +594,7 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 		A.rec_base = h->d_rec_base; A.n_seg = (uint32_t)h->seg.size();
 		A.bins = h->d_bins; A.window = h->cfg.window; A.variant = h->cfg.mode == NGSCOV_MODE_WIG ? 1 : 0;
 		A.rezero = 1; A.st = h->d_st;
+		A.debug = getenv("NGSCOV_DEBUG_SCAN") ? atoi(getenv("NGSCOV_DEBUG_SCAN")) : 0;
 		k_scan_runs<<<(unsigned)h->n_tiles, NGS_SCAN_THREADS, 0, h->s_main>>>(A);
 		h->stats.launches += 1;
 		CK(cudaGetLastError());

@@ -144,6 +144,12 @@ NGS_HD uint32_t ngs_put_u32(Ptr dst, uint32_t v)
 	for (uint32_t i = n; i-- > 0;) { uint32_t q = v / 10u; dst[i] = (char)('0' + (v - q * 10u)); v = q; }
 	return n;
 }
+/* same with the digit count already known */
+template <class Ptr>
+NGS_HD void ngs_put_u32n(Ptr dst, uint32_t v, uint32_t n)
+{
+	for (uint32_t i = n; i-- > 0;) { uint32_t q = v / 10u; dst[i] = (char)('0' + (v - q * 10u)); v = q; }
+}
 template <class Ptr>
 NGS_HD uint32_t ngs_put_i32(Ptr dst, int32_t v)
 {
@@ -242,16 +248,23 @@ NGS_HD int64_t ngs_walk(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o, int6
                         Sink &sink, int sign, ngs_counts &cnt)
 {
 	const int64_t n = mem.size();
-	while (o < hi) {
-		ngs_hdr h;
-		if (o + 36 > n) return NGS_EXIT_PARTIAL(o);
-		mem.hdr_lite(o, h);
+	if (o >= hi) return o;
+	if (o + 36 > n) return NGS_EXIT_PARTIAL(o);
+	ngs_hdr h;
+	mem.hdr_lite(o, h);
+	for (;;) {
 		if (!ngs_hdr_valid(h, cfg.n_ref)) return NGS_EXIT_INVALID;
 		if (o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar > n) return NGS_EXIT_PARTIAL(o);
+		/* the next header is requested before this record is decoded: two loads in flight per chain */
+		const int64_t nx = o + 4 + (int64_t)h.block_size;
+		const bool more = nx < hi, have = more && nx + 36 <= n;
+		ngs_hdr hn = h;
+		if (have) mem.hdr_lite(nx, hn);
 		ngs_decode_record(cfg, mem, o, h, sink, sign, cnt);
-		o += 4 + (int64_t)h.block_size;
+		if (!more) return nx;
+		if (!have) return NGS_EXIT_PARTIAL(nx);
+		o = nx; h = hn;
 	}
-	return o;
 }
 
 /* Speculative entry search in [lo, hi): first offset whose record and the `depth-1` records chained

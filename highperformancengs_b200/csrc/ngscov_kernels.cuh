@@ -410,6 +410,7 @@ struct ScanArgs {
 	unsigned long long *bins;        /* window bins (concatenated contigs) */
 	uint32_t window; int variant;
 	int rezero;
+	int debug;                       /* bit 0: skip the look-back wait (timing experiments only, wrong results) */
 	ngs_dev_state *st;
 };
 
@@ -435,31 +436,32 @@ struct BinAcc {   /* per-thread pending (bin, value): consecutive runs of a thre
 
 __global__ void __launch_bounds__(NGS_SCAN_THREADS) k_scan_runs(ScanArgs A)
 {
-	__shared__ int s_tile[NGS_SCAN_THREADS * 20];        /* 16 ints + 4 pad per thread: conflict-free 128-bit reads */
+	__shared__ __align__(16) int s_tile[NGS_TILE / 2 + NGS_TILE];   /* phase 1: 256 x (16 + 4 pad) ints for the transposition (conflict-free
+	                                                                    128-bit reads); phase 2: compact boundary list (u16 pos + i32 depth) */
 	__shared__ long long s_wsum[8]; __shared__ unsigned int s_wcnt[8]; __shared__ unsigned int s_wlast[8];
-	__shared__ unsigned long long s_tile_id;
-	__shared__ long long s_ex_sum; __shared__ unsigned long long s_ex_cnt; __shared__ unsigned int s_ex_last;
+	__shared__ unsigned int s_lb_inc[8], s_lb_last[8]; __shared__ long long s_lb_sum[8]; __shared__ unsigned long long s_lb_cnt[8];
 	__shared__ long long s_bk[8], s_bv[8];
 	__shared__ unsigned int s_wr[8]; __shared__ int s_wmax[8], s_wmin[8];
-	__shared__ unsigned long long s_rfirst[8], s_rlast[8];
+	__shared__ unsigned int s_rfirst[8], s_rlast[8];
 
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	if (t == 0) {
-		s_tile_id = atomicAdd(&A.st->scan_ticket, 1ull);
-	}
-	__syncthreads();
-	const uint64_t tile = s_tile_id;
+	/* tile id = blockIdx.x: CTAs are dispatched in increasing block order, so every predecessor of a
+	 * resident tile is resident or finished and the look-back cannot starve (no ticket round trip) */
+	const uint64_t tile = blockIdx.x;
 	if (tile >= A.n_tiles) return;
+
+	/* coalesced 128-bit loads (striped) issued first; the segment lookup overlaps their latency */
+	int4 *gp = reinterpret_cast<int4 *>(A.diff + tile * (uint64_t)NGS_TILE);
+	int4 v4[4];
+	#pragma unroll
+	for (int j = 0; j < 4; ++j) v4[j] = gp[j * NGS_SCAN_THREADS + t];
 	const uint32_t si = A.tile2seg[tile];
 	const ngs_seg sg = A.seg[si];
-
-	/* coalesced 128-bit loads (striped), transpose through shared memory to 16 consecutive per thread */
-	int4 *gp = reinterpret_cast<int4 *>(A.diff + tile * (uint64_t)NGS_TILE);
+	/* transpose through shared memory to 16 consecutive elements per thread */
 	#pragma unroll
 	for (int j = 0; j < 4; ++j) {
 		const int q = j * NGS_SCAN_THREADS + t;              /* int4 index within the tile */
-		const int4 v = gp[q];
-		*reinterpret_cast<int4 *>(&s_tile[(q >> 2) * 20 + (q & 3) * 4]) = v;
+		*reinterpret_cast<int4 *>(&s_tile[(q >> 2) * 20 + (q & 3) * 4]) = v4[j];
 		if (A.rezero) gp[q] = make_int4(0, 0, 0, 0);
 	}
 	__syncthreads();
@@ -493,67 +495,65 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS) k_scan_runs(ScanArgs A)
 	}
 	/* exclusive prefix of this thread within the tile */
 	const int psum = __shfl_up_sync(0xffffffffu, isum, 1);
-	const unsigned int pcnt = __shfl_up_sync(0xffffffffu, icnt, 1), plast = __shfl_up_sync(0xffffffffu, ilast, 1);
+	const unsigned int pcnt = __shfl_up_sync(0xffffffffu, icnt, 1);
 	long long ex_sum = wpre_sum + (lane ? psum : 0);
 	unsigned int ex_cnt = wpre_cnt + (lane ? pcnt : 0);
-	unsigned int ex_last = lane ? (plast > wpre_last ? plast : wpre_last) : wpre_last;
 
 	/* tile-relative -> contig position of element 0 of this tile */
 	const uint32_t pos0 = sg.clip_lo + (uint32_t)((tile - sg.tile0) * NGS_TILE);
 	const uint32_t agg_lastb = tot_last ? pos0 + tot_last : 0;     /* 1 + contig position, 0 = none */
 
-	/* ---- decoupled look-back (warp 0) */
-	if (warp == 0) {
-		long long run_sum = 0; unsigned long long run_cnt = 0; unsigned int run_last = 0;
-		if (tile == 0) {
-			if (lane == 0) {
-				st_relaxed_u64(&A.stA[0], (NGS_ST_INC << 62) | (unsigned long long)tot_cnt);
-				st_relaxed_u64(&A.stB[0], (NGS_ST_INC << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
-			}
-		} else {
-			if (lane == 0) {
-				st_relaxed_u64(&A.stA[tile], (NGS_ST_AGG << 62) | (unsigned long long)tot_cnt);
-				st_relaxed_u64(&A.stB[tile], (NGS_ST_AGG << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
-			}
-			long long base = (long long)tile - 1;
-			for (;;) {
-				const long long idx = base - lane;
-				unsigned long long a = NGS_ST_INC << 62, b = NGS_ST_INC << 62;   /* virtual tiles before 0: inclusive zero */
-				if (idx >= 0) {
-					do {
-						a = ld_relaxed_u64(&A.stA[idx]);
-						b = ld_relaxed_u64(&A.stB[idx]);
-					} while ((a >> 62) == NGS_ST_EMPTY || (a >> 62) != (b >> 62));
-				}
-				const unsigned int incl_mask = __ballot_sync(0xffffffffu, (a >> 62) == NGS_ST_INC);
-				const int first_inc = incl_mask ? __ffs(incl_mask) - 1 : 32;        /* nearest inclusive predecessor */
-				/* combine lanes 0..first_inc (nearest first) */
-				long long vs = lane <= first_inc ? (long long)(int)(uint32_t)b : 0;
-				unsigned long long vc = lane <= first_inc ? (a & 0x3FFFFFFFFFFFFFFFull) : 0;
-				unsigned int vl = lane <= first_inc ? (unsigned int)((b >> 32) & 0x3FFFFFFFu) : 0;
-				#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) {
-					vs += __shfl_xor_sync(0xffffffffu, vs, o);
-					vc += __shfl_xor_sync(0xffffffffu, vc, o);
-				}
-				/* nearest (lowest lane) non-zero lastb wins */
-				const unsigned int has = __ballot_sync(0xffffffffu, vl != 0);
-				unsigned int near_l = 0;
-				if (has) near_l = __shfl_sync(0xffffffffu, vl, __ffs(has) - 1);
-				run_sum += vs; run_cnt += vc; if (run_last == 0) run_last = near_l;
-				if (first_inc < 32) break;
-				base -= 32;
-			}
-			if (lane == 0) {
-				const unsigned int inc_last = agg_lastb ? agg_lastb : run_last;
-				st_relaxed_u64(&A.stA[tile], (NGS_ST_INC << 62) | (run_cnt + tot_cnt));
-				st_relaxed_u64(&A.stB[tile], (NGS_ST_INC << 62) | ((unsigned long long)inc_last << 32) | (uint32_t)(int)(run_sum + tot_sum));
-			}
-		}
-		if (lane == 0) { s_ex_sum = run_sum; s_ex_cnt = run_cnt; s_ex_last = run_last; }
+	/* ---- decoupled look-back, block-wide: thread i inspects predecessor tile-1-i, so one round covers
+	 * 256 predecessors (with ~600 tiles in flight a warp-wide window needs ~19 dependent L2 round
+	 * trips per tile, which is what bounded this kernel; 256-wide needs 2-3) */
+	long long tile_sum = 0; unsigned long long tile_cnt = 0; unsigned int tile_last = 0;
+	if (t == 0) {
+		const unsigned long long stt = tile == 0 ? NGS_ST_INC : NGS_ST_AGG;
+		st_relaxed_u64(&A.stA[tile], (stt << 62) | (unsigned long long)tot_cnt);
+		st_relaxed_u64(&A.stB[tile], (stt << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
 	}
-	__syncthreads();
-	const long long tile_sum = s_ex_sum; const unsigned long long tile_cnt = s_ex_cnt; const unsigned int tile_last = s_ex_last;
+	if (tile > 0 && !(A.debug & 1)) {
+		long long base = (long long)tile - 1;
+		for (;;) {
+			const long long idx = base - t;
+			unsigned long long a = NGS_ST_INC << 62, b = NGS_ST_INC << 62;       /* virtual tiles before 0: inclusive zero */
+			if (idx >= 0) {
+				do {
+					a = ld_relaxed_u64(&A.stA[idx]);
+					b = ld_relaxed_u64(&A.stB[idx]);
+				} while ((a >> 62) == NGS_ST_EMPTY || (a >> 62) != (b >> 62));
+			}
+			const unsigned int im = __ballot_sync(0xffffffffu, (a >> 62) == NGS_ST_INC);
+			if (lane == 0) s_lb_inc[warp] = im ? (unsigned)(warp * 32 + __ffs(im) - 1) : 0xffffffffu;
+			__syncthreads();
+			unsigned int first_inc = 0xffffffffu;                                /* nearest inclusive predecessor (thread index) */
+			#pragma unroll
+			for (int w = 0; w < 8; ++w) first_inc = s_lb_inc[w] < first_inc ? s_lb_inc[w] : first_inc;
+			const bool incl = (unsigned)t <= first_inc;
+			long long vs = incl ? (long long)(int)(uint32_t)b : 0;
+			unsigned long long vc = incl ? (a & 0x3FFFFFFFFFFFFFFFull) : 0;
+			const unsigned int vl = incl ? (unsigned int)((b >> 32) & 0x3FFFFFFFu) : 0;
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) { vs += __shfl_xor_sync(0xffffffffu, vs, o); vc += __shfl_xor_sync(0xffffffffu, vc, o); }
+			const unsigned int has = __ballot_sync(0xffffffffu, vl != 0);
+			unsigned int near_l = 0;
+			if (has) near_l = __shfl_sync(0xffffffffu, vl, __ffs(has) - 1);      /* lowest lane = nearest tile */
+			if (lane == 0) { s_lb_sum[warp] = vs; s_lb_cnt[warp] = vc; s_lb_last[warp] = near_l; }
+			__syncthreads();
+			unsigned int rl = 0;
+			#pragma unroll
+			for (int w = 0; w < 8; ++w) { tile_sum += s_lb_sum[w]; tile_cnt += s_lb_cnt[w]; if (rl == 0) rl = s_lb_last[w]; }
+			if (tile_last == 0) tile_last = rl;
+			if (first_inc != 0xffffffffu) break;
+			base -= NGS_SCAN_THREADS;
+			__syncthreads();
+		}
+		if (t == 0) {
+			const unsigned int inc_last = agg_lastb ? agg_lastb : tile_last;
+			st_relaxed_u64(&A.stA[tile], (NGS_ST_INC << 62) | (tile_cnt + tot_cnt));
+			st_relaxed_u64(&A.stB[tile], (NGS_ST_INC << 62) | ((unsigned long long)inc_last << 32) | (uint32_t)(int)(tile_sum + tot_sum));
+		}
+	}
 	if (t == 0) {
 		if (tile == sg.tile0) A.rec_base[si] = tile_cnt;
 		if (tile == A.n_tiles - 1) {
@@ -563,32 +563,37 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS) k_scan_runs(ScanArgs A)
 	}
 	if (tot_cnt == 0) return;
 
-	/* ---- emit boundary records + bins */
-	int depth = (int)(tile_sum + ex_sum);
-	unsigned long long rec = tile_cnt + ex_cnt;
-	unsigned int last = ex_last ? pos0 + ex_last : tile_last;     /* 1 + contig position of previous boundary */
-	BinAcc bacc; bacc.bins = A.bins + sg.bins0; bacc.k = -1; bacc.acc = 0;
-	unsigned int my_runs = 0; int my_max = 0, my_min = 0;
-	unsigned long long my_first = ~0ull, my_last = 0;
+	/* ---- compact the tile's boundaries into shared memory (sparse pass, tiny body) ...
+	 * the transposition buffer is dead by now (every thread holds its 16 elements in registers and two
+	 * block barriers have passed), so it is reused for the compact (position, depth-before) list */
+	unsigned short *c_pos = reinterpret_cast<unsigned short *>(s_tile);              /* [4096] tile-relative position */
+	int *c_dep = s_tile + NGS_TILE / 2;                                               /* [4096] depth before the boundary */
 	if (tcnt) {
+		int depth = (int)(tile_sum + ex_sum);
+		unsigned int r = ex_cnt;
 		#pragma unroll
 		for (int i = 0; i < 16; ++i) {
-			if (d[i] != 0) {
-				const uint32_t pos = pos0 + (uint32_t)(t * 16 + i);
-				if (rec < A.run_cap) {
-					A.run_start[rec] = last ? last - 1 : 0;
-					A.run_end[rec] = pos;
-					A.run_depth[rec] = depth;
-				}
-				if (depth != 0) {
-					const uint32_t s = last ? last - 1 : 0;
-					ngs_bin_run(A.variant, s, pos, (int64_t)depth, A.window, sg.ref_len, sg.n_win, bacc);
-					++my_runs; my_max = depth > my_max ? depth : my_max; my_min = depth < my_min ? depth : my_min;
-					if (my_first == ~0ull) my_first = rec;
-					my_last = rec;
-				}
-				depth += d[i]; last = pos + 1; ++rec;
-			}
+			if (d[i] != 0) { c_pos[r] = (unsigned short)(t * 16 + i); c_dep[r] = depth; depth += d[i]; ++r; }
+		}
+	}
+	__syncthreads();
+	/* ---- ... then emit them densely: thread r handles record r, r+256, .. (coalesced stores) */
+	BinAcc bacc; bacc.bins = A.bins + sg.bins0; bacc.k = -1; bacc.acc = 0;
+	unsigned int my_runs = 0, my_first = 0xffffffffu, my_last = 0; int my_max = 0, my_min = 0;
+	const uint32_t W = A.window;
+	const uint32_t kt = pos0 / W;                                   /* window of the tile's first position */
+	const uint64_t wlo = (uint64_t)kt * W, whi = wlo + W - 1;        /* fast path: run inside [wlo, whi) and inside the contig */
+	for (unsigned int r = t; r < tot_cnt; r += NGS_SCAN_THREADS) {
+		const uint32_t pos = pos0 + c_pos[r];
+		const int depth = c_dep[r];
+		const uint32_t start = r ? pos0 + c_pos[r - 1] : (tile_last ? tile_last - 1 : 0);
+		const unsigned long long rec = tile_cnt + r;
+		if (rec < A.run_cap) { A.run_start[rec] = start; A.run_end[rec] = pos; A.run_depth[rec] = depth; }
+		if (depth != 0) {
+			if (start >= wlo && pos <= whi && pos <= sg.ref_len) bacc(kt, (int64_t)(pos - start) * depth);
+			else ngs_bin_run(A.variant, start, pos, (int64_t)depth, W, sg.ref_len, sg.n_win, bacc);
+			++my_runs; my_max = depth > my_max ? depth : my_max; my_min = depth < my_min ? depth : my_min;
+			my_first = r < my_first ? r : my_first; my_last = r;
 		}
 	}
 	/* ---- warp- then block-level aggregation of the pending window contribution and the statistics
@@ -608,14 +613,9 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS) k_scan_runs(ScanArgs A)
 				wk = k0; wv = v;
 			} else if (has) atomicAdd(bacc.bins + bacc.k, (unsigned long long)bacc.acc);
 		}
-		const unsigned rm = __ballot_sync(full, my_runs != 0);
 		const unsigned wr = __reduce_add_sync(full, my_runs);
 		const int wmax = __reduce_max_sync(full, my_max), wmin = __reduce_min_sync(full, my_min);
-		unsigned long long wfirst = ~0ull, wlast = 0;
-		if (rm) {
-			wfirst = __shfl_sync(full, my_first, __ffs(rm) - 1);
-			wlast = __shfl_sync(full, my_last, 31 - __clz(rm));
-		}
+		const unsigned wfirst = __reduce_min_sync(full, my_first), wlast = __reduce_max_sync(full, my_last);
 		if (lane == 0) {
 			s_bk[warp] = wk; s_bv[warp] = wv;
 			s_wr[warp] = wr; s_wmax[warp] = wmax; s_wmin[warp] = wmin; s_rfirst[warp] = wfirst; s_rlast[warp] = wlast;
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS) k_scan_runs(ScanArgs A)
 	__syncthreads();
 	if (t == 0) {
 		long long ck = -1, cv = 0;
-		unsigned long long nr = 0, fr = ~0ull, lr = 0; int mx = 0, mn = 0;
+		unsigned long long nr = 0; unsigned int fr = 0xffffffffu, lr = 0; int mx = 0, mn = 0;
 		for (int w = 0; w < 8; ++w) {
 			if (s_bk[w] >= 0) {
 				if (s_bk[w] == ck) cv += s_bv[w];
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS) k_scan_runs(ScanArgs A)
 		if (nr) {
 			atomicAdd(&A.st->n_runs, nr);
 			atomicMax(&A.st->max_depth, mx); atomicMin(&A.st->min_depth, mn);
-			atomicMin(&A.st->first_run, fr); atomicMax(&A.st->last_run, lr);
+			atomicMin(&A.st->first_run, tile_cnt + fr); atomicMax(&A.st->last_run, tile_cnt + lr);
 		}
 	}
 }
@@ -658,28 +658,46 @@ struct BedProducer {
 	const unsigned long long *rec_base; const ngs_seg *seg; uint32_t n_seg;
 	NameTable nt;
 	unsigned long long drop_idx, mod_idx; uint32_t mod_end;
-	struct Item { uint32_t s, e; int d; uint32_t ctg; };
-	__device__ __forceinline__ uint32_t seg_of(unsigned long long r) const
+	struct Item { uint32_t s, e; int d; uint32_t ctg; uint32_t nd; };     /* nd: digit counts packed 8 bits each */
+	struct Cache { unsigned long long lo, hi; uint32_t ctg, name_len; unsigned long long name8; };
+	__device__ __forceinline__ void init(Cache &c) const { c.lo = 1; c.hi = 0; c.ctg = 0; c.name_len = 0; c.name8 = 0; }
+	__device__ __forceinline__ void locate(unsigned long long r, Cache &c) const
 	{
 		uint32_t lo = 0, hi = n_seg;                          /* last segment with rec_base <= r */
 		while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (rec_base[mid] <= r) lo = mid; else hi = mid; }
-		return lo;
+		c.lo = rec_base[lo]; c.hi = rec_base[lo + 1]; c.ctg = seg[lo].contig;
+		const uint32_t a = nt.name_off[c.ctg];
+		c.name_len = nt.name_off[c.ctg + 1] - a;
+		c.name8 = 0;
+		for (uint32_t i = 0; i < c.name_len && i < 8; ++i) c.name8 |= (unsigned long long)(unsigned char)nt.names[a + i] << (8 * i);
 	}
-	__device__ __forceinline__ uint32_t length(unsigned long long r, Item &it) const
+	__device__ __forceinline__ uint32_t length(unsigned long long r, Item &it, Cache &c) const
 	{
 		it.d = run_depth[r];
 		if (it.d == 0 || r == drop_idx) { it.d = 0; return 0; }
 		it.s = run_start[r]; it.e = (r == mod_idx) ? mod_end : run_end[r];
-		it.ctg = seg[seg_of(r)].contig;
-		return (nt.name_off[it.ctg + 1] - nt.name_off[it.ctg]) + ngs_ndigits(it.s) + 1 + ngs_ndigits(it.e) + 1 + ngs_len_i32(it.d) + 1;
+		if (r < c.lo || r >= c.hi) locate(r, c);
+		it.ctg = c.ctg;
+		const uint32_t ns = ngs_ndigits(it.s), ne = ngs_ndigits(it.e), nd = ngs_len_i32(it.d);
+		it.nd = ns | ne << 8 | nd << 16;
+		return c.name_len + ns + 1 + ne + 1 + nd + 1;
 	}
-	__device__ __forceinline__ void write(char *dst, const Item &it) const
+	__device__ __forceinline__ void write(char *dst, const Item &it, const Cache &c) const
 	{
-		const uint32_t a = nt.name_off[it.ctg], nl = nt.name_off[it.ctg + 1] - a;
-		for (uint32_t i = 0; i < nl; ++i) dst[i] = nt.names[a + i];
+		uint32_t nl;
+		if (it.ctg == c.ctg && c.name_len <= 8) {            /* the common case: name bytes cached in a register */
+			unsigned long long v = c.name8;
+			nl = c.name_len;
+			for (uint32_t i = 0; i < nl; ++i) { dst[i] = (char)(v & 0xff); v >>= 8; }
+		} else {                                              /* long name, or a thread whose items straddle two contigs */
+			const uint32_t a = nt.name_off[it.ctg];
+			nl = nt.name_off[it.ctg + 1] - a;
+			for (uint32_t i = 0; i < nl; ++i) dst[i] = nt.names[a + i];
+		}
 		dst += nl;
-		dst += ngs_put_u32(dst, it.s); *dst++ = '\t';
-		dst += ngs_put_u32(dst, it.e); *dst++ = '\t';
+		const uint32_t ns = it.nd & 0xff, ne = (it.nd >> 8) & 0xff;
+		ngs_put_u32n(dst, it.s, ns); dst += ns; *dst++ = '\t';
+		ngs_put_u32n(dst, it.e, ne); dst += ne; *dst++ = '\t';
 		dst += ngs_put_i32(dst, it.d); *dst = '\n';
 	}
 };
@@ -689,13 +707,15 @@ struct DepthProducer {
 	const unsigned long long *bins; const unsigned long long *win_base;   /* [n_ref+1] first item of contig */
 	const uint32_t *ref_len; uint32_t n_ref; uint32_t window; NameTable nt;
 	struct Item { uint32_t ws, we, ctg; unsigned long long h; };
+	struct Cache { int unused; };
+	__device__ __forceinline__ void init(Cache &) const {}
 	__device__ __forceinline__ uint32_t ctg_of(unsigned long long r) const
 	{
 		uint32_t lo = 0, hi = n_ref;
 		while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (win_base[mid] <= r) lo = mid; else hi = mid; }
 		return lo;
 	}
-	__device__ __forceinline__ uint32_t length(unsigned long long r, Item &it) const
+	__device__ __forceinline__ uint32_t length(unsigned long long r, Item &it, Cache &) const
 	{
 		it.ctg = ctg_of(r);
 		const unsigned long long k = r - win_base[it.ctg];
@@ -704,7 +724,7 @@ struct DepthProducer {
 		it.h = ngs_hundredths(__ddiv_rn((double)(long long)bins[r], (double)window));
 		return (nt.name_off[it.ctg + 1] - nt.name_off[it.ctg]) + ngs_ndigits(it.ws) + 1 + ngs_ndigits(it.we) + 1 + ngs_len_f2(it.h) + 1;
 	}
-	__device__ __forceinline__ void write(char *dst, const Item &it) const
+	__device__ __forceinline__ void write(char *dst, const Item &it, const Cache &) const
 	{
 		const uint32_t a = nt.name_off[it.ctg], nl = nt.name_off[it.ctg + 1] - a;
 		for (uint32_t i = 0; i < nl; ++i) dst[i] = nt.names[a + i];
@@ -721,7 +741,9 @@ struct WigProducer {
 	uint32_t n_ref; uint32_t window;
 	const char *hdr; const uint32_t *hdr_off;                             /* "variableStep chrom=%s span=%d\n" per contig */
 	struct Item { uint32_t ws, ctg; int is_hdr; unsigned long long h; };
-	__device__ __forceinline__ uint32_t length(unsigned long long r, Item &it) const
+	struct Cache { int unused; };
+	__device__ __forceinline__ void init(Cache &) const {}
+	__device__ __forceinline__ uint32_t length(unsigned long long r, Item &it, Cache &) const
 	{
 		/* item space: contig c owns items [win_base[c] + c, win_base[c+1] + c + 1) */
 		uint32_t lo = 0, hi = n_ref;
@@ -736,7 +758,7 @@ struct WigProducer {
 		it.h = ngs_hundredths(__ddiv_rn((double)(long long)b, (double)window));
 		return ngs_ndigits(it.ws) + 1 + ngs_len_f2(it.h) + 1;
 	}
-	__device__ __forceinline__ void write(char *dst, const Item &it) const
+	__device__ __forceinline__ void write(char *dst, const Item &it, const Cache &) const
 	{
 		if (it.is_hdr) {
 			const uint32_t a = hdr_off[it.ctg], nl = hdr_off[it.ctg + 1] - a;
@@ -761,19 +783,19 @@ template <class Producer, int IPT>
 __global__ void __launch_bounds__(NGS_FMT_THREADS) k_format_lines(FmtArgs A, Producer P)
 {
 	extern __shared__ __align__(16) char s_stage[];
-	__shared__ unsigned int s_w[8];
-	__shared__ unsigned long long s_tile_id, s_off;
+	__shared__ unsigned int s_w[8], s_li[8];
+	__shared__ unsigned long long s_lb[8];
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	if (t == 0) s_tile_id = atomicAdd(&A.st->fmt_ticket, 1ull);
-	__syncthreads();
-	const unsigned long long tile = s_tile_id;
+	const unsigned long long tile = blockIdx.x;          /* dispatch order = tile order, see k_scan_runs */
 	if (tile >= A.n_tiles) return;
 	const unsigned long long r0 = tile * (unsigned long long)(NGS_FMT_THREADS * IPT) + (unsigned long long)t * IPT;
 	typename Producer::Item it[IPT];
+	typename Producer::Cache cache;
+	P.init(cache);
 	uint32_t len[IPT], tlen = 0;
 	#pragma unroll
 	for (int i = 0; i < IPT; ++i) {
-		len[i] = (r0 + i < A.n_items) ? P.length(r0 + i, it[i]) : 0;
+		len[i] = (r0 + i < A.n_items) ? P.length(r0 + i, it[i], cache) : 0;
 		tlen += len[i];
 	}
 	/* block exclusive scan of tlen */
@@ -786,38 +808,42 @@ __global__ void __launch_bounds__(NGS_FMT_THREADS) k_format_lines(FmtArgs A, Pro
 	#pragma unroll
 	for (int w = 0; w < 8; ++w) { if (w < warp) wpre += s_w[w]; total += s_w[w]; }
 	uint32_t off = wpre + inc - tlen;
-	/* look-back over tile byte totals */
-	if (warp == 0) {
-		unsigned long long run = 0;
-		if (tile == 0) { if (lane == 0) st_relaxed_u64(&A.status[0], (NGS_ST_INC << 62) | total); }
-		else {
-			if (lane == 0) st_relaxed_u64(&A.status[tile], (NGS_ST_AGG << 62) | total);
-			long long base = (long long)tile - 1;
-			for (;;) {
-				const long long idx = base - lane;
-				unsigned long long a = NGS_ST_INC << 62;
-				if (idx >= 0) { do { a = ld_relaxed_u64(&A.status[idx]); } while ((a >> 62) == NGS_ST_EMPTY); }
-				const unsigned int incl_mask = __ballot_sync(0xffffffffu, (a >> 62) == NGS_ST_INC);
-				const int first_inc = incl_mask ? __ffs(incl_mask) - 1 : 32;
-				unsigned long long v = lane <= first_inc ? (a & 0x3FFFFFFFFFFFFFFFull) : 0;
-				#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-				run += v;
-				if (first_inc < 32) break;
-				base -= 32;
-			}
-			if (lane == 0) st_relaxed_u64(&A.status[tile], (NGS_ST_INC << 62) | (run + total));
+	/* look-back over tile byte totals, block-wide (thread i inspects tile-1-i) */
+	unsigned long long run = 0;
+	if (t == 0) st_relaxed_u64(&A.status[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | total);
+	if (tile > 0) {
+		long long base = (long long)tile - 1;
+		for (;;) {
+			const long long idx = base - t;
+			unsigned long long a = NGS_ST_INC << 62;
+			if (idx >= 0) { do { a = ld_relaxed_u64(&A.status[idx]); } while ((a >> 62) == NGS_ST_EMPTY); }
+			const unsigned int im = __ballot_sync(0xffffffffu, (a >> 62) == NGS_ST_INC);
+			if (lane == 0) s_li[warp] = im ? (unsigned)(warp * 32 + __ffs(im) - 1) : 0xffffffffu;
+			__syncthreads();
+			unsigned int first_inc = 0xffffffffu;
+			#pragma unroll
+			for (int w = 0; w < 8; ++w) first_inc = s_li[w] < first_inc ? s_li[w] : first_inc;
+			unsigned long long v = (unsigned)t <= first_inc ? (a & 0x3FFFFFFFFFFFFFFFull) : 0;
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+			if (lane == 0) s_lb[warp] = v;
+			__syncthreads();
+			#pragma unroll
+			for (int w = 0; w < 8; ++w) run += s_lb[w];
+			if (first_inc != 0xffffffffu) break;
+			base -= NGS_FMT_THREADS;
+			__syncthreads();
 		}
-		if (lane == 0) { s_off = run; if (tile == A.n_tiles - 1) A.st->fmt_bytes = run + total; }
+		if (t == 0) st_relaxed_u64(&A.status[tile], (NGS_ST_INC << 62) | (run + total));
 	}
-	__syncthreads();
-	const unsigned long long goff = s_off;
+	if (t == 0 && tile == A.n_tiles - 1) A.st->fmt_bytes = run + total;
+	const unsigned long long goff = run;
 	if (total == 0 || goff + total > A.out_cap) return;
 	/* assemble lines in shared memory, shifted so that 16-byte alignment matches the global address */
 	const uint32_t mis = (uint32_t)((uintptr_t)(A.out + goff) & 15);
 	if (total + mis <= A.stage_bytes) {
 		#pragma unroll
-		for (int i = 0; i < IPT; ++i) { if (len[i]) P.write(s_stage + mis + off, it[i]); off += len[i]; }
+		for (int i = 0; i < IPT; ++i) { if (len[i]) P.write(s_stage + mis + off, it[i], cache); off += len[i]; }
 		__syncthreads();
 		char *g = A.out + goff - mis;                       /* 16-byte aligned */
 		const uint32_t end = mis + total;
@@ -832,7 +858,7 @@ __global__ void __launch_bounds__(NGS_FMT_THREADS) k_format_lines(FmtArgs A, Pro
 	} else {
 		/* lines too long for the staging area (very long contig names): write straight to global */
 		#pragma unroll
-		for (int i = 0; i < IPT; ++i) { if (len[i]) P.write(A.out + goff + off, it[i]); off += len[i]; }
+		for (int i = 0; i < IPT; ++i) { if (len[i]) P.write(A.out + goff + off, it[i], cache); off += len[i]; }
 	}
 }
 
