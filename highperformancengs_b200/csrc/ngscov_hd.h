@@ -239,38 +239,78 @@ NGS_HD void ngs_decode_record(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o
 	}
 }
 
-/* Walk the record chain from offset o while records START before `hi`.  Returns the exit code:
+/* Walk the record chain from offset o while records START before `hi`.  The exit code is
  *   >= hi            offset of the first record start at or beyond hi (may exceed the chunk size)
  *   NGS_EXIT_PARTIAL the record at that offset has its header/CIGAR cut by the chunk end
- *   NGS_EXIT_INVALID a record failed validation                                             */
+ *   NGS_EXIT_INVALID a record failed validation
+ * The walk is split into begin/step so that a warp can advance all of its chains in lock step (one
+ * record per lane per iteration) and stay converged; ngs_walk is the plain sequential composition. */
+typedef struct {
+	int64_t o;          /* offset of the record whose header is in h */
+	int64_t result;     /* exit code once active == 0 */
+	ngs_hdr h;
+	int active;
+} ngs_walk_state;
+
+template <class Mem>
+NGS_HD void ngs_walk_begin(const Mem &mem, int64_t o, int64_t hi, ngs_walk_state &st)
+{
+	st.o = o; st.active = 0; st.result = o;
+	if (o >= hi) return;
+	if (o + 36 > mem.size()) { st.result = NGS_EXIT_PARTIAL(o); return; }
+	mem.hdr_lite(o, st.h);
+	st.active = 1;
+}
+
+template <class Mem, class Sink>
+NGS_HD void ngs_walk_step(const ngs_walk_cfg &cfg, const Mem &mem, int64_t hi, Sink &sink, int sign, ngs_counts &cnt, ngs_walk_state &st)
+{
+	const int64_t n = mem.size(), o = st.o;
+	const ngs_hdr h = st.h;
+	if (!ngs_hdr_valid(h, cfg.n_ref)) { st.active = 0; st.result = NGS_EXIT_INVALID; return; }
+	if (o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar > n) { st.active = 0; st.result = NGS_EXIT_PARTIAL(o); return; }
+	/* the next header is requested before this record is decoded: two loads in flight per chain */
+	const int64_t nx = o + 4 + (int64_t)h.block_size;
+	const bool more = nx < hi, have = more && nx + 36 <= n;
+	if (have) mem.hdr_lite(nx, st.h);
+	ngs_decode_record(cfg, mem, o, h, sink, sign, cnt);
+	st.o = nx;
+	if (!more) { st.active = 0; st.result = nx; }
+	else if (!have) { st.active = 0; st.result = NGS_EXIT_PARTIAL(nx); }
+}
+
 template <class Mem, class Sink>
 NGS_HD int64_t ngs_walk(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o, int64_t hi,
                         Sink &sink, int sign, ngs_counts &cnt)
 {
-	const int64_t n = mem.size();
-	if (o >= hi) return o;
-	if (o + 36 > n) return NGS_EXIT_PARTIAL(o);
-	ngs_hdr h;
-	mem.hdr_lite(o, h);
-	for (;;) {
-		if (!ngs_hdr_valid(h, cfg.n_ref)) return NGS_EXIT_INVALID;
-		if (o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar > n) return NGS_EXIT_PARTIAL(o);
-		/* the next header is requested before this record is decoded: two loads in flight per chain */
-		const int64_t nx = o + 4 + (int64_t)h.block_size;
-		const bool more = nx < hi, have = more && nx + 36 <= n;
-		ngs_hdr hn = h;
-		if (have) mem.hdr_lite(nx, hn);
-		ngs_decode_record(cfg, mem, o, h, sink, sign, cnt);
-		if (!more) return nx;
-		if (!have) return NGS_EXIT_PARTIAL(nx);
-		o = nx; h = hn;
-	}
+	ngs_walk_state st;
+	ngs_walk_begin(mem, o, hi, st);
+	while (st.active) ngs_walk_step(cfg, mem, hi, sink, sign, cnt, st);
+	return st.result;
 }
 
-/* Speculative entry search in [lo, hi): first offset whose record and the `depth-1` records chained
- * after it all look plausible.  NGS_NONE if there is none (or it cannot be checked inside the chunk).
+/* Speculation: does a record chain of `depth` plausible records start at offset o? */
+template <class Mem>
+NGS_HD int ngs_candidate_ok(const ngs_walk_cfg &cfg, const Mem &mem, const uint32_t *ref_len, int64_t o)
+{
+	const int64_t n = mem.size();
+	int64_t c = o;
+	for (int depth = 0; depth < 3; ++depth) {
+		ngs_hdr h;
+		if (c + 36 > n) break;                                   /* chain leaves the chunk: accept */
+		mem.hdr(c, h);
+		if (!ngs_hdr_plausible(h, cfg.n_ref, ref_len)) return 0;
+		const int64_t nul = c + 36 + (int64_t)h.l_qname - 1;
+		if (nul < n && mem.u8(nul) != 0) return 0;
+		c += 4 + (int64_t)h.block_size;
+	}
+	return 1;
+}
+
+/* Speculative entry search in [lo, hi): first offset whose record and the two records chained after
+ * it all look plausible.  NGS_NONE if there is none (or it cannot be checked inside the chunk).
  * mem.next_candidate(o, end, n_ref) returns the first offset in [o, end) whose block_size and refID
- * fields are in range (a tight, convergent byte scan), or NGS_NONE. */
+ * fields are in range (a tight byte scan), or NGS_NONE. */
 template <class Mem>
 NGS_HD int64_t ngs_find_entry(const ngs_walk_cfg &cfg, const Mem &mem, const uint32_t *ref_len, int64_t lo, int64_t hi)
 {
@@ -280,17 +320,7 @@ NGS_HD int64_t ngs_find_entry(const ngs_walk_cfg &cfg, const Mem &mem, const uin
 	for (;;) {
 		o = mem.next_candidate(o, end, (uint32_t)cfg.n_ref);
 		if (o == NGS_NONE) return NGS_NONE;
-		int64_t c = o; int ok = 1;
-		for (int depth = 0; depth < 3; ++depth) {
-			ngs_hdr h;
-			if (c + 36 > n) break;                                   /* chain leaves the chunk: accept */
-			mem.hdr(c, h);
-			if (!ngs_hdr_plausible(h, cfg.n_ref, ref_len)) { ok = 0; break; }
-			const int64_t nul = c + 36 + (int64_t)h.l_qname - 1;
-			if (nul < n && mem.u8(nul) != 0) { ok = 0; break; }
-			c += 4 + (int64_t)h.block_size;
-		}
-		if (ok) return o;
+		if (ngs_candidate_ok(cfg, mem, ref_len, o)) return o;
 		++o;
 	}
 }

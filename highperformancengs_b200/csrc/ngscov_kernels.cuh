@@ -54,6 +54,21 @@ struct ngs_dev_state {
 
 /* ------------------------------------------------------------------------------------------------ */
 /* memory policy: unaligned little-endian field access on the inflated stream in HBM               */
+/* 128-bit / 32-bit read-only loads that ask L2 to fetch the whole 128-byte line: the next record of a
+ * chain usually starts in the same line, so its header then comes from L2 instead of DRAM */
+__device__ __forceinline__ uint4 ldg_line_v4(const uint4 *p)
+{
+	uint4 r;
+	asm volatile("ld.global.nc.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ uint32_t ldg_line_u32(const uint32_t *p)
+{
+	uint32_t r;
+	asm volatile("ld.global.nc.L2::128B.u32 %0, [%1];" : "=r"(r) : "l"(p));
+	return r;
+}
+
 struct DevMem {
 	const uint8_t *base;     /* offset 0 of the chunk (carry bytes live just before it) */
 	int64_t n;
@@ -96,9 +111,9 @@ struct DevMem {
 		const uintptr_t a = (uintptr_t)(base + o);
 		const uint4 *p = (const uint4 *)(a & ~(uintptr_t)15);
 		const uint32_t bo = (uint32_t)(a & 15);
-		const uint4 q0 = __ldg(p), q1 = __ldg(p + 1);
+		const uint4 q0 = ldg_line_v4(p), q1 = ldg_line_v4(p + 1);
 		uint4 q2 = make_uint4(0, 0, 0, 0);
-		if (bo > 8) q2 = __ldg(p + 2);
+		if (bo > 8) q2 = ldg_line_v4(p + 2);
 		uint32_t w[10] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y };
 		if (bo & 8) {
 			#pragma unroll
@@ -165,32 +180,46 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 	return v;
 }
 
-/* K1+K2: one thread per sub-chunk. */
+/* K1+K2: one thread per sub-chunk.  Both phases run warp-synchronously so that the 32 independent
+ * chains of a warp stay converged: (1) the entry search alternates a cheap byte scan with a converged
+ * deep validation round; (2) the walk advances every live chain by one record per iteration. */
 __global__ void __launch_bounds__(256) k_ingest_walk(IngestArgs A)
 {
+	const unsigned full = 0xffffffffu;
 	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	ngs_counts cnt = { 0, 0, 0, 0 };
 	unsigned long long walks = 0;
-	if (c < A.n_sub) {
-		DevMem mem = { A.base, A.n };
-		const int64_t lo = c << A.shift;
-		int64_t hi = lo + ((int64_t)1 << A.shift);
-		if (hi > A.n) hi = A.n;
-		long long entry, ex = 0;
-		if (c == 0) {
-			const long long e0 = A.entry0_from_state ? A.st->entry_next : A.fixed_entry0;
-			entry = e0 < hi ? e0 : NGS_NONE;
-		} else {
-			entry = ngs_find_entry(A.cfg, mem, A.ref_len, lo, hi);
-		}
-		if (entry != NGS_NONE) {
-			DevSink sink; sink.init(A.diff, &A.st->flags);
-			ex = ngs_walk(A.cfg, mem, entry, hi, sink, +1, cnt);
-			sink.flush();
-			walks = 1;
-		}
-		A.entry[c] = entry; A.exit[c] = ex;
+	const bool live = c < A.n_sub;
+	DevMem mem = { A.base, A.n };
+	const int64_t lo = live ? (c << A.shift) : 0;
+	int64_t hi = live ? lo + ((int64_t)1 << A.shift) : 0;
+	if (hi > A.n) hi = A.n;
+	long long entry = NGS_NONE;
+	bool searching = live && c != 0;
+	if (live && c == 0) {
+		const long long e0 = A.entry0_from_state ? A.st->entry_next : A.fixed_entry0;
+		entry = e0 < hi ? e0 : NGS_NONE;
 	}
+	{
+		const int64_t end = hi < A.n - 35 ? hi : A.n - 35;
+		int64_t o = lo;
+		while (__any_sync(full, searching)) {
+			if (searching) { o = mem.next_candidate(o, end, (uint32_t)A.cfg.n_ref); if (o == NGS_NONE) searching = false; }
+			__syncwarp();
+			if (searching) {
+				if (ngs_candidate_ok(A.cfg, mem, A.ref_len, o)) { entry = o; searching = false; } else ++o;
+			}
+		}
+	}
+	ngs_walk_state ws;
+	ws.active = 0; ws.result = 0; ws.o = 0;
+	DevSink sink; sink.init(A.diff, &A.st->flags);
+	if (entry != NGS_NONE) { ngs_walk_begin(mem, entry, hi, ws); walks = 1; }
+	while (__any_sync(full, ws.active != 0)) {
+		if (ws.active) ngs_walk_step(A.cfg, mem, hi, sink, +1, cnt, ws);
+	}
+	sink.flush();
+	if (live) { A.entry[c] = entry; A.exit[c] = entry != NGS_NONE ? ws.result : 0; }
 	/* block-aggregate the counters */
 	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
 	                   v2 = warp_sum_u64(cnt.m_ops), v3 = warp_sum_u64(cnt.cigar_words), v4 = warp_sum_u64(walks);
