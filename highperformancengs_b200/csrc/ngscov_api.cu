@@ -203,6 +203,7 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	CK(cudaEventCreateWithFlags(&h->ev_verified, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&h->ev_finalized, cudaEventDisableTiming));
 	CK(cudaEventCreate(&h->ev_t0)); CK(cudaEventCreate(&h->ev_t1));
+	CK(cudaFuncSetAttribute(k_ingest_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)NGS_TILE_THREADS << 10) + NGS_TILE_MARGIN)));
 	build_geometry(h);
 	CKC(dev_upload(h, &h->d_seg, h->seg));
 	CKC(dev_upload(h, &h->d_ctg2seg, h->ctg2seg));
@@ -364,6 +365,7 @@ static IngestArgs make_ingest_args(ngscov *h, const uint8_t *base, int64_t n, in
 	A.cfg.ctg2seg = h->d_ctg2seg; A.cfg.seg = h->d_seg;
 	A.ref_len = h->d_ref_len; A.diff = h->d_diff; A.st = h->d_st;
 	A.fixed_entry0 = fixed0; A.entry0_from_state = from_state ? 1 : 0;
+	A.debug = getenv("NGSCOV_DEBUG_INGEST") ? atoi(getenv("NGSCOV_DEBUG_INGEST")) : 0;
 	return A;
 }
 
@@ -410,7 +412,7 @@ static int pick_shift(ngscov *h, int32_t first_block_size)
 	int64_t rec = (int64_t)first_block_size + 4;
 	if (rec < 36) rec = 36;
 	if (rec > 4096) rec = 4096;
-	int64_t want = rec * 20; int s = 9;                       /* ~20 records per sub-chunk, 512 B .. 32 KiB */
+	int64_t want = rec * 32; int s = 9;                       /* ~32-64 records per sub-chunk, 512 B .. 32 KiB */
 	while (((int64_t)1 << s) < want && s < 15) ++s;
 	h->shift = s;
 	return 0;
@@ -422,9 +424,20 @@ static int submit_chunk(ngscov *h, const uint8_t *base, int64_t n, bool from_sta
 	int r = ensure_sub(h, n_sub);
 	if (r) return r;
 	IngestArgs A = make_ingest_args(h, base, n, n_sub, from_state, fixed0);
-	const unsigned nb = (unsigned)((n_sub + 255) / 256);
 	CK(cudaEventRecord(next_event(h->ev_ing, h->n_ing), h->s_main));
-	k_ingest_walk<<<nb, 256, 0, h->s_main>>>(A);
+	/* The shared-memory staged variant is kept selectable (NGSCOV_TILES=1) but is not the default: on B200 it
+	 * measured slower than walking in HBM because its 64 KB tiles cap occupancy at 6 warps/SM, and the
+	 * profile shows the walk is bound by RED traffic, not by stream-read latency (ingest). */
+	const char *tenv = getenv("NGSCOV_TILES");
+	const bool tiles = tenv && atoi(tenv) == 1 && h->shift <= 10 && (((uintptr_t)base) & 15) == 0;
+	if (tiles) {
+		const size_t smem = ((size_t)NGS_TILE_THREADS << h->shift) + NGS_TILE_MARGIN;
+		const unsigned nb = (unsigned)((n_sub + NGS_TILE_THREADS - 1) / NGS_TILE_THREADS);
+		k_ingest_tiles<<<nb, NGS_TILE_THREADS, smem, h->s_main>>>(A);
+	} else {
+		const unsigned nb = (unsigned)((n_sub + 255) / 256);
+		k_ingest_walk<<<nb, 256, 0, h->s_main>>>(A);
+	}
 	h->stats.launches += 1;
 	CK(cudaGetLastError());
 	h->pending = true; h->p_base = base; h->p_n = n; h->p_nsub = n_sub; h->p_from_state = from_state; h->p_fixed0 = fixed0;

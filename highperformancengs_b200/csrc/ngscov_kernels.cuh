@@ -143,16 +143,18 @@ struct DevMem {
 /* delta sink: one pending (address,count) pair for the +1 stream and one for the -1 stream, so that
  * pile-ups (identical starts / ends in consecutive records) collapse into a single RED */
 struct DevSink {
-	int *diff; unsigned int *flags;
+	int *diff; unsigned int *flags; int dbg;
 	unsigned long long pa, pb; int ca, cb;
-	__device__ __forceinline__ void init(int *d, unsigned int *f) { diff = d; flags = f; pa = pb = ~0ull; ca = cb = 0; }
+	__device__ __forceinline__ void init(int *d, unsigned int *f, int dg = 0) { diff = d; flags = f; pa = pb = ~0ull; ca = cb = 0; dbg = dg; }
 	__device__ __forceinline__ void add2(uint64_t ia, uint64_t ib, int sign)
 	{
+		if (dbg & 1) { ca += (int)ia; cb += (int)ib; return; }     /* timing experiment: no atomics */
 		if (ia == pa) ca += sign; else { if (ca) atomicAdd(diff + pa, ca); pa = ia; ca = sign; }
 		if (ib == pb) cb -= sign; else { if (cb) atomicAdd(diff + pb, cb); pb = ib; cb = -sign; }
 	}
 	__device__ __forceinline__ void flush()
 	{
+		if (dbg & 1) { if (ca + cb == 0x12345677) atomicAdd(diff, 1); return; }
 		if (ca) atomicAdd(diff + pa, ca);
 		if (cb) atomicAdd(diff + pb, cb);
 		ca = cb = 0; pa = pb = ~0ull;
@@ -169,6 +171,7 @@ struct IngestArgs {
 	const uint32_t *ref_len;
 	int *diff;
 	ngs_dev_state *st;
+	int debug;                             /* timing experiments only: bit0 no atomics */
 	long long fixed_entry0;                /* used when entry0_from_state == 0 */
 	int entry0_from_state;                 /* 1: first entry = st->entry_next (streamed pushes) */
 };
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(256) k_ingest_walk(IngestArgs A)
 	}
 	ngs_walk_state ws;
 	ws.active = 0; ws.result = 0; ws.o = 0;
-	DevSink sink; sink.init(A.diff, &A.st->flags);
+	DevSink sink; sink.init(A.diff, &A.st->flags, A.debug);
 	if (entry != NGS_NONE) { ngs_walk_begin(mem, entry, hi, ws); walks = 1; }
 	while (__any_sync(full, ws.active != 0)) {
 		if (ws.active) ngs_walk_step(A.cfg, mem, hi, sink, +1, cnt, ws);
@@ -221,6 +224,156 @@ __global__ void __launch_bounds__(256) k_ingest_walk(IngestArgs A)
 	sink.flush();
 	if (live) { A.entry[c] = entry; A.exit[c] = entry != NGS_NONE ? ws.result : 0; }
 	/* block-aggregate the counters */
+	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
+	                   v2 = warp_sum_u64(cnt.m_ops), v3 = warp_sum_u64(cnt.cigar_words), v4 = warp_sum_u64(walks);
+	if ((threadIdx.x & 31) == 0) {
+		if (v0) atomicAdd(&A.st->records, v0);
+		if (v1) atomicAdd(&A.st->kept, v1);
+		if (v2) atomicAdd(&A.st->m_ops, v2);
+		if (v3) atomicAdd(&A.st->cigar_words, v3);
+		if (v4) atomicAdd(&A.st->spec_walks, v4);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* K1+K2, shared-memory staged variant (small records).  The per-thread chain walk is a chain of
+ * dependent loads; issued against HBM each hop costs a DRAM round trip and the kernel ends up bound
+ * by memory latency at ~40 % of the bandwidth (ncu: long-scoreboard stalls on the header loads).
+ * Here a CTA first pulls its whole stream tile (NGS_TILE_THREADS sub-chunks + a margin for the record
+ * that overhangs the tile end) into shared memory with ONE bulk async copy (cp.async.bulk, TMA
+ * engine, mbarrier completion), so HBM sees large sequential requests issued far ahead, and the hops
+ * of the walk then cost shared-memory latency.  Bytes outside the staged window (the carry before
+ * offset 0, or a header + CIGAR longer than the margin) fall back to the global-memory path. */
+#define NGS_TILE_THREADS 64
+#define NGS_TILE_MARGIN  1024
+
+struct TileMem {
+	DevMem g;                       /* whole chunk in global memory */
+	const uint8_t *sm;              /* staged bytes: chunk offsets [t0, t1) */
+	int64_t t0, t1;
+	__device__ __forceinline__ int64_t size() const { return g.n; }
+	__device__ __forceinline__ uint32_t u32(int64_t o) const
+	{
+		if (o >= t0 && o + 8 <= t1) {
+			const uint32_t off = (uint32_t)(o - t0);
+			const uint32_t *p = (const uint32_t *)(sm + (off & ~3u));
+			return __funnelshift_r(p[0], p[1], (off & 3) * 8);
+		}
+		return g.u32(o);
+	}
+	__device__ __forceinline__ uint32_t u8(int64_t o) const
+	{
+		if (o >= t0 && o < t1) return sm[o - t0];
+		return g.u8(o);
+	}
+	__device__ __forceinline__ void hdr_lite(int64_t o, ngs_hdr &h) const
+	{
+		if (o >= t0 && o + 48 <= t1) {
+			const uint32_t off = (uint32_t)(o - t0);
+			const uint32_t *p = (const uint32_t *)(sm + (off & ~3u));
+			const uint32_t sh = (off & 3) * 8;
+			uint32_t w[7];
+			#pragma unroll
+			for (int i = 0; i < 7; ++i) w[i] = p[i];
+			uint32_t f[6];
+			#pragma unroll
+			for (int i = 0; i < 6; ++i) f[i] = __funnelshift_r(w[i], w[i + 1], sh);
+			h.block_size = (int32_t)f[0]; h.ref_id = (int32_t)f[1]; h.pos = (int32_t)f[2];
+			h.l_qname = f[3] & 0xff; h.n_cigar = f[4] & 0xffff; h.flag = f[4] >> 16; h.l_seq = (int32_t)f[5];
+			h.next_ref_id = 0; h.next_pos = 0;
+		} else g.hdr_lite(o, h);
+	}
+	__device__ __forceinline__ void hdr(int64_t o, ngs_hdr &h) const
+	{
+		h.block_size = (int32_t)u32(o); h.ref_id = (int32_t)u32(o + 4); h.pos = (int32_t)u32(o + 8);
+		const uint32_t a = u32(o + 12), b = u32(o + 16);
+		h.l_qname = a & 0xff; h.n_cigar = b & 0xffff; h.flag = b >> 16;
+		h.l_seq = (int32_t)u32(o + 20); h.next_ref_id = (int32_t)u32(o + 24); h.next_pos = (int32_t)u32(o + 28);
+	}
+	__device__ __forceinline__ int64_t next_candidate(int64_t o, int64_t end, uint32_t n_ref) const
+	{
+		if (o >= end) return NGS_NONE;
+		if (o < t0 || end + 12 > t1) return g.next_candidate(o, end, n_ref);
+		uint32_t off = (uint32_t)(o - t0);
+		const uint32_t *p = (const uint32_t *)(sm + (off & ~3u));
+		uint32_t sh = (off & 3) * 8;
+		uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+		p += 3;
+		for (;;) {
+			const uint32_t bs = __funnelshift_r(w0, w1, sh), rid = __funnelshift_r(w1, w2, sh);
+			if (bs - 32u <= NGS_MAX_BS - 32u && rid + 1u <= n_ref) return o;
+			if (++o >= end) return NGS_NONE;
+			sh += 8;
+			if (sh == 32) { sh = 0; w0 = w1; w1 = w2; w2 = *p++; }
+		}
+	}
+};
+
+__global__ void __launch_bounds__(NGS_TILE_THREADS) k_ingest_tiles(IngestArgs A)
+{
+	extern __shared__ __align__(128) uint8_t s_stream[];
+	__shared__ __align__(8) unsigned long long s_bar;
+	const unsigned full = 0xffffffffu;
+	const int t = threadIdx.x;
+	const int64_t tile_bytes = (int64_t)NGS_TILE_THREADS << A.shift;
+	const int64_t t0 = (int64_t)blockIdx.x * tile_bytes;
+	int64_t t1 = t0 + tile_bytes + NGS_TILE_MARGIN;
+	if (t1 > A.n) t1 = A.n;
+	t1 = t0 + ((t1 - t0) & ~(int64_t)15);                     /* bulk copies move multiples of 16 bytes */
+	const uint32_t nbytes = (uint32_t)(t1 - t0);
+	const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+	if (t == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (t == 0 && nbytes) {
+		const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_stream);
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(nbytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		             :: "r"(dst), "l"(A.base + t0), "r"(nbytes), "r"(bar) : "memory");
+	}
+	if (nbytes) {
+		uint32_t done = 0;
+		while (!done) {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+			             : "=r"(done) : "r"(bar) : "memory");
+		}
+	}
+	const int64_t c = (int64_t)blockIdx.x * NGS_TILE_THREADS + t;
+	ngs_counts cnt = { 0, 0, 0, 0 };
+	unsigned long long walks = 0;
+	const bool live = c < A.n_sub;
+	TileMem mem; mem.g.base = A.base; mem.g.n = A.n; mem.sm = s_stream; mem.t0 = t0; mem.t1 = t1;
+	const int64_t lo = live ? (c << A.shift) : 0;
+	int64_t hi = live ? lo + ((int64_t)1 << A.shift) : 0;
+	if (hi > A.n) hi = A.n;
+	long long entry = NGS_NONE;
+	bool searching = live && c != 0;
+	if (live && c == 0) {
+		const long long e0 = A.entry0_from_state ? A.st->entry_next : A.fixed_entry0;
+		entry = e0 < hi ? e0 : NGS_NONE;
+	}
+	{
+		const int64_t end = hi < A.n - 35 ? hi : A.n - 35;
+		int64_t o = lo;
+		while (__any_sync(full, searching)) {
+			if (searching) { o = mem.next_candidate(o, end, (uint32_t)A.cfg.n_ref); if (o == NGS_NONE) searching = false; }
+			__syncwarp();
+			if (searching) {
+				if (ngs_candidate_ok(A.cfg, mem, A.ref_len, o)) { entry = o; searching = false; } else ++o;
+			}
+		}
+	}
+	ngs_walk_state ws;
+	ws.active = 0; ws.result = 0; ws.o = 0;
+	DevSink sink; sink.init(A.diff, &A.st->flags, A.debug);
+	if (entry != NGS_NONE) { ngs_walk_begin(mem, entry, hi, ws); walks = 1; }
+	while (__any_sync(full, ws.active != 0)) {
+		if (ws.active) ngs_walk_step(A.cfg, mem, hi, sink, +1, cnt, ws);
+	}
+	sink.flush();
+	if (live) { A.entry[c] = entry; A.exit[c] = entry != NGS_NONE ? ws.result : 0; }
 	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
 	                   v2 = warp_sum_u64(cnt.m_ops), v3 = warp_sum_u64(cnt.cigar_words), v4 = warp_sum_u64(walks);
 	if ((threadIdx.x & 31) == 0) {
