@@ -1,0 +1,102 @@
+"""GPU: (a) engine against the committed reference outputs (golden), (b) the C drop-in drivers end to end
+on BAM files, (c) region sharding: slices processed separately and stitched equal the whole."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import bamutil, cases
+from tests.test_oracle_golden import check_against_gold, PARAMS, _input
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name,kind,params,tool,window", PARAMS, ids=[f"{p[0]}-{p[3]}-{p[4]}" for p in PARAMS])
+def test_engine_matches_reference_outputs(name, kind, params, tool, window):
+    from highperformancengs_b200 import CoverageEngine
+    names, lens, recs, g = _input(name, kind, params)
+    mode = 0 if tool == "depth" else 1
+    with CoverageEngine(names, lens, mode=mode, window=window, emit_wig=True) as eng:
+        eng.push_host(recs, last=True)
+        eng.finish()
+        got = {k: eng.output(i) for i, k in enumerate(("bedgraph", "depth", "wig", "chromsize")) if mode == 0 or i >= 2}
+    check_against_gold(got, f"{name}|{tool}|{window}")
+
+
+@pytest.mark.parametrize("case,tool,window", [("random1", "depth", 150), ("random1", "wig", 150), ("c2_s0.0005", "depth", 20000),
+                                              ("c4_s0.01", "wig", 100), ("toy", "depth", 10)])
+def test_c_driver_writes_reference_identical_files(tmp_path, case, tool, window):
+    exe = os.path.join(ROOT, "highperformancengs_b200", "host", "bam2depth" if tool == "depth" else "bam2wig")
+    spec = [c for c in cases.CASES if c[0] == case][0]
+    names, lens, recs, g = cases.case_input(spec[1], spec[2])
+    bam = str(tmp_path / (case + ".bam"))
+    if g is not None:
+        g.write_bam(bam)
+    else:
+        bamutil.write_bam(bam, names, lens, recs)
+    args = [exe, "-o", str(tmp_path / "o"), "-w", str(window)] + (["-W"] if tool == "depth" else []) + [bam]
+    env = dict(os.environ, NGSCOV_STAGING_MB="1")           # small staging: records straddle pushes
+    r = subprocess.run(args, cwd=str(tmp_path), capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert f"Converted {bam} to wig format at" in r.stderr and f"{names[0].decode()} at " in r.stderr
+    files = {"wig": "o.1.wig", "chromsize": "o.1.chromSize.txt"}
+    if tool == "depth":
+        files.update(bedgraph=os.path.basename(bam) + ".1.bedGraph", depth="o.1.depth")
+    got = {k: open(str(tmp_path / p), "rb").read() for k, p in files.items()}
+    check_against_gold(got, f"{case}|{tool}|{window}")
+
+
+def _sharded(names, lens, recs, mode, window, n):
+    """n engines on one GPU, each owning a genome slice but fed the whole stream (deltas are clipped)."""
+    from highperformancengs_b200 import CoverageEngine, shard
+    slices = shard.plan_slices(lens, n)
+    engs = [CoverageEngine(names, lens, mode=mode, window=window, emit_wig=True, slice_beg=b, slice_end=e) for b, e in slices if e > b]
+    try:
+        for e in engs:
+            e.push_host(recs, last=True)
+            e.finish_runs()
+        decisions, corr = shard.stitch([e.halo() for e in engs])
+        bins = None
+        for e, d in zip(engs, decisions):
+            e.halo_put(*d)
+            b = e.bins()
+            bins = b if bins is None else bins + b
+        for run, sign in corr:
+            engs[0].bins_apply_run(run, sign, bins)
+        engs[0].bins_put(bins)
+        bed = b""
+        for i, e in enumerate(engs):
+            e.format(e.default_mask() if i == 0 else ((1 << 0) if mode == 0 else 0))
+            if mode == 0:
+                bed += e.output(0)
+        out = {"bedgraph": bed, "depth": engs[0].output(1) if mode == 0 else b"", "wig": engs[0].output(2), "chromsize": engs[0].output(3)}
+        return out
+    finally:
+        for e in engs:
+            e.close()
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sharded_equals_whole(oracle, n, mode):
+    names, lens, reads = bamutil.random_case(5, n_reads=6000, contigs=((b"c1", 150000), (b"c2", 40000), (b"c3", 300000)))
+    recs = bamutil.records(reads, seq=False)
+    for window in (1000, 16384, 777):
+        exp = oracle.run(recs, names, lens, mode, window)
+        got = _sharded(names, lens, recs, mode, window, n)
+        for k in (("bedgraph", "depth", "wig", "chromsize") if mode == 0 else ("wig", "chromsize")):
+            assert got[k] == exp[k], f"n={n} mode={mode} w={window}: {k} differs"
+
+
+def test_sharded_low_coverage_long_runs(oracle):
+    """constant-depth runs that span whole shards (chained merges)"""
+    names, lens = [b"c1"], [200000]
+    reads = [(0, 100, 0, "150000M"), (0, 120000, 0, "70000M"), (0, 199000, 0, "1000M")]
+    recs = bamutil.records(reads, seq=False)
+    for mode in (0, 1):
+        exp = oracle.run(recs, names, lens, mode, 20000)
+        got = _sharded(names, lens, recs, mode, 20000, 8)
+        for k in (("bedgraph", "depth", "wig") if mode == 0 else ("wig",)):
+            assert got[k] == exp[k], (mode, k)

@@ -556,8 +556,10 @@ int bamgen_write_bam(bamgen_t *g, const char *path, int level)
 		s = next;
 	}
 	if (save_tid >= 0) {
-		idx_chunk(&R[save_tid], save_bin, save_off, VOFF(total));
-		idx_chunk(&R[save_tid], 37450, off_beg, VOFF(total));
+		/* samtools takes bam_tell() after the read that hit end-of-file, i.e. past the 28-byte EOF block */
+		const uint64_t vend = (coff[nblk] + 28) << 16;
+		idx_chunk(&R[save_tid], save_bin, save_off, vend);
+		idx_chunk(&R[save_tid], 37450, off_beg, vend);
 		idx_chunk(&R[save_tid], 37450, n_mapped, n_unmapped);
 	}
 	if (stopped) n_no_coor = n_no_coor;   /* counted above for every tid<0 record */
