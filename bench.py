@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--window", type=int, default=20000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--check", action="store_true", help="small scales only: gather every rank's text on rank 0 and compare with the CPU oracle")
     ap.add_argument("--ref-sample-reads", type=int, default=1000000)
     ap.add_argument("--cpu-sample-reads", type=int, default=2000000)
     args = ap.parse_args()
@@ -324,6 +325,24 @@ def main():
             dist.all_reduce(tb2, op=dist.ReduceOp.SUM)
         e2e = {"value": g.n_reads / (te[0].item() * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(tb2[0].item()),
                "d2h_bytes_per_step": int(tb2[1].item()), "ms_per_step": te[0].item(), "steps": k}
+
+    if args.check:
+        # parity of the sharded job: concatenate the ranks' bedGraph in rank order, .depth from rank 0
+        step_resident()
+        bed = eng.output(OUT_BEDGRAPH)
+        parts = [None] * world
+        if world > 1:
+            dist.all_gather_object(parts, bed)
+        else:
+            parts = [bed]
+        if rank == 0:
+            from tests import oracle_py
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+            exp = oracle_py.run(g.records(), g.names, lens, 0, args.window)
+            ok = b"".join(parts) == exp["bedgraph"] and eng.output(OUT_DEPTH) == exp["depth"]
+            print(f"check: {world} shard(s), bedGraph {sum(map(len, parts))} bytes, parity {'OK' if ok else 'FAILED'}", file=sys.stderr, flush=True)
+            if not ok:
+                raise SystemExit("sharded output differs from the oracle")
 
     if rank == 0:
         peak, peak_src = peaks()
