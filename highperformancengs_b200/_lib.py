@@ -76,7 +76,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("NGSCOV_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise ImportError(f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "or `make -C highperformancengs_b200/csrc` (there is no CPU fallback)")

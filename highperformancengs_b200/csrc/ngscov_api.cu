@@ -46,6 +46,10 @@ struct ngscov {
 	/* sub-chunk walk */
 	int shift;
 	long long *d_entry, *d_exit, *d_bmax; size_t sub_cap, bmax_cap;
+	unsigned int *d_count; unsigned short *d_slots; size_t slots_cap;
+	unsigned long long *d_ctr, *h_ctr;        /* striped K2 counters */
+	bool fused;                               /* NGSCOV_FUSED=1: the single-kernel walk+decode variant */
+	bool p_k2_done;
 	ngs_dev_state *d_st, *h_st;
 
 	/* pending (unverified) chunk */
@@ -247,7 +251,12 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	CK(cudaMalloc((void **)&h->d_carry, NGS_CARRY_MAX));
 	CK(cudaMalloc((void **)&h->d_st, sizeof(ngs_dev_state)));
 	CK(cudaHostAlloc((void **)&h->h_st, sizeof(ngs_dev_state), cudaHostAllocDefault));
+	CK(cudaMalloc((void **)&h->d_ctr, NGS_CTR_STRIPES * 16 * 8));
+	CK(cudaHostAlloc((void **)&h->h_ctr, NGS_CTR_STRIPES * 16 * 8, cudaHostAllocDefault));
 	h->stage_cap = cfg->staging_bytes ? (size_t)cfg->staging_bytes : (size_t)256 << 20;
+	/* Two ingest organisations are kept, both parity-tested: the fused walk+decode kernel (default: fastest on
+	 * B200 today) and the K1 frame / K2 per-record decode split (NGSCOV_SPLIT=1), see DESIGN.md section 4. */
+	h->fused = !(getenv("NGSCOV_SPLIT") && atoi(getenv("NGSCOV_SPLIT")) == 1);
 	h->shift = 0;
 	const char *env = getenv("NGSCOV_SUBCHUNK");
 	if (env && atoi(env) >= 64) { int v = atoi(env), s = 6; while ((1 << (s + 1)) <= v) ++s; h->shift = s; }
@@ -261,12 +270,13 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	cudaDeviceSynchronize();
 	void *dev[] = { h->d_seg, h->d_ctg2seg, h->d_tile2seg, h->d_ref_len, h->d_win_base, h->d_diff, h->d_bins, h->d_names,
 	                h->d_name_off, h->d_wighdr, h->d_wighdr_off, h->d_chunk[0], h->d_chunk[1], h->d_carry, h->d_entry, h->d_exit,
-	                h->d_bmax, h->d_st, h->d_run_start, h->d_run_end, h->d_run_depth, h->d_rec_base, h->d_stA, h->d_stB,
+	                h->d_bmax, h->d_count, h->d_slots, h->d_ctr, h->d_st, h->d_run_start, h->d_run_end, h->d_run_depth, h->d_rec_base, h->d_stA, h->d_stB,
 	                h->d_fmt_status, h->d_text[0], h->d_text[1], h->d_text[2], h->d_text[3] };
 	for (void *p : dev) if (p) cudaFree(p);
 	for (int i = 0; i < 2; ++i) if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
 	for (int i = 0; i < 4; ++i) if (h->h_text[i]) cudaFreeHost(h->h_text[i]);
 	if (h->h_st) cudaFreeHost(h->h_st);
+	if (h->h_ctr) cudaFreeHost(h->h_ctr);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
 	if (h->s_copy) cudaStreamDestroy(h->s_copy);
 	for (int i = 0; i < 2; ++i) if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -294,6 +304,7 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	memset(&h->stats, 0, sizeof h->stats);
 	h->stats.ms_zero = keep_zero;
 	CK(cudaMemsetAsync(h->d_st, 0, sizeof(ngs_dev_state), h->s_main));
+	CK(cudaMemsetAsync(h->d_ctr, 0, NGS_CTR_STRIPES * 16 * 8, h->s_main));
 	CK(cudaStreamSynchronize(h->s_main));
 	h->pending = false; h->last_pushed = false; h->last_flags = 0; h->sticky_err = 0;
 	h->runs_done = false; h->formatted = false;
@@ -344,7 +355,20 @@ static int ensure_sub(ngscov *h, int64_t n_sub)
 		const size_t cap = (size_t)n_sub + (size_t)n_sub / 8 + 1024;
 		CK(cudaMalloc((void **)&h->d_entry, cap * 8));
 		CK(cudaMalloc((void **)&h->d_exit, cap * 8));
+		if (h->d_count) cudaFree(h->d_count);
+		h->d_count = nullptr;
+		CK(cudaMalloc((void **)&h->d_count, cap * 4));
 		h->sub_cap = cap;
+	}
+	if (!h->fused) {
+		const size_t need = ((size_t)n_sub << (h->shift - 5)) + 64;
+		if (need > h->slots_cap) {
+			CK(cudaStreamSynchronize(h->s_main));
+			if (h->d_slots) cudaFree(h->d_slots);
+			h->d_slots = nullptr; h->slots_cap = 0;
+			CK(cudaMalloc((void **)&h->d_slots, (need + need / 8) * 2));
+			h->slots_cap = need + need / 8;
+		}
 	}
 	const size_t nb = ((size_t)n_sub + NGS_VER_PER_BLOCK - 1) / NGS_VER_PER_BLOCK;
 	if (nb > h->bmax_cap) {
@@ -364,6 +388,7 @@ static IngestArgs make_ingest_args(ngscov *h, const uint8_t *base, int64_t n, in
 	A.cfg.n_ref = h->n_ref; A.cfg.flag_mask = h->cfg.mode == NGSCOV_MODE_DEPTH ? 0x704u : 0x4u;
 	A.cfg.ctg2seg = h->d_ctg2seg; A.cfg.seg = h->d_seg;
 	A.ref_len = h->d_ref_len; A.diff = h->d_diff; A.st = h->d_st;
+	A.count = h->d_count; A.slots = h->d_slots; A.slot_shift = h->shift - 5; A.ctr = h->d_ctr;
 	A.fixed_entry0 = fixed0; A.entry0_from_state = from_state ? 1 : 0;
 	A.debug = getenv("NGSCOV_DEBUG_INGEST") ? atoi(getenv("NGSCOV_DEBUG_INGEST")) : 0;
 	return A;
@@ -393,10 +418,18 @@ static int resolve_pending(ngscov *h)
 		const unsigned long long key = h->h_st->first_bad_key;
 		if ((key & 1) || iter > 100000) { h->sticky_err = NGSCOV_EFORMAT; h->pending = false; return NGSCOV_EFORMAT; }
 		IngestArgs A = make_ingest_args(h, h->p_base, h->p_n, h->p_nsub, h->p_from_state, h->p_fixed0);
-		k_repair<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
+		if (h->fused) k_repair<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
+		else k_repair_chain<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
 		h->stats.launches += 1;
+		h->p_k2_done = false;                    /* the optimistic K2 saw n_bad != 0 and did nothing */
 		int r = launch_verify(h);
 		if (r) return r;
+	}
+	if (!h->fused && !h->p_k2_done) {
+		IngestArgs A = make_ingest_args(h, h->p_base, h->p_n, h->p_nsub, h->p_from_state, h->p_fixed0);
+		k_decode_scatter<<<(unsigned)((h->p_nsub + 7) / 8), 256, 0, h->s_main>>>(A);
+		h->stats.launches += 1;
+		h->p_k2_done = true;
 	}
 	k_finalize_chunk<<<1, 256, 0, h->s_main>>>(h->p_base, h->p_n, h->d_st, h->d_carry);
 	h->stats.launches += 1;
@@ -425,24 +458,37 @@ static int submit_chunk(ngscov *h, const uint8_t *base, int64_t n, bool from_sta
 	if (r) return r;
 	IngestArgs A = make_ingest_args(h, base, n, n_sub, from_state, fixed0);
 	CK(cudaEventRecord(next_event(h->ev_ing, h->n_ing), h->s_main));
-	/* The shared-memory staged variant is kept selectable (NGSCOV_TILES=1) but is not the default: on B200 it
-	 * measured slower than walking in HBM because its 64 KB tiles cap occupancy at 6 warps/SM, and the
-	 * profile shows the walk is bound by RED traffic, not by stream-read latency (ingest). */
-	const char *tenv = getenv("NGSCOV_TILES");
-	const bool tiles = tenv && atoi(tenv) == 1 && h->shift <= 10 && (((uintptr_t)base) & 15) == 0;
-	if (tiles) {
-		const size_t smem = ((size_t)NGS_TILE_THREADS << h->shift) + NGS_TILE_MARGIN;
-		const unsigned nb = (unsigned)((n_sub + NGS_TILE_THREADS - 1) / NGS_TILE_THREADS);
-		k_ingest_tiles<<<nb, NGS_TILE_THREADS, smem, h->s_main>>>(A);
-	} else {
+	if (!h->fused) {
+		/* K1: frame the records (speculative chain walk, no atomics, full occupancy) */
 		const unsigned nb = (unsigned)((n_sub + 255) / 256);
-		k_ingest_walk<<<nb, 256, 0, h->s_main>>>(A);
+		k_chain_walk<<<nb, 256, 0, h->s_main>>>(A);
+	} else {
+		/* single-kernel variants (NGSCOV_FUSED=1; NGSCOV_TILES=1 stages tiles in shared memory): kept for A/B
+		 * measurements, see DESIGN.md section 4 */
+		const char *tenv = getenv("NGSCOV_TILES");
+		const bool tiles = tenv && atoi(tenv) == 1 && h->shift <= 10 && (((uintptr_t)base) & 15) == 0;
+		if (tiles) {
+			const size_t smem = ((size_t)NGS_TILE_THREADS << h->shift) + NGS_TILE_MARGIN;
+			const unsigned nb = (unsigned)((n_sub + NGS_TILE_THREADS - 1) / NGS_TILE_THREADS);
+			k_ingest_tiles<<<nb, NGS_TILE_THREADS, smem, h->s_main>>>(A);
+		} else {
+			const unsigned nb = (unsigned)((n_sub + 255) / 256);
+			k_ingest_walk<<<nb, 256, 0, h->s_main>>>(A);
+		}
 	}
 	h->stats.launches += 1;
 	CK(cudaGetLastError());
 	h->pending = true; h->p_base = base; h->p_n = n; h->p_nsub = n_sub; h->p_from_state = from_state; h->p_fixed0 = fixed0;
 	h->diff_dirty = true;
 	r = launch_verify(h);
+	if (!r && !h->fused) {
+		/* K2 queued optimistically behind the verification: it returns at once if a mismatch was found,
+		 * and is then launched again by resolve_pending after the repair */
+		k_decode_scatter<<<(unsigned)((n_sub + 7) / 8), 256, 0, h->s_main>>>(A);
+		h->stats.launches += 1;
+		h->p_k2_done = true;
+		CK(cudaGetLastError());
+	}
 	CK(cudaEventRecord(next_event(h->ev_ing, h->n_ing), h->s_main));
 	return r;
 }
@@ -568,8 +614,13 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 	int r = resolve_pending(h);
 	if (r) return r;
 	CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, NGS_CTR_STRIPES * 16 * 8, cudaMemcpyDeviceToHost, h->s_main));
 	CK(cudaStreamSynchronize(h->s_main));
 	CK(cudaStreamSynchronize(h->s_copy));
+	for (int i = 0; i < NGS_CTR_STRIPES; ++i) {     /* K2 counts in stripes; the fused variant counts in the state block */
+		h->h_st->records += h->h_ctr[i * 16 + 0]; h->h_st->kept += h->h_ctr[i * 16 + 1];
+		h->h_st->m_ops += h->h_ctr[i * 16 + 2]; h->h_st->cigar_words += h->h_ctr[i * 16 + 3];
+	}
 	h->stats.ms_ingest += sum_events(h->ev_ing, h->n_ing);
 	h->stats.ms_h2d += sum_events(h->ev_cp, h->n_cp);
 	const ngs_dev_state st = *h->h_st;

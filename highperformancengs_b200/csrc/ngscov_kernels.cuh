@@ -26,7 +26,18 @@
 #define NGS_TILE         (NGS_SCAN_THREADS * NGS_SCAN_ITEMS)   /* 4096 difference-array elements */
 #define NGS_FMT_THREADS  256
 #define NGS_BAD_CAP      4096
+#ifndef NGS_SCAN_MINB
+#define NGS_SCAN_MINB 8
+#endif
+#ifndef NGS_ING_MINB
+#define NGS_ING_MINB 1
+#endif
+#ifndef NGS_FMT_MINB
+#define NGS_FMT_MINB 1
+#endif
 
+#define NGS_CTR_STRIPES  64           /* counter stripes, one 128-byte line each: same-address atomics from ~10^6
+                                         warps otherwise serialise in L2 and stall every load of the state line */
 #define NGS_FLAG_ERANGE  1u
 #define NGS_FLAG_EFORMAT 2u
 
@@ -51,6 +62,10 @@ struct ngs_dev_state {
 	unsigned long long fmt_ticket;
 	unsigned long long fmt_bytes;
 };
+
+/* numeric value of an exit slot for the running max */
+__device__ __forceinline__ long long exit_num(long long x) { return x == NGS_EXIT_INVALID ? 0 : x; }
+#define NGS_VER_PER_BLOCK 1024   /* sub-chunks per verify block: 256 threads x 4 */
 
 /* ------------------------------------------------------------------------------------------------ */
 /* memory policy: unaligned little-endian field access on the inflated stream in HBM               */
@@ -167,11 +182,15 @@ struct IngestArgs {
 	int shift;                             /* log2(sub-chunk bytes) */
 	int64_t n_sub;
 	long long *entry, *exit;               /* [n_sub] */
+	unsigned int *count;                   /* [n_sub] records starting in the sub-chunk */
+	unsigned short *slots;                 /* [n_sub << slot_shift] record offsets relative to the sub-chunk's entry */
+	int slot_shift;                        /* log2(slots per sub-chunk) = shift - 5 (a record is >= 36 bytes) */
 	ngs_walk_cfg cfg;
 	const uint32_t *ref_len;
 	int *diff;
 	ngs_dev_state *st;
 	int debug;                             /* timing experiments only: bit0 no atomics */
+	unsigned long long *ctr;               /* [NGS_CTR_STRIPES][16] striped counters: records, kept, m_ops, cigar_words */
 	long long fixed_entry0;                /* used when entry0_from_state == 0 */
 	int entry0_from_state;                 /* 1: first entry = st->entry_next (streamed pushes) */
 };
@@ -186,7 +205,7 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 /* K1+K2: one thread per sub-chunk.  Both phases run warp-synchronously so that the 32 independent
  * chains of a warp stay converged: (1) the entry search alternates a cheap byte scan with a converged
  * deep validation round; (2) the walk advances every live chain by one record per iteration. */
-__global__ void __launch_bounds__(256) k_ingest_walk(IngestArgs A)
+__global__ void __launch_bounds__(256, NGS_ING_MINB) k_ingest_walk(IngestArgs A)
 {
 	const unsigned full = 0xffffffffu;
 	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,6 +251,181 @@ __global__ void __launch_bounds__(256) k_ingest_walk(IngestArgs A)
 		if (v2) atomicAdd(&A.st->m_ops, v2);
 		if (v3) atomicAdd(&A.st->cigar_words, v3);
 		if (v4) atomicAdd(&A.st->spec_walks, v4);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* K1: record-offset discovery.  Same speculative sub-chunk chain walk as k_ingest_walk, but it only
+ * frames records: every record start found is written to the sub-chunk's slot row (16-bit offset from
+ * the sub-chunk's entry).  It needs few registers (full occupancy hides the dependent-load latency of
+ * the chain) and issues no atomics; after k_verify_* / k_repair_chain have made the chains consistent
+ * the decode runs as K2 with one thread per RECORD, where consecutive lanes hold consecutive records:
+ * their loads and their +1/-1 REDs then fall into a handful of cache lines per warp instead of 32. */
+template <class Mem>
+__device__ __forceinline__ long long chain_walk(const ngs_walk_cfg &cfg, const Mem &mem, long long entry, int64_t hi,
+                                                unsigned short *row, unsigned int n_slots, unsigned int &count)
+{
+	const int64_t n = mem.size();
+	int64_t o = entry;
+	count = 0;
+	if (o >= hi) return o;
+	if (o + 36 > n) return NGS_EXIT_PARTIAL(o);
+	ngs_hdr h;
+	mem.hdr_lite(o, h);
+	for (;;) {
+		if (!ngs_hdr_valid(h, cfg.n_ref)) return NGS_EXIT_INVALID;
+		if (o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar > n) return NGS_EXIT_PARTIAL(o);
+		if (count < n_slots) row[count] = (unsigned short)(o - entry);
+		++count;
+		const int64_t nx = o + 4 + (int64_t)h.block_size;
+		if (nx >= hi) return nx;
+		if (nx + 36 > n) return NGS_EXIT_PARTIAL(nx);
+		mem.hdr_lite(nx, h);
+		o = nx;
+	}
+}
+
+__global__ void __launch_bounds__(256, 8) k_chain_walk(IngestArgs A)
+{
+	const unsigned full = 0xffffffffu;
+	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = c < A.n_sub;
+	DevMem mem = { A.base, A.n };
+	const int64_t lo = live ? (c << A.shift) : 0;
+	int64_t hi = live ? lo + ((int64_t)1 << A.shift) : 0;
+	if (hi > A.n) hi = A.n;
+	long long entry = NGS_NONE;
+	bool searching = live && c != 0;
+	if (live && c == 0) {
+		const long long e0 = A.entry0_from_state ? A.st->entry_next : A.fixed_entry0;
+		entry = e0 < hi ? e0 : NGS_NONE;
+	}
+	{
+		const int64_t end = hi < A.n - 35 ? hi : A.n - 35;
+		int64_t o = lo;
+		while (__any_sync(full, searching)) {
+			if (searching) { o = mem.next_candidate(o, end, (uint32_t)A.cfg.n_ref); if (o == NGS_NONE) searching = false; }
+			__syncwarp();
+			if (searching) {
+				if (ngs_candidate_ok(A.cfg, mem, A.ref_len, o)) { entry = o; searching = false; } else ++o;
+			}
+		}
+	}
+	unsigned int count = 0; long long ex = 0;
+	if (entry != NGS_NONE) ex = chain_walk(A.cfg, mem, entry, hi, A.slots + ((size_t)c << A.slot_shift), 1u << A.slot_shift, count);
+	if (live) { A.entry[c] = entry; A.exit[c] = ex; A.count[c] = count; }
+	const unsigned long long w = warp_sum_u64(entry != NGS_NONE ? 1ull : 0ull);
+	if ((threadIdx.x & 31) == 0 && w) atomicAdd(&A.st->spec_walks, w);
+}
+
+/* Rare path, single thread: zip the true chain forward from the first mismatching sub-chunk until it
+ * meets an already-framed entry, rewriting entry / exit / count / slots on the way. */
+__global__ void k_repair_chain(IngestArgs A, long long first_bad, const long long *bexcl)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	DevMem mem = { A.base, A.n };
+	long long cur = bexcl[first_bad / NGS_VER_PER_BLOCK];
+	for (long long k = (first_bad / NGS_VER_PER_BLOCK) * NGS_VER_PER_BLOCK; k < first_bad; ++k) {
+		const long long x = exit_num(A.exit[k]);
+		cur = x > cur ? x : cur;
+	}
+	long long c = first_bad, repaired = 0;
+	for (;;) {
+		long long cc = cur >= A.n ? A.n_sub : (cur < 0 ? 0 : (cur >> A.shift));
+		if (cc > A.n_sub) cc = A.n_sub;
+		for (long long k = c; k < cc; ++k)              /* sub-chunks the true chain jumps over hold no record start */
+			if (A.entry[k] != NGS_NONE) { A.entry[k] = NGS_NONE; A.exit[k] = 0; A.count[k] = 0; ++repaired; }
+		if (cc >= A.n_sub) break;
+		if (A.entry[cc] == cur) break;                  /* converged */
+		long long hi = (cc + 1) << A.shift; if (hi > A.n) hi = A.n;
+		unsigned int cnt = 0;
+		const long long x = chain_walk(A.cfg, mem, cur, hi, A.slots + ((size_t)cc << A.slot_shift), 1u << A.slot_shift, cnt);
+		A.entry[cc] = cur; A.exit[cc] = x; A.count[cc] = cnt; ++repaired;
+		c = cc + 1;
+		cur = (x == NGS_EXIT_INVALID || x >= NGS_EXIT_INF) ? A.n : x;
+	}
+	atomicAdd(&A.st->spec_repaired, (unsigned long long)repaired);
+}
+
+/* K2 sink: one record per lane.  Sorted input puts equal positions in adjacent lanes, so pile-ups
+ * (targeted panels: thousands of reads starting at one base) are folded with a warp match before the
+ * RED; `fold` is decided once per record batch from the headers, plain REDs otherwise. */
+struct WarpSink {
+	int *diff; unsigned int *flags; int dbg; bool fold;
+	__device__ __forceinline__ void one(uint64_t idx, int v)
+	{
+		if (dbg & 1) return;                                   /* timing experiment: no atomics */
+		if (fold) {
+			const unsigned m = __match_any_sync(__activemask(), idx);
+			if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(diff + idx, v * __popc(m));
+		} else atomicAdd(diff + idx, v);
+	}
+	__device__ __forceinline__ void add2(uint64_t ia, uint64_t ib, int sign) { one(ia, sign); one(ib, -sign); }
+	__device__ __forceinline__ void flag_range_error() { atomicOr(flags, NGS_FLAG_ERANGE); }
+};
+
+/* K2: core/CIGAR decode + scatter.  One warp per sub-chunk row; a lane takes slots lane and lane+32 of
+ * each 64-slot batch and requests both headers before decoding either (two independent loads in
+ * flight per lane, consecutive lanes = consecutive records = neighbouring cache lines). */
+__global__ void __launch_bounds__(256) k_decode_scatter(IngestArgs A)
+{
+	const unsigned full = 0xffffffffu;
+	const ngs_dev_state *st = A.st;
+	if (st->n_bad != 0 || (st->flags & NGS_FLAG_EFORMAT)) return;      /* launched optimistically behind the verification */
+	const int lane = threadIdx.x & 31;
+	const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	ngs_counts cnt = { 0, 0, 0, 0 };
+	if (c < A.n_sub) {
+		const unsigned int n_slots = 1u << A.slot_shift, have = A.count[c];
+		const unsigned int framed = have < n_slots ? have : n_slots;
+		if (framed) {
+			const long long e = A.entry[c];
+			const unsigned short *row = A.slots + ((size_t)c << A.slot_shift);
+			DevMem mem = { A.base, A.n };
+			WarpSink sink = { A.diff, &A.st->flags, A.debug, false };
+			for (unsigned int b = 0; b < framed; b += 64) {
+				const unsigned int k0 = b + lane, k1 = b + 32 + lane;
+				const bool a0 = k0 < framed, a1 = k1 < framed;
+				int64_t o0 = 0, o1 = 0;
+				ngs_hdr h0, h1;
+				h0.pos = -2 - lane; h1.pos = -2 - lane; h0.ref_id = h1.ref_id = -1;
+				if (a0) { o0 = e + row[k0]; mem.hdr_lite(o0, h0); }
+				if (a1) { o1 = e + row[k1]; mem.hdr_lite(o1, h1); }
+				/* pile-up detection: does any lane share its start with the next lane? */
+				const int p0n = __shfl_down_sync(full, h0.pos, 1), p1n = __shfl_down_sync(full, h1.pos, 1);
+				const bool d0 = __any_sync(full, a0 && lane < 31 && p0n == h0.pos);
+				const bool d1 = __any_sync(full, a1 && lane < 31 && p1n == h1.pos);
+				sink.fold = d0;
+				if (a0) ngs_decode_record(A.cfg, mem, o0, h0, sink, +1, cnt);
+				__syncwarp();
+				sink.fold = d1;
+				if (a1) ngs_decode_record(A.cfg, mem, o1, h1, sink, +1, cnt);
+				__syncwarp();
+				/* records beyond the row's capacity (only possible with pathologically small records): the lane
+				 * holding the last slot keeps walking the chain */
+				if (have > n_slots && (k0 == n_slots - 1 || k1 == n_slots - 1)) {
+					int64_t o = (k0 == n_slots - 1) ? o0 + 4 + (int64_t)h0.block_size : o1 + 4 + (int64_t)h1.block_size;
+					sink.fold = false;
+					for (unsigned int r = n_slots; r < have; ++r) {
+						ngs_hdr h;
+						mem.hdr_lite(o, h);
+						ngs_decode_record(A.cfg, mem, o, h, sink, +1, cnt);
+						o += 4 + (int64_t)h.block_size;
+					}
+				}
+			}
+		}
+	}
+	/* block-level reduction, then one atomic per counter per CTA into this CTA's stripe */
+	__shared__ unsigned long long s_c[8][4];
+	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
+	                   v2 = warp_sum_u64(cnt.m_ops), v3 = warp_sum_u64(cnt.cigar_words);
+	if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5][0] = v0; s_c[threadIdx.x >> 5][1] = v1; s_c[threadIdx.x >> 5][2] = v2; s_c[threadIdx.x >> 5][3] = v3; }
+	__syncthreads();
+	if (threadIdx.x < 4) {
+		unsigned long long t = 0;
+		for (int w = 0; w < 8; ++w) t += s_c[w][threadIdx.x];
+		if (t) atomicAdd(A.ctr + (size_t)(blockIdx.x % NGS_CTR_STRIPES) * 16 + threadIdx.x, t);
 	}
 }
 
@@ -385,8 +579,6 @@ __global__ void __launch_bounds__(NGS_TILE_THREADS) k_ingest_tiles(IngestArgs A)
 	}
 }
 
-/* numeric value of an exit slot for the running max */
-__device__ __forceinline__ long long exit_num(long long x) { return x == NGS_EXIT_INVALID ? 0 : x; }
 
 __device__ __forceinline__ long long block_max_ll(long long v, long long *sm)
 {
@@ -401,7 +593,6 @@ __device__ __forceinline__ long long block_max_ll(long long v, long long *sm)
 	return r;
 }
 
-#define NGS_VER_PER_BLOCK 1024   /* sub-chunks per verify block: 256 threads x 4 */
 
 __global__ void __launch_bounds__(256) k_verify_blockmax(const long long *exit, int64_t n_sub, long long *bmax)
 {
@@ -616,7 +807,7 @@ struct BinAcc {   /* per-thread pending (bin, value): consecutive runs of a thre
 	}
 };
 
-__global__ void __launch_bounds__(NGS_SCAN_THREADS) k_scan_runs(ScanArgs A)
+__global__ void __launch_bounds__(NGS_SCAN_THREADS, NGS_SCAN_MINB) k_scan_runs(ScanArgs A)
 {
 	__shared__ __align__(16) int s_tile[NGS_TILE / 2 + NGS_TILE];   /* phase 1: 256 x (16 + 4 pad) ints for the transposition (conflict-free
 	                                                                    128-bit reads); phase 2: compact boundary list (u16 pos + i32 depth) */
@@ -962,7 +1153,7 @@ struct FmtArgs {
 };
 
 template <class Producer, int IPT>
-__global__ void __launch_bounds__(NGS_FMT_THREADS) k_format_lines(FmtArgs A, Producer P)
+__global__ void __launch_bounds__(NGS_FMT_THREADS, NGS_FMT_MINB) k_format_lines(FmtArgs A, Producer P)
 {
 	extern __shared__ __align__(16) char s_stage[];
 	__shared__ unsigned int s_w[8], s_li[8];

@@ -63,9 +63,15 @@ def test_random_cases(oracle, mode, mname, seed, window):
 
 @pytest.mark.parametrize("staging", [4096, 70000])
 @pytest.mark.parametrize("sub", ["64", "512"])
-def test_straddling_pushes(oracle, monkeypatch, staging, sub):
-    """records cut by push boundaries (carry path) and tiny sub-chunks (speculation + repair path)"""
+@pytest.mark.parametrize("variant", ["fused", "split", "tiles"])
+def test_straddling_pushes(oracle, monkeypatch, staging, sub, variant):
+    """records cut by push boundaries (carry path) and tiny sub-chunks (speculation + repair path), for
+    every ingest organisation: fused walk+decode, K1 frame / K2 decode split, shared-memory staged tiles"""
     monkeypatch.setenv("NGSCOV_SUBCHUNK", sub)
+    if variant == "split":
+        monkeypatch.setenv("NGSCOV_SPLIT", "1")
+    if variant == "tiles":
+        monkeypatch.setenv("NGSCOV_TILES", "1")
     names, lens, reads = bamutil.random_case(7, n_reads=4000)
     recs = bamutil.records(reads)
     exp = oracle.run(recs, names, lens, 0, 500)
@@ -84,7 +90,10 @@ def test_empty_input(oracle):
 
 @pytest.mark.parametrize("config,scale,window", [(1, 0.05, 20000), (2, 0.0005, 20000), (4, 0.01, 100), (4, 0.01, 20000), (5, 0.002, 20000)])
 @pytest.mark.parametrize("resident", [False, True])
-def test_generator_configs(oracle, config, scale, window, resident):
+@pytest.mark.parametrize("variant", ["fused", "split"])
+def test_generator_configs(oracle, monkeypatch, config, scale, window, resident, variant):
+    if variant == "split":
+        monkeypatch.setenv("NGSCOV_SPLIT", "1")
     from highperformancengs_b200.gen import Generator
     g = Generator(config, scale=scale)
     recs = g.records()
