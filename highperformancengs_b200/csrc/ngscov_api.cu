@@ -752,6 +752,7 @@ static int run_format(ngscov *h, int which, unsigned long long n_items, const Pr
 	if ((r = ensure_buf(h, &h->d_text[which], &cap, bound + 64))) return r;
 	h->d_text_cap[which] = cap;
 	int ipt = 4;
+	if (getenv("NGSCOV_FMT_IPT")) { const int v = atoi(getenv("NGSCOV_FMT_IPT")); if (v == 1 || v == 2 || v == 4) ipt = v; }
 	const uint32_t smem_max = 96 * 1024;
 	while (ipt > 1 && (size_t)NGS_FMT_THREADS * ipt * max_line + 32 > smem_max) ipt >>= 1;
 	uint32_t stage = (uint32_t)std::min<size_t>((size_t)NGS_FMT_THREADS * ipt * max_line + 32, smem_max);

@@ -144,6 +144,32 @@ NGS_HD uint32_t ngs_put_u32(Ptr dst, uint32_t v)
 	for (uint32_t i = n; i-- > 0;) { uint32_t q = v / 10u; dst[i] = (char)('0' + (v - q * 10u)); v = q; }
 	return n;
 }
+/* eight decimal digits of v (< 10^8) as ASCII, most significant digit in the LOWEST byte, computed with
+ * three SWAR divide steps on packed lanes instead of eight dependent divisions by ten */
+NGS_HD uint64_t ngs_digits8(uint32_t v)
+{
+	const uint32_t hi4 = v / 10000u, lo4 = v - hi4 * 10000u;
+	uint64_t x = (uint64_t)hi4 | ((uint64_t)lo4 << 32);                 /* two 4-digit numbers in 32-bit lanes */
+	uint64_t q = ((x * 5243ull) >> 19) & 0x0000007F0000007Full;          /* /100 per lane (exact below 10^4) */
+	x = q | ((x - q * 100ull) << 16);                                    /* four 2-digit numbers in 16-bit lanes */
+	q = ((x * 103ull) >> 10) & 0x000F000F000F000Full;                    /* /10 per lane (exact below 100) */
+	x = q | ((x - q * 10ull) << 8);                                      /* eight digits in byte lanes */
+	return x + 0x3030303030303030ull;
+}
+/* writes the n (1..10) digits of v at dst */
+template <class Ptr>
+NGS_HD void ngs_put_u32_swar(Ptr dst, uint32_t v, uint32_t n)
+{
+	const uint32_t top = v / 100000000u;                                 /* 0..42 */
+	uint64_t d = ngs_digits8(v - top * 100000000u);
+	if (n > 8) {
+		if (n == 10) { dst[0] = (char)('0' + top / 10u); dst[1] = (char)('0' + top % 10u); dst += 2; }
+		else { dst[0] = (char)('0' + top); dst += 1; }
+		n = 8;
+	}
+	d >>= 8 * (8 - n);
+	for (uint32_t i = 0; i < n; ++i) { dst[i] = (char)(d & 0xff); d >>= 8; }
+}
 /* same with the digit count already known */
 template <class Ptr>
 NGS_HD void ngs_put_u32n(Ptr dst, uint32_t v, uint32_t n)

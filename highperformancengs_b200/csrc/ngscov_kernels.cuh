@@ -1069,8 +1069,8 @@ struct BedProducer {
 		}
 		dst += nl;
 		const uint32_t ns = it.nd & 0xff, ne = (it.nd >> 8) & 0xff;
-		ngs_put_u32n(dst, it.s, ns); dst += ns; *dst++ = '\t';
-		ngs_put_u32n(dst, it.e, ne); dst += ne; *dst++ = '\t';
+		ngs_put_u32_swar(dst, it.s, ns); dst += ns; *dst++ = '\t';
+		ngs_put_u32_swar(dst, it.e, ne); dst += ne; *dst++ = '\t';
 		dst += ngs_put_i32(dst, it.d); *dst = '\n';
 	}
 };
