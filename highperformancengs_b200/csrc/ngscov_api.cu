@@ -70,6 +70,16 @@ struct ngscov {
 	char *h_text[4]; size_t h_text_cap[4]; bool h_text_valid[4];
 	std::string chromsize;
 
+	/* streaming per-contig finalize (single shard, sorted input): scan + format + D2H of a contig start as soon
+	 * as a higher refID has been decoded, so the device->host copy of the text overlaps the host->device copy
+	 * of the rest of the stream */
+	bool stream_fin; size_t next_fin_seg; unsigned long long mops_fin; bool bins_zeroed;
+	size_t bed_off;                          /* bedGraph bytes produced so far */
+	size_t bed_d2h;                          /* ... of which already queued for D2H */
+	ngs_dev_state *h_st2;                    /* pinned read-back of the state block after scan / format launches */
+	cudaStream_t s_out; cudaEvent_t ev_fmt;
+	unsigned long long acc_boundaries, acc_runs; int acc_max, acc_min;
+
 	ngscov_stats_t stats;
 	int sm_count;
 	/* per-push timing events (start/end pairs), reused across inputs */
@@ -203,6 +213,8 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	h->sm_count = prop.multiProcessorCount;
 	CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&h->ev_fmt, cudaEventDisableTiming));
 	for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&h->ev_verified, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&h->ev_finalized, cudaEventDisableTiming));
@@ -251,11 +263,13 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	CK(cudaMalloc((void **)&h->d_carry, NGS_CARRY_MAX));
 	CK(cudaMalloc((void **)&h->d_st, sizeof(ngs_dev_state)));
 	CK(cudaHostAlloc((void **)&h->h_st, sizeof(ngs_dev_state), cudaHostAllocDefault));
+	CK(cudaHostAlloc((void **)&h->h_st2, sizeof(ngs_dev_state), cudaHostAllocDefault));
 	CK(cudaMalloc((void **)&h->d_ctr, NGS_CTR_STRIPES * 16 * 8));
 	CK(cudaHostAlloc((void **)&h->h_ctr, NGS_CTR_STRIPES * 16 * 8, cudaHostAllocDefault));
 	h->stage_cap = cfg->staging_bytes ? (size_t)cfg->staging_bytes : (size_t)256 << 20;
 	/* Two ingest organisations are kept, both parity-tested: the fused walk+decode kernel (default: fastest on
 	 * B200 today) and the K1 frame / K2 per-record decode split (NGSCOV_SPLIT=1), see DESIGN.md section 4. */
+	h->stream_fin = cfg->slice_end == 0 && !(getenv("NGSCOV_STREAM_FINALIZE") && atoi(getenv("NGSCOV_STREAM_FINALIZE")) == 0);
 	h->fused = !(getenv("NGSCOV_SPLIT") && atoi(getenv("NGSCOV_SPLIT")) == 1);
 	h->shift = 0;
 	const char *env = getenv("NGSCOV_SUBCHUNK");
@@ -277,6 +291,9 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	for (int i = 0; i < 4; ++i) if (h->h_text[i]) cudaFreeHost(h->h_text[i]);
 	if (h->h_st) cudaFreeHost(h->h_st);
 	if (h->h_ctr) cudaFreeHost(h->h_ctr);
+	if (h->h_st2) cudaFreeHost(h->h_st2);
+	if (h->s_out) cudaStreamDestroy(h->s_out);
+	if (h->ev_fmt) cudaEventDestroy(h->ev_fmt);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
 	if (h->s_copy) cudaStreamDestroy(h->s_copy);
 	for (int i = 0; i < 2; ++i) if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -313,6 +330,9 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	for (int i = 0; i < 4; ++i) { h->text_len[i] = 0; h->text_ready[i] = false; h->h_text_valid[i] = false; }
 	h->stage_busy[0] = h->stage_busy[1] = false;
 	h->n_ing = 0; h->n_cp = 0;
+	CK(cudaStreamSynchronize(h->s_out));
+	h->next_fin_seg = 0; h->mops_fin = 0; h->bins_zeroed = false; h->bed_off = 0; h->bed_d2h = 0;
+	h->acc_boundaries = h->acc_runs = 0; h->acc_max = h->acc_min = 0;
 	return 0;
 }
 
@@ -320,7 +340,7 @@ extern "C" int ngscov_sync(ngscov_t *h)
 {
 	if (!h) return NGSCOV_EINVAL;
 	CK(cudaSetDevice(h->device));
-	CK(cudaStreamSynchronize(h->s_copy)); CK(cudaStreamSynchronize(h->s_main));
+	CK(cudaStreamSynchronize(h->s_copy)); CK(cudaStreamSynchronize(h->s_main)); CK(cudaStreamSynchronize(h->s_out));
 	return 0;
 }
 
@@ -409,7 +429,9 @@ static int launch_verify(ngscov *h)
 }
 
 /* wait for the verification of the chunk in flight; repair mis-speculated sub-chunks; fix the carry */
-static int resolve_pending(ngscov *h)
+static int stream_finalize(ngscov *h, size_t seg_end);
+
+static int resolve_pending(ngscov *h, bool allow_stream = false)
 {
 	if (!h->pending) return 0;
 	for (int iter = 0; ; ++iter) {
@@ -436,6 +458,11 @@ static int resolve_pending(ngscov *h)
 	CK(cudaEventRecord(h->ev_finalized, h->s_main));
 	CK(cudaGetLastError());
 	h->pending = false;
+	/* sorted input: every contig below the highest refID decoded so far is complete */
+	if (allow_stream && h->stream_fin && h->fused && !(h->h_st->flags & (NGS_FLAG_EFORMAT | NGS_FLAG_ERANGE)) && h->h_st->max_ref_p1 > 1) {
+		const size_t upto = std::min<size_t>(h->h_st->max_ref_p1 - 1, h->seg.size());
+		if (upto > h->next_fin_seg) return stream_finalize(h, upto);
+	}
 	return 0;
 }
 
@@ -499,7 +526,7 @@ extern "C" int ngscov_push(ngscov_t *h, int idx, size_t nbytes, int flags)
 	if (h->runs_done || h->last_pushed) return NGSCOV_ESTATE;
 	if (h->sticky_err) return h->sticky_err;
 	CK(cudaSetDevice(h->device));
-	int r = resolve_pending(h);
+	int r = resolve_pending(h, true);
 	if (r) return r;
 	if (flags & NGSCOV_PUSH_LAST) { h->last_pushed = true; h->last_flags = flags; }
 	h->stats.stream_bytes += nbytes;
@@ -556,7 +583,7 @@ extern "C" int ngscov_push_host(ngscov_t *h, const void *host, size_t nbytes, in
 	if ((r = issue_h2d(h, idx, src, std::min(cap, nbytes)))) return r;
 	for (size_t k = 0; k < nchunks; ++k, idx ^= 1) {
 		const size_t off = k * cap, m = std::min(cap, nbytes - off);
-		if ((r = resolve_pending(h))) return r;                      /* chunk k-1 verified, its buffer is free */
+		if ((r = resolve_pending(h, true))) return r;                /* chunk k-1 verified, its buffer is free */
 		if (k + 1 < nchunks && (r = issue_h2d(h, idx ^ 1, src + off + m, std::min(cap, nbytes - off - m)))) return r;
 		uint8_t *data = h->d_chunk[idx] + NGS_HEADROOM;
 		CK(cudaStreamWaitEvent(h->s_main, h->ev_h2d[idx], 0));
@@ -605,6 +632,79 @@ static int ensure_buf(ngscov *h, T **p, size_t *cap, size_t need)
 	return 0;
 }
 
+/* Scan + run compaction + window bins over segments [s0, s1).  Records are written from index 0 of the
+ * run buffers; h_rec_base[0..s1-s0] receives the per-segment record offsets, h_st2 the counters. */
+static int scan_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_bound)
+{
+	int r;
+	const uint64_t t0 = h->seg[s0].tile0, t1 = s1 < h->seg.size() ? h->seg[s1].tile0 : h->n_tiles;
+	const uint64_t elems = (t1 - t0) * (uint64_t)NGS_TILE;
+	/* boundary records: at most two per accumulated M interval, never more than tracked positions */
+	const size_t need = (size_t)std::min<unsigned long long>(2ull * mops_bound, elems) + 16;
+	{
+		size_t cap0 = h->run_cap, cap1 = h->run_cap, cap2 = h->run_cap;
+		if ((r = ensure_buf(h, &h->d_run_start, &cap0, need))) return r;
+		if ((r = ensure_buf(h, &h->d_run_end, &cap1, need))) return r;
+		if ((r = ensure_buf(h, &h->d_run_depth, &cap2, need))) return r;
+		h->run_cap = std::min(cap0, std::min(cap1, cap2));
+	}
+	tic(h);
+	if (t1 > t0) {
+		CK(cudaMemsetAsync(h->d_stA + t0, 0, (t1 - t0) * 8, h->s_main));
+		CK(cudaMemsetAsync(h->d_stB + t0, 0, (t1 - t0) * 8, h->s_main));
+	}
+	if (!h->bins_zeroed) { CK(cudaMemsetAsync(h->d_bins, 0, h->n_bins * 8, h->s_main)); h->bins_zeroed = true; }
+	{	/* reset only the scan fields of the device state block (the ingest fields stay live) */
+		ngs_dev_state *t = h->h_st2;
+		memset(t, 0, sizeof *t);
+		t->first_run = ~0ull;
+		const size_t o0 = offsetof(ngs_dev_state, scan_ticket), o1 = offsetof(ngs_dev_state, fmt_ticket);
+		CK(cudaMemcpyAsync((char *)h->d_st + o0, (char *)t + o0, o1 - o0, cudaMemcpyHostToDevice, h->s_main));
+		CK(cudaStreamSynchronize(h->s_main));          /* h_st2 is reused as the read-back buffer below */
+	}
+	if (t1 > t0) {
+		ScanArgs A;
+		A.diff = h->d_diff; A.tile_first = t0; A.n_tiles = t1; A.seg_first = (uint32_t)s0;
+		A.tile2seg = h->d_tile2seg; A.seg = h->d_seg;
+		A.stA = h->d_stA; A.stB = h->d_stB;
+		A.run_start = h->d_run_start; A.run_end = h->d_run_end; A.run_depth = h->d_run_depth; A.run_cap = h->run_cap;
+		A.rec_base = h->d_rec_base; A.n_seg = (uint32_t)s1;
+		A.bins = h->d_bins; A.window = h->cfg.window; A.variant = h->cfg.mode == NGSCOV_MODE_WIG ? 1 : 0;
+		A.rezero = 1; A.st = h->d_st;
+		A.debug = getenv("NGSCOV_DEBUG_SCAN") ? atoi(getenv("NGSCOV_DEBUG_SCAN")) : 0;
+		k_scan_runs<<<(unsigned)(t1 - t0), NGS_SCAN_THREADS, 0, h->s_main>>>(A);
+		h->stats.launches += 1;
+		CK(cudaGetLastError());
+	}
+	CK(cudaMemcpyAsync(h->h_st2, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
+	h->h_rec_base.assign(h->seg.size() + 1, 0);
+	if (t1 > t0) CK(cudaMemcpyAsync(h->h_rec_base.data(), h->d_rec_base, (s1 - s0 + 1) * 8, cudaMemcpyDeviceToHost, h->s_main));
+	h->stats.ms_scan += toc(h);
+	const ngs_dev_state &s2 = *h->h_st2;
+	h->acc_boundaries += s2.n_boundaries; h->acc_runs += s2.n_runs;
+	h->acc_max = std::max(h->acc_max, s2.max_depth); h->acc_min = std::min(h->acc_min, s2.min_depth);
+	h->stats.boundaries = h->acc_boundaries; h->stats.runs = h->acc_runs; h->stats.positions = h->n_elems;
+	if (s2.n_boundaries > h->run_cap) return h->sticky_err = NGSCOV_ENOMEM;
+	return 0;
+}
+
+static int format_bed_range(ngscov *h, size_t s0, size_t s1);
+
+/* Finalize segments [next_fin_seg, seg_end) while the rest of the stream is still arriving. */
+static int stream_finalize(ngscov *h, size_t seg_end)
+{
+	int r;
+	const unsigned long long mops_now = h->h_st->m_ops;
+	const size_t s0 = h->next_fin_seg;
+	if ((r = scan_range(h, s0, seg_end, mops_now - h->mops_fin))) return r;
+	/* how many of the intervals seen so far belong to the finished contigs is not known exactly; every interval
+	 * makes at most two boundaries, so boundaries/2 is a safe lower bound of what they consumed */
+	h->mops_fin += h->h_st2->n_boundaries / 2;
+	if (h->cfg.mode == NGSCOV_MODE_DEPTH && (r = format_bed_range(h, s0, seg_end))) return r;
+	h->next_fin_seg = seg_end;
+	return 0;
+}
+
 extern "C" int ngscov_finish_runs(ngscov_t *h)
 {
 	if (!h) return NGSCOV_EINVAL;
@@ -630,58 +730,31 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 	if ((st.entry_next != 0 || st.carry_len != 0) && !(h->last_flags & NGSCOV_PUSH_TRUNCATED_OK)) return h->sticky_err = NGSCOV_EFORMAT;
 	if (st.flags & NGS_FLAG_ERANGE) return h->sticky_err = NGSCOV_ERANGE;
 
-	/* boundary records: at most two per accumulated M interval, never more than tracked positions */
-	size_t need = (size_t)std::min<unsigned long long>(2ull * st.m_ops, h->n_elems) + 16;
-	{
-		size_t cap0 = h->run_cap, cap1 = h->run_cap, cap2 = h->run_cap;
-		if ((r = ensure_buf(h, &h->d_run_start, &cap0, need))) return r;
-		if ((r = ensure_buf(h, &h->d_run_end, &cap1, need))) return r;
-		if ((r = ensure_buf(h, &h->d_run_depth, &cap2, need))) return r;
-		h->run_cap = std::min(cap0, std::min(cap1, cap2));
-	}
-	tic(h);
-	CK(cudaMemsetAsync(h->d_stA, 0, h->n_tiles * 8, h->s_main));
-	CK(cudaMemsetAsync(h->d_stB, 0, h->n_tiles * 8, h->s_main));
-	CK(cudaMemsetAsync(h->d_bins, 0, h->n_bins * 8, h->s_main));
-	{
-		ngs_dev_state init = st;
-		init.scan_ticket = 0; init.n_boundaries = 0; init.n_runs = 0; init.first_run = ~0ull; init.last_run = 0;
-		init.max_depth = 0; init.min_depth = 0;
-		*h->h_st = init;
-		CK(cudaMemcpyAsync(h->d_st, h->h_st, sizeof(ngs_dev_state), cudaMemcpyHostToDevice, h->s_main));
-	}
-	if (h->n_tiles) {
-		ScanArgs A;
-		A.diff = h->d_diff; A.n_tiles = h->n_tiles; A.tile2seg = h->d_tile2seg; A.seg = h->d_seg;
-		A.stA = h->d_stA; A.stB = h->d_stB;
-		A.run_start = h->d_run_start; A.run_end = h->d_run_end; A.run_depth = h->d_run_depth; A.run_cap = h->run_cap;
-		A.rec_base = h->d_rec_base; A.n_seg = (uint32_t)h->seg.size();
-		A.bins = h->d_bins; A.window = h->cfg.window; A.variant = h->cfg.mode == NGSCOV_MODE_WIG ? 1 : 0;
-		A.rezero = 1; A.st = h->d_st;
-		A.debug = getenv("NGSCOV_DEBUG_SCAN") ? atoi(getenv("NGSCOV_DEBUG_SCAN")) : 0;
-		k_scan_runs<<<(unsigned)h->n_tiles, NGS_SCAN_THREADS, 0, h->s_main>>>(A);
-		h->stats.launches += 1;
-		CK(cudaGetLastError());
+	const bool streamed = h->next_fin_seg > 0;
+	if (h->next_fin_seg < h->seg.size() || h->seg.empty()) {
+		if (h->seg.empty()) { h->h_rec_base.assign(1, 0); memset(h->h_st2, 0, sizeof *h->h_st2); }
+		else if ((r = scan_range(h, h->next_fin_seg, h->seg.size(), st.m_ops - h->mops_fin))) return r;
 	}
 	h->diff_dirty = false;
-	CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
-	h->h_rec_base.assign(h->seg.size() + 1, 0);
-	if (h->n_tiles) CK(cudaMemcpyAsync(h->h_rec_base.data(), h->d_rec_base, (h->seg.size() + 1) * 8, cudaMemcpyDeviceToHost, h->s_main));
-	h->stats.ms_scan += toc(h);
-	const ngs_dev_state s2 = *h->h_st;
-	h->stats.boundaries = s2.n_boundaries; h->stats.runs = s2.n_runs; h->stats.positions = h->n_elems;
-	if (s2.n_boundaries > h->run_cap) return h->sticky_err = NGSCOV_ENOMEM;
-	/* halo */
-	h->halo.n_runs = s2.n_runs;
-	if (s2.n_runs) {
-		const unsigned long long idx[2] = { s2.first_run, s2.last_run };
-		ngscov_run *dst[2] = { &h->halo.first, &h->halo.last };
-		for (int k = 0; k < 2; ++k) {
-			CK(cudaMemcpy(&dst[k]->start, h->d_run_start + idx[k], 4, cudaMemcpyDeviceToHost));
-			CK(cudaMemcpy(&dst[k]->end, h->d_run_end + idx[k], 4, cudaMemcpyDeviceToHost));
-			CK(cudaMemcpy(&dst[k]->depth, h->d_run_depth + idx[k], 4, cudaMemcpyDeviceToHost));
-			size_t s = std::upper_bound(h->h_rec_base.begin(), h->h_rec_base.begin() + h->seg.size(), idx[k]) - h->h_rec_base.begin() - 1;
-			dst[k]->contig = (int32_t)h->seg[s].contig;
+	memset(&h->halo, 0, sizeof h->halo); h->halo.first.contig = h->halo.last.contig = -1;
+	if (streamed) {
+		/* the remaining contigs' text is produced here too so that everything is in flight to the host */
+		if (h->cfg.mode == NGSCOV_MODE_DEPTH && h->next_fin_seg < h->seg.size() && (r = format_bed_range(h, h->next_fin_seg, h->seg.size()))) return r;
+		h->next_fin_seg = h->seg.size();
+		h->halo.n_runs = h->acc_runs;                    /* first / last are not tracked in streamed mode (single shard) */
+	} else {
+		const ngs_dev_state &s2 = *h->h_st2;
+		h->halo.n_runs = s2.n_runs;
+		if (s2.n_runs) {
+			const unsigned long long idx[2] = { s2.first_run, s2.last_run };
+			ngscov_run *dst[2] = { &h->halo.first, &h->halo.last };
+			for (int k = 0; k < 2; ++k) {
+				CK(cudaMemcpy(&dst[k]->start, h->d_run_start + idx[k], 4, cudaMemcpyDeviceToHost));
+				CK(cudaMemcpy(&dst[k]->end, h->d_run_end + idx[k], 4, cudaMemcpyDeviceToHost));
+				CK(cudaMemcpy(&dst[k]->depth, h->d_run_depth + idx[k], 4, cudaMemcpyDeviceToHost));
+				size_t sg = std::upper_bound(h->h_rec_base.begin(), h->h_rec_base.begin() + h->seg.size(), idx[k]) - h->h_rec_base.begin() - 1;
+				dst[k]->contig = (int32_t)h->seg[sg].contig;
+			}
 		}
 	}
 	h->runs_done = true;
@@ -701,8 +774,9 @@ extern "C" int ngscov_halo_put(ngscov_t *h, int drop_first, uint32_t new_last_en
 	if (!h) return NGSCOV_EINVAL;
 	if (!h->runs_done || h->formatted) return NGSCOV_ESTATE;
 	if (h->halo.n_runs == 0) return drop_first || new_last_end ? NGSCOV_EINVAL : 0;
-	h->drop_idx = drop_first ? h->h_st->first_run : ~0ull;
-	if (new_last_end) { h->mod_idx = h->h_st->last_run; h->mod_end = new_last_end; } else h->mod_idx = ~0ull;
+	if (h->next_fin_seg > 0) return NGSCOV_ESTATE;           /* streamed finalize: the text is already made */
+	h->drop_idx = drop_first ? h->h_st2->first_run : ~0ull;
+	if (new_last_end) { h->mod_idx = h->h_st2->last_run; h->mod_end = new_last_end; } else h->mod_idx = ~0ull;
 	return 0;
 }
 
@@ -744,13 +818,38 @@ extern "C" int ngscov_bins_apply_run(ngscov_t *h, const ngscov_run *run, int sig
 	return 0;
 }
 
+/* make room for `need` bytes in a text buffer, keeping its first `keep` bytes */
+static int grow_text(ngscov *h, int which, size_t need, size_t keep)
+{
+	if (need <= h->d_text_cap[which] && h->d_text[which]) return 0;
+	char *nb = nullptr;
+	const size_t want = need + need / 4 + 4096;
+	CK(cudaMalloc((void **)&nb, want));
+	if (keep && h->d_text[which]) CK(cudaMemcpyAsync(nb, h->d_text[which], keep, cudaMemcpyDeviceToDevice, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	CK(cudaStreamSynchronize(h->s_out));
+	if (h->d_text[which]) cudaFree(h->d_text[which]);
+	h->d_text[which] = nb; h->d_text_cap[which] = want;
+	return 0;
+}
+static int grow_host_text(ngscov *h, int which, size_t need, size_t keep)
+{
+	if (need <= h->h_text_cap[which] && h->h_text[which]) return 0;
+	char *nb = nullptr;
+	const size_t want = need + need / 4 + 4096;
+	CK(cudaHostAlloc((void **)&nb, want, cudaHostAllocDefault));
+	CK(cudaStreamSynchronize(h->s_out));
+	if (keep && h->h_text[which]) memcpy(nb, h->h_text[which], keep);
+	if (h->h_text[which]) cudaFreeHost(h->h_text[which]);
+	h->h_text[which] = nb; h->h_text_cap[which] = want;
+	return 0;
+}
+
 template <class Producer>
-static int run_format(ngscov *h, int which, unsigned long long n_items, const Producer &P, uint32_t max_line, size_t bound)
+static int run_format(ngscov *h, int which, unsigned long long n_items, const Producer &P, uint32_t max_line, size_t bound, size_t out_off = 0)
 {
 	int r;
-	size_t cap = h->d_text_cap[which];
-	if ((r = ensure_buf(h, &h->d_text[which], &cap, bound + 64))) return r;
-	h->d_text_cap[which] = cap;
+	if ((r = grow_text(h, which, out_off + bound + 64, out_off))) return r;
 	int ipt = 4;
 	if (getenv("NGSCOV_FMT_IPT")) { const int v = atoi(getenv("NGSCOV_FMT_IPT")); if (v == 1 || v == 2 || v == 4) ipt = v; }
 	const uint32_t smem_max = 96 * 1024;
@@ -758,16 +857,17 @@ static int run_format(ngscov *h, int which, unsigned long long n_items, const Pr
 	uint32_t stage = (uint32_t)std::min<size_t>((size_t)NGS_FMT_THREADS * ipt * max_line + 32, smem_max);
 	const unsigned long long per = (unsigned long long)NGS_FMT_THREADS * ipt;
 	const unsigned long long n_tiles = (n_items + per - 1) / per;
-	h->text_len[which] = 0; h->text_ready[which] = true; h->h_text_valid[which] = false;
+	h->text_len[which] = out_off; h->text_ready[which] = true; h->h_text_valid[which] = false;
 	if (n_tiles == 0) return 0;
 	size_t scap = h->fmt_status_cap;
 	if ((r = ensure_buf(h, &h->d_fmt_status, &scap, (size_t)n_tiles))) return r;
 	h->fmt_status_cap = scap;
+	tic(h);
 	CK(cudaMemsetAsync(h->d_fmt_status, 0, n_tiles * 8, h->s_main));
 	CK(cudaMemsetAsync(&h->d_st->fmt_ticket, 0, 16, h->s_main));      /* fmt_ticket + fmt_bytes */
 	FmtArgs A;
-	A.n_items = n_items; A.n_tiles = n_tiles; A.status = h->d_fmt_status; A.out = h->d_text[which];
-	A.out_cap = h->d_text_cap[which]; A.st = h->d_st; A.stage_bytes = stage;
+	A.n_items = n_items; A.n_tiles = n_tiles; A.status = h->d_fmt_status; A.out = h->d_text[which] + out_off;
+	A.out_cap = h->d_text_cap[which] - out_off; A.st = h->d_st; A.stage_bytes = stage;
 	if (ipt == 4) {
 		CK(cudaFuncSetAttribute(k_format_lines<Producer, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
 		k_format_lines<Producer, 4><<<(unsigned)n_tiles, NGS_FMT_THREADS, stage, h->s_main>>>(A, P);
@@ -780,15 +880,47 @@ static int run_format(ngscov *h, int which, unsigned long long n_items, const Pr
 	}
 	h->stats.launches += 1;
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
-	CK(cudaStreamSynchronize(h->s_main));
-	if (h->h_st->fmt_bytes > h->d_text_cap[which]) return NGSCOV_ENOMEM;
-	h->text_len[which] = (size_t)h->h_st->fmt_bytes;
+	unsigned long long *fb = &h->h_st2->fmt_bytes;
+	CK(cudaMemcpyAsync(fb, &h->d_st->fmt_bytes, 8, cudaMemcpyDeviceToHost, h->s_main));
+	h->stats.ms_format += toc(h);
+	if (*fb > h->d_text_cap[which] - out_off) return NGSCOV_ENOMEM;
+	h->text_len[which] = out_off + (size_t)*fb;
 	h->stats.out_bytes[which] = h->text_len[which];
 	return 0;
 }
 
 static uint32_t dig(uint64_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n; } return n; }
+
+/* bedGraph text of segments [s0, s1) from the records of the scan_range that just ran over them; appended at
+ * bed_off.  In streamed mode the new bytes are queued for D2H at once (stream s_out). */
+static int format_bed_range(ngscov *h, size_t s0, size_t s1)
+{
+	int r;
+	const bool streamed = h->stream_fin && (h->next_fin_seg > 0 || s1 < h->seg.size() || s0 > 0);
+	const ngs_dev_state st = *h->h_st2;
+	BedProducer P;
+	P.run_start = h->d_run_start; P.run_end = h->d_run_end; P.run_depth = h->d_run_depth;
+	P.rec_base = h->d_rec_base; P.seg = h->d_seg + s0; P.n_seg = (uint32_t)(s1 - s0);
+	P.nt.names = h->d_names; P.nt.name_off = h->d_name_off;
+	P.drop_idx = h->drop_idx; P.mod_idx = h->mod_idx; P.mod_end = h->mod_end;
+	const uint32_t dd = std::max(dig((uint64_t)std::max(st.max_depth, 0)), 1 + dig((uint64_t)(-(int64_t)std::min(st.min_depth, 0))));
+	size_t bound = 0;
+	for (size_t sg = s0; sg < s1; ++sg) {
+		const unsigned long long k = h->h_rec_base[sg - s0 + 1] - h->h_rec_base[sg - s0];
+		const uint32_t pd = dig(std::max<uint64_t>(h->seg[sg].lim, h->mod_end));
+		bound += (size_t)k * (h->ref_name[h->seg[sg].contig].size() + 1 + 2 * pd + 2 + dd + 1);
+	}
+	r = run_format(h, NGSCOV_OUT_BEDGRAPH, st.n_boundaries, P, h->max_name_tab + 10 + 1 + 10 + 1 + 11 + 1, bound, h->bed_off);
+	if (r) return r;
+	h->bed_off = h->text_len[NGSCOV_OUT_BEDGRAPH];
+	if (streamed && h->bed_off > h->bed_d2h) {
+		if ((r = grow_host_text(h, NGSCOV_OUT_BEDGRAPH, h->bed_off, h->bed_d2h))) return r;
+		CK(cudaMemcpyAsync(h->h_text[NGSCOV_OUT_BEDGRAPH] + h->bed_d2h, h->d_text[NGSCOV_OUT_BEDGRAPH] + h->bed_d2h, h->bed_off - h->bed_d2h,
+		                   cudaMemcpyDeviceToHost, h->s_out));
+		h->bed_d2h = h->bed_off;
+	}
+	return 0;
+}
 
 extern "C" int ngscov_format(ngscov_t *h, uint32_t which_mask)
 {
@@ -796,23 +928,9 @@ extern "C" int ngscov_format(ngscov_t *h, uint32_t which_mask)
 	if (!h->runs_done) return NGSCOV_ESTATE;
 	CK(cudaSetDevice(h->device));
 	int r = 0;
-	tic(h);
 	NameTable nt = { h->d_names, h->d_name_off };
-	const ngs_dev_state st = *h->h_st;
-	if (which_mask & (1u << NGSCOV_OUT_BEDGRAPH)) {
-		BedProducer P;
-		P.run_start = h->d_run_start; P.run_end = h->d_run_end; P.run_depth = h->d_run_depth;
-		P.rec_base = h->d_rec_base; P.seg = h->d_seg; P.n_seg = (uint32_t)h->seg.size(); P.nt = nt;
-		P.drop_idx = h->drop_idx; P.mod_idx = h->mod_idx; P.mod_end = h->mod_end;
-		const uint32_t dd = std::max(dig((uint64_t)std::max(st.max_depth, 0)), 1 + dig((uint64_t)(-(int64_t)std::min(st.min_depth, 0))));
-		size_t bound = 0;
-		for (size_t s = 0; s < h->seg.size(); ++s) {
-			const unsigned long long k = h->h_rec_base[s + 1] - h->h_rec_base[s];
-			const uint32_t pd = dig(std::max<uint64_t>(h->seg[s].lim, h->mod_end));
-			bound += (size_t)k * (h->ref_name[h->seg[s].contig].size() + 1 + 2 * pd + 2 + dd + 1);
-		}
-		r = run_format(h, NGSCOV_OUT_BEDGRAPH, st.n_boundaries, P, h->max_name_tab + 10 + 1 + 10 + 1 + 11 + 1, bound);
-		if (r) return r;
+	if ((which_mask & (1u << NGSCOV_OUT_BEDGRAPH)) && h->next_fin_seg == 0) {      /* streamed inputs already have their text */
+		if ((r = format_bed_range(h, 0, h->seg.size()))) return r;
 	}
 	if (which_mask & (1u << NGSCOV_OUT_DEPTH)) {
 		DepthProducer P;
@@ -838,7 +956,6 @@ extern "C" int ngscov_format(ngscov_t *h, uint32_t which_mask)
 		h->text_ready[NGSCOV_OUT_CHROMSIZE] = true;
 		h->stats.out_bytes[NGSCOV_OUT_CHROMSIZE] = h->chromsize.size();
 	}
-	h->stats.ms_format += toc(h);
 	h->formatted = true;
 	return 0;
 }
@@ -870,6 +987,12 @@ extern "C" int ngscov_output(ngscov_t *h, int which, const char **buf, size_t *l
 	if (!h->text_ready[which]) return NGSCOV_ESTATE;
 	if (which == NGSCOV_OUT_CHROMSIZE) { *buf = h->chromsize.data(); *len = h->chromsize.size(); return 0; }
 	CK(cudaSetDevice(h->device));
+	if (which == NGSCOV_OUT_BEDGRAPH && h->bed_d2h && h->bed_d2h == h->text_len[which] && !h->h_text_valid[which]) {
+		tic(h);
+		CK(cudaStreamSynchronize(h->s_out));               /* streamed finalize: the copy has been in flight since the scan */
+		h->stats.ms_d2h += toc(h);
+		h->h_text_valid[which] = true;
+	}
 	if (!h->h_text_valid[which]) {
 		const size_t n = h->text_len[which];
 		if (n > h->h_text_cap[which] || !h->h_text[which]) {
@@ -891,7 +1014,7 @@ extern "C" int ngscov_output(ngscov_t *h, int which, const char **buf, size_t *l
 extern "C" int ngscov_runs_get(ngscov_t *h, ngscov_run *runs, uint64_t cap, uint64_t *n)
 {
 	if (!h || !n) return NGSCOV_EINVAL;
-	if (!h->runs_done) return NGSCOV_ESTATE;
+	if (!h->runs_done || h->next_fin_seg > 0) return NGSCOV_ESTATE;      /* streamed inputs keep only the last contig's records */
 	CK(cudaSetDevice(h->device));
 	const uint64_t nb = h->stats.boundaries;
 	*n = h->stats.runs;

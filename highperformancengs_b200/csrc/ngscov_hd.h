@@ -223,6 +223,7 @@ NGS_HD uint32_t ngs_put_f2(Ptr dst, uint64_t hundredths)
  */
 typedef struct {
 	uint64_t records, kept, m_ops, cigar_words;
+	uint32_t max_ref_p1;         /* 1 + highest refID seen (0: none): sorted input => every lower contig is complete */
 } ngs_counts;
 
 typedef struct {
@@ -238,6 +239,7 @@ NGS_HD void ngs_decode_record(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o
                               Sink &sink, int sign, ngs_counts &cnt)
 {
 	cnt.records += 1; cnt.cigar_words += h.n_cigar;
+	if ((uint32_t)(h.ref_id + 1) > cnt.max_ref_p1) cnt.max_ref_p1 = (uint32_t)(h.ref_id + 1);
 	if ((h.flag & cfg.flag_mask) || h.ref_id < 0 || h.pos >= (1 << 29)) return;
 	cnt.kept += 1;
 	const int32_t si = cfg.ctg2seg[h.ref_id];

@@ -53,6 +53,8 @@ struct ngs_dev_state {
 	long long entry_next;              /* entry offset of the next chunk relative to its data start */
 	unsigned int carry_len;
 	unsigned int flags;                /* NGS_FLAG_* */
+	unsigned int max_ref_p1;           /* 1 + highest refID decoded so far */
+	unsigned int pad0;
 	/* scan */
 	unsigned long long scan_ticket;
 	unsigned long long n_boundaries, n_runs;
@@ -242,6 +244,10 @@ __global__ void __launch_bounds__(256, NGS_ING_MINB) k_ingest_walk(IngestArgs A)
 	}
 	sink.flush();
 	if (live) { A.entry[c] = entry; A.exit[c] = entry != NGS_NONE ? ws.result : 0; }
+	{
+		const unsigned mr = __reduce_max_sync(full, cnt.max_ref_p1);
+		if ((threadIdx.x & 31) == 0 && mr) atomicMax(&A.st->max_ref_p1, mr);
+	}
 	/* block-aggregate the counters */
 	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
 	                   v2 = warp_sum_u64(cnt.m_ops), v3 = warp_sum_u64(cnt.cigar_words), v4 = warp_sum_u64(walks);
@@ -416,6 +422,10 @@ __global__ void __launch_bounds__(256) k_decode_scatter(IngestArgs A)
 			}
 		}
 	}
+	{
+		const unsigned mr = __reduce_max_sync(0xffffffffu, cnt.max_ref_p1);
+		if ((threadIdx.x & 31) == 0 && mr) atomicMax(&A.st->max_ref_p1, mr);
+	}
 	/* block-level reduction, then one atomic per counter per CTA into this CTA's stripe */
 	__shared__ unsigned long long s_c[8][4];
 	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
@@ -568,6 +578,10 @@ __global__ void __launch_bounds__(NGS_TILE_THREADS) k_ingest_tiles(IngestArgs A)
 	}
 	sink.flush();
 	if (live) { A.entry[c] = entry; A.exit[c] = entry != NGS_NONE ? ws.result : 0; }
+	{
+		const unsigned mr = __reduce_max_sync(full, cnt.max_ref_p1);
+		if ((threadIdx.x & 31) == 0 && mr) atomicMax(&A.st->max_ref_p1, mr);
+	}
 	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
 	                   v2 = warp_sum_u64(cnt.m_ops), v3 = warp_sum_u64(cnt.cigar_words), v4 = warp_sum_u64(walks);
 	if ((threadIdx.x & 31) == 0) {
@@ -732,6 +746,7 @@ __global__ void k_repair(IngestArgs A, long long first_bad, const long long *bex
 	atomicAdd(&A.st->m_ops, add.m_ops - sub.m_ops);
 	atomicAdd(&A.st->cigar_words, add.cigar_words - sub.cigar_words);
 	atomicAdd(&A.st->spec_repaired, (unsigned long long)repaired);
+	if (add.max_ref_p1) atomicMax(&A.st->max_ref_p1, add.max_ref_p1);
 }
 
 /* after a clean verify: derive the next chunk's entry and save the bytes of a cut record */
@@ -772,7 +787,8 @@ __global__ void __launch_bounds__(256) k_place_carry(uint8_t *data_start, const 
 
 struct ScanArgs {
 	int *diff;                       /* difference array, zeroed again on the way through */
-	uint64_t n_tiles;
+	uint64_t tile_first, n_tiles;    /* this launch scans tiles [tile_first, n_tiles): whole array, or one finished contig */
+	uint32_t seg_first;              /* rec_base[] is indexed by segment - seg_first */
 	const uint32_t *tile2seg;        /* [n_tiles] */
 	const ngs_seg *seg;
 	unsigned long long *stA, *stB;   /* [n_tiles] look-back words: A = status:2|count:62, B = status:2|lastb:30|sum:32 */
@@ -820,7 +836,7 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS, NGS_SCAN_MINB) k_scan_runs(S
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 	/* tile id = blockIdx.x: CTAs are dispatched in increasing block order, so every predecessor of a
 	 * resident tile is resident or finished and the look-back cannot starve (no ticket round trip) */
-	const uint64_t tile = blockIdx.x;
+	const uint64_t tile = A.tile_first + blockIdx.x;
 	if (tile >= A.n_tiles) return;
 
 	/* coalesced 128-bit loads (striped) issued first; the segment lookup overlaps their latency */
@@ -881,16 +897,16 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS, NGS_SCAN_MINB) k_scan_runs(S
 	 * trips per tile, which is what bounded this kernel; 256-wide needs 2-3) */
 	long long tile_sum = 0; unsigned long long tile_cnt = 0; unsigned int tile_last = 0;
 	if (t == 0) {
-		const unsigned long long stt = tile == 0 ? NGS_ST_INC : NGS_ST_AGG;
+		const unsigned long long stt = tile == A.tile_first ? NGS_ST_INC : NGS_ST_AGG;
 		st_relaxed_u64(&A.stA[tile], (stt << 62) | (unsigned long long)tot_cnt);
 		st_relaxed_u64(&A.stB[tile], (stt << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
 	}
-	if (tile > 0 && !(A.debug & 1)) {
+	if (tile > A.tile_first && !(A.debug & 1)) {
 		long long base = (long long)tile - 1;
 		for (;;) {
 			const long long idx = base - t;
-			unsigned long long a = NGS_ST_INC << 62, b = NGS_ST_INC << 62;       /* virtual tiles before 0: inclusive zero */
-			if (idx >= 0) {
+			unsigned long long a = NGS_ST_INC << 62, b = NGS_ST_INC << 62;       /* virtual tiles before the first: inclusive zero */
+			if (idx >= (long long)A.tile_first) {
 				do {
 					a = ld_relaxed_u64(&A.stA[idx]);
 					b = ld_relaxed_u64(&A.stB[idx]);
@@ -928,9 +944,9 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS, NGS_SCAN_MINB) k_scan_runs(S
 		}
 	}
 	if (t == 0) {
-		if (tile == sg.tile0) A.rec_base[si] = tile_cnt;
+		if (tile == sg.tile0) A.rec_base[si - A.seg_first] = tile_cnt;
 		if (tile == A.n_tiles - 1) {
-			for (uint32_t s2 = si + 1; s2 <= A.n_seg; ++s2) A.rec_base[s2] = tile_cnt + tot_cnt;
+			for (uint32_t s2 = si + 1; s2 <= A.n_seg; ++s2) A.rec_base[s2 - A.seg_first] = tile_cnt + tot_cnt;
 			A.st->n_boundaries = tile_cnt + tot_cnt;
 		}
 	}

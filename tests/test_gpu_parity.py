@@ -26,7 +26,6 @@ def run_engine(names, lens, recs, mode, window, emit_wig=True, staging_bytes=0, 
         out = {"bedgraph": eng.output(0) if mode == 0 else b"", "depth": eng.output(1) if mode == 0 else b"",
                "wig": eng.output(2) if (mode == 1 or emit_wig) else b"", "chromsize": eng.output(3) if (mode == 1 or emit_wig) else b""}
         out["stats"] = eng.stats()
-        out["runs"] = eng.runs()
         return out
     finally:
         eng.close()
@@ -131,3 +130,30 @@ def test_small_overhang_matches_oracle(oracle):
         exp = oracle.run(recs, names, lens, mode, 300)
         got = run_engine(names, lens, recs, mode, 300)
         check(got, exp, mode, "overhang")
+
+
+def test_runs_get_matches_bedgraph(oracle):
+    """the binary run records (single push, no streamed finalize) are the bedGraph lines"""
+    from highperformancengs_b200 import CoverageEngine
+    names, lens, reads = bamutil.random_case(9, n_reads=2000)
+    recs = bamutil.records(reads, seq=False)
+    exp = oracle.run(recs, names, lens, 0, 500)
+    with CoverageEngine(names, lens, mode=0, window=500) as eng:
+        eng.push_host(recs, last=True)
+        eng.finish()
+        runs = eng.runs()
+    text = "".join("%s\t%d\t%d\t%d\n" % (names[c].decode(), s, e, d) for c, s, e, d in runs)
+    assert text.encode() == exp["bedgraph"]
+
+
+@pytest.mark.parametrize("staging", [8192, 40000])
+def test_streamed_per_contig_finalize(oracle, staging):
+    """many contigs + small pushes: contigs are scanned / formatted / copied back while later ones are still
+    being pushed (the streamed finalize path); result must not change"""
+    contigs = tuple((("ctg%d" % i).encode(), 3000 + 700 * i) for i in range(12))
+    names, lens, reads = bamutil.random_case(13, n_reads=5000, contigs=contigs)
+    recs = bamutil.records(reads)
+    for mode in (0, 1):
+        exp = oracle.run(recs, names, lens, mode, 250)
+        got = run_engine(names, lens, recs, mode, 250, staging_bytes=staging)
+        check(got, exp, mode, f"streamed staging={staging} mode={mode}")
