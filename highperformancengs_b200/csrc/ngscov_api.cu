@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 
 #define NGS_HEADROOM (NGS_CARRY_MAX + 256)
 
@@ -36,6 +37,7 @@ struct ngscov {
 
 	/* names */
 	char *d_names; uint32_t *d_name_off; uint32_t max_name_tab;   /* "name\t" */
+	unsigned long long *d_name8;
 	char *d_wighdr; uint32_t *d_wighdr_off; uint32_t max_wighdr;
 
 	/* staging + chunk buffers */
@@ -77,6 +79,7 @@ struct ngscov {
 	size_t bed_off;                          /* bedGraph bytes produced so far */
 	size_t bed_d2h;                          /* ... of which already queued for D2H */
 	ngs_dev_state *h_st2;                    /* pinned read-back of the state block after scan / format launches */
+	ngs_dev_state *h_tmpl;                   /* pinned, constant: initial values of the scan fields */
 	cudaStream_t s_out; cudaEvent_t ev_fmt;
 	unsigned long long acc_boundaries, acc_runs; int acc_max, acc_min;
 
@@ -250,6 +253,12 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 			h->chromsize += nm + cs;
 		}
 		CKC(dev_upload(h, &h->d_names, names)); CKC(dev_upload(h, &h->d_name_off, noff));
+		{
+			std::vector<unsigned long long> n8(h->n_ref, 0);
+			for (int i = 0; i < h->n_ref; ++i)
+				for (uint32_t k = 0; k < 8 && noff[i] + k < noff[i + 1]; ++k) n8[i] |= (unsigned long long)(unsigned char)names[noff[i] + k] << (8 * k);
+			CKC(dev_upload(h, &h->d_name8, n8));
+		}
 		CKC(dev_upload(h, &h->d_wighdr, wh)); CKC(dev_upload(h, &h->d_wighdr_off, whoff));
 	}
 	CK(cudaMalloc((void **)&h->d_diff, std::max<uint64_t>(1, h->n_elems) * sizeof(int)));
@@ -264,6 +273,8 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	CK(cudaMalloc((void **)&h->d_st, sizeof(ngs_dev_state)));
 	CK(cudaHostAlloc((void **)&h->h_st, sizeof(ngs_dev_state), cudaHostAllocDefault));
 	CK(cudaHostAlloc((void **)&h->h_st2, sizeof(ngs_dev_state), cudaHostAllocDefault));
+	CK(cudaHostAlloc((void **)&h->h_tmpl, sizeof(ngs_dev_state), cudaHostAllocDefault));
+	memset(h->h_tmpl, 0, sizeof(ngs_dev_state)); h->h_tmpl->first_run = ~0ull;
 	CK(cudaMalloc((void **)&h->d_ctr, NGS_CTR_STRIPES * 16 * 8));
 	CK(cudaHostAlloc((void **)&h->h_ctr, NGS_CTR_STRIPES * 16 * 8, cudaHostAllocDefault));
 	h->stage_cap = cfg->staging_bytes ? (size_t)cfg->staging_bytes : (size_t)256 << 20;
@@ -282,7 +293,7 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	if (!h) return;
 	cudaSetDevice(h->device);
 	cudaDeviceSynchronize();
-	void *dev[] = { h->d_seg, h->d_ctg2seg, h->d_tile2seg, h->d_ref_len, h->d_win_base, h->d_diff, h->d_bins, h->d_names,
+	void *dev[] = { h->d_seg, h->d_ctg2seg, h->d_tile2seg, h->d_ref_len, h->d_win_base, h->d_diff, h->d_bins, h->d_names, h->d_name8,
 	                h->d_name_off, h->d_wighdr, h->d_wighdr_off, h->d_chunk[0], h->d_chunk[1], h->d_carry, h->d_entry, h->d_exit,
 	                h->d_bmax, h->d_count, h->d_slots, h->d_ctr, h->d_st, h->d_run_start, h->d_run_end, h->d_run_depth, h->d_rec_base, h->d_stA, h->d_stB,
 	                h->d_fmt_status, h->d_text[0], h->d_text[1], h->d_text[2], h->d_text[3] };
@@ -292,6 +303,7 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	if (h->h_st) cudaFreeHost(h->h_st);
 	if (h->h_ctr) cudaFreeHost(h->h_ctr);
 	if (h->h_st2) cudaFreeHost(h->h_st2);
+	if (h->h_tmpl) cudaFreeHost(h->h_tmpl);
 	if (h->s_out) cudaStreamDestroy(h->s_out);
 	if (h->ev_fmt) cudaEventDestroy(h->ev_fmt);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
@@ -655,20 +667,16 @@ static int scan_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_b
 	}
 	if (!h->bins_zeroed) { CK(cudaMemsetAsync(h->d_bins, 0, h->n_bins * 8, h->s_main)); h->bins_zeroed = true; }
 	{	/* reset only the scan fields of the device state block (the ingest fields stay live) */
-		ngs_dev_state *t = h->h_st2;
-		memset(t, 0, sizeof *t);
-		t->first_run = ~0ull;
 		const size_t o0 = offsetof(ngs_dev_state, scan_ticket), o1 = offsetof(ngs_dev_state, fmt_ticket);
-		CK(cudaMemcpyAsync((char *)h->d_st + o0, (char *)t + o0, o1 - o0, cudaMemcpyHostToDevice, h->s_main));
-		CK(cudaStreamSynchronize(h->s_main));          /* h_st2 is reused as the read-back buffer below */
+		CK(cudaMemcpyAsync((char *)h->d_st + o0, (const char *)h->h_tmpl + o0, o1 - o0, cudaMemcpyHostToDevice, h->s_main));
 	}
 	if (t1 > t0) {
 		ScanArgs A;
-		A.diff = h->d_diff; A.tile_first = t0; A.n_tiles = t1; A.seg_first = (uint32_t)s0;
-		A.tile2seg = h->d_tile2seg; A.seg = h->d_seg;
-		A.stA = h->d_stA; A.stB = h->d_stB;
+		A.diff = h->d_diff + t0 * (uint64_t)NGS_TILE; A.n_tiles = t1 - t0; A.tile_off = t0;
+		A.tile2seg = h->d_tile2seg + t0; A.seg = h->d_seg;
+		A.stA = h->d_stA + t0; A.stB = h->d_stB + t0;
 		A.run_start = h->d_run_start; A.run_end = h->d_run_end; A.run_depth = h->d_run_depth; A.run_cap = h->run_cap;
-		A.rec_base = h->d_rec_base; A.n_seg = (uint32_t)s1;
+		A.rec_base = h->d_rec_base - s0; A.n_seg = (uint32_t)s1;      /* the kernel indexes by global segment */
 		A.bins = h->d_bins; A.window = h->cfg.window; A.variant = h->cfg.mode == NGSCOV_MODE_WIG ? 1 : 0;
 		A.rezero = 1; A.st = h->d_st;
 		A.debug = getenv("NGSCOV_DEBUG_SCAN") ? atoi(getenv("NGSCOV_DEBUG_SCAN")) : 0;
@@ -691,7 +699,16 @@ static int scan_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_b
 static int format_bed_range(ngscov *h, size_t s0, size_t s1);
 
 /* Finalize segments [next_fin_seg, seg_end) while the rest of the stream is still arriving. */
+static double g_fin_wall = 0; static int g_fin_calls = 0;
+static int stream_finalize_impl(ngscov *h, size_t seg_end);
 static int stream_finalize(ngscov *h, size_t seg_end)
+{
+	const auto t0 = std::chrono::steady_clock::now();
+	const int r = stream_finalize_impl(h, seg_end);
+	g_fin_wall += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++g_fin_calls;
+	return r;
+}
+static int stream_finalize_impl(ngscov *h, size_t seg_end)
 {
 	int r;
 	const unsigned long long mops_now = h->h_st->m_ops;
@@ -757,6 +774,7 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 			}
 		}
 	}
+	if (getenv("NGSCOV_DEBUG")) { fprintf(stderr, "ngscov: streamed finalize: %d calls, %.3f s host wall\n", g_fin_calls, g_fin_wall); g_fin_wall = 0; g_fin_calls = 0; }
 	h->runs_done = true;
 	return 0;
 }
@@ -901,7 +919,7 @@ static int format_bed_range(ngscov *h, size_t s0, size_t s1)
 	BedProducer P;
 	P.run_start = h->d_run_start; P.run_end = h->d_run_end; P.run_depth = h->d_run_depth;
 	P.rec_base = h->d_rec_base; P.seg = h->d_seg + s0; P.n_seg = (uint32_t)(s1 - s0);
-	P.nt.names = h->d_names; P.nt.name_off = h->d_name_off;
+	P.nt.names = h->d_names; P.nt.name_off = h->d_name_off; P.nt.name8 = h->d_name8;
 	P.drop_idx = h->drop_idx; P.mod_idx = h->mod_idx; P.mod_end = h->mod_end;
 	const uint32_t dd = std::max(dig((uint64_t)std::max(st.max_depth, 0)), 1 + dig((uint64_t)(-(int64_t)std::min(st.min_depth, 0))));
 	size_t bound = 0;
@@ -913,7 +931,7 @@ static int format_bed_range(ngscov *h, size_t s0, size_t s1)
 	r = run_format(h, NGSCOV_OUT_BEDGRAPH, st.n_boundaries, P, h->max_name_tab + 10 + 1 + 10 + 1 + 11 + 1, bound, h->bed_off);
 	if (r) return r;
 	h->bed_off = h->text_len[NGSCOV_OUT_BEDGRAPH];
-	if (streamed && h->bed_off > h->bed_d2h) {
+	if (streamed && h->bed_off > h->bed_d2h && !getenv("NGSCOV_DEBUG_NOD2H")) {
 		if ((r = grow_host_text(h, NGSCOV_OUT_BEDGRAPH, h->bed_off, h->bed_d2h))) return r;
 		CK(cudaMemcpyAsync(h->h_text[NGSCOV_OUT_BEDGRAPH] + h->bed_d2h, h->d_text[NGSCOV_OUT_BEDGRAPH] + h->bed_d2h, h->bed_off - h->bed_d2h,
 		                   cudaMemcpyDeviceToHost, h->s_out));
@@ -928,7 +946,7 @@ extern "C" int ngscov_format(ngscov_t *h, uint32_t which_mask)
 	if (!h->runs_done) return NGSCOV_ESTATE;
 	CK(cudaSetDevice(h->device));
 	int r = 0;
-	NameTable nt = { h->d_names, h->d_name_off };
+	NameTable nt = { h->d_names, h->d_name_off, h->d_name8 };
 	if ((which_mask & (1u << NGSCOV_OUT_BEDGRAPH)) && h->next_fin_seg == 0) {      /* streamed inputs already have their text */
 		if ((r = format_bed_range(h, 0, h->seg.size()))) return r;
 	}

@@ -123,8 +123,10 @@ NGS_HD void ngs_bin_run(int variant, uint32_t s, uint32_t e, int64_t d, uint32_t
 /* ---- decimal formatting --------------------------------------------------------------------------*/
 NGS_HD uint32_t ngs_ndigits(uint32_t v)
 {
-	return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 :
-	       v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+	/* balanced decision tree: four compares instead of a chain of nine */
+	return v < 10000u ? (v < 100u ? (v < 10u ? 1u : 2u) : (v < 1000u ? 3u : 4u))
+	                  : (v < 1000000u ? (v < 100000u ? 5u : 6u)
+	                                  : (v < 100000000u ? (v < 10000000u ? 7u : 8u) : (v < 1000000000u ? 9u : 10u)));
 }
 NGS_HD uint32_t ngs_ndigits64(uint64_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n; } return n; }
 /* printf("%d") length */
@@ -168,7 +170,15 @@ NGS_HD void ngs_put_u32_swar(Ptr dst, uint32_t v, uint32_t n)
 		n = 8;
 	}
 	d >>= 8 * (8 - n);
-	for (uint32_t i = 0; i < n; ++i) { dst[i] = (char)(d & 0xff); d >>= 8; }
+	const uint32_t lo = (uint32_t)d, hi = (uint32_t)(d >> 32);
+	dst[0] = (char)(lo & 0xff);                       /* n >= 1 */
+	if (n > 1) dst[1] = (char)((lo >> 8) & 0xff);
+	if (n > 2) dst[2] = (char)((lo >> 16) & 0xff);
+	if (n > 3) dst[3] = (char)(lo >> 24);
+	if (n > 4) dst[4] = (char)(hi & 0xff);
+	if (n > 5) dst[5] = (char)((hi >> 8) & 0xff);
+	if (n > 6) dst[6] = (char)((hi >> 16) & 0xff);
+	if (n > 7) dst[7] = (char)(hi >> 24);
 }
 /* same with the digit count already known */
 template <class Ptr>
