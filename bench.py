@@ -355,6 +355,16 @@ def main():
         kernels = {"ingest": "k_ingest_walk", "scan": "k_scan_runs", "format": "k_format_lines"}
         ach = stages[dom][0] / (stages[dom][1] * 1e-3) / 1e9 / world if stages[dom][1] > 0 else 0.0
         b_all = b_ing + b_scan + b_fmt
+        # DRAM traffic of the dominant kernel per launch from the committed ncu capture (profiles/r1_traffic.json,
+        # full-size single-GPU workload only; null otherwise)
+        traffic = None
+        try:
+            if world == 1 and args.scale == 1.0:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
+                key = [k for k in tj if k.startswith(kernels[dom])][0]
+                traffic = tj[key]["dram_read_bytes"] + tj[key]["dram_write_bytes"]
+        except Exception:
+            traffic = None
         line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
                 "data": "synthetic",
@@ -362,7 +372,7 @@ def main():
                            "parallelism": f"region-shard x{world}", "l2": "inputs (stream + difference array) far larger than the 126 MB L2; no flush needed",
                            "stream_bytes": int(in_bytes), "bases_per_s": value * 150.0, "gen_seconds": round(t_gen, 2)},
                 "roofline": {"bound": "hbm", "kernel": kernels[dom], "stage": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                             "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": stages[dom][0] / world, "ms_per_launch": stages[dom][1]},
                 "engine": {"algorithmic_bytes_per_step": b_all, "bytes_per_read": b_all / max(records, 1),
                            "hbm_frac_whole_step": b_all / (ms_step * 1e-3) / 1e9 / world / peak,

@@ -25,6 +25,13 @@
 #define NGS_SCAN_THREADS 256
 #endif
 #define NGS_SCAN_WARPS   (NGS_SCAN_THREADS / 32)
+#ifndef NGS_LB_PER
+#define NGS_LB_PER 1                 /* predecessors inspected per thread per look-back round (4: 30.1 ms, 1: 17.8 ms) */
+#endif
+#ifndef NGS_LB_THREADS
+#define NGS_LB_THREADS NGS_SCAN_THREADS   /* threads taking part in the look-back (status polling is L2 traffic:
+                                            256 pollers x 16 B per round is a quarter of the tile's own 16 KB) */
+#endif
 #define NGS_SCAN_SMEM    ((NGS_SCAN_THREADS * NGS_SCAN_ITEMS / 2 + NGS_SCAN_THREADS * NGS_SCAN_ITEMS) * 4)
 #define NGS_SCAN_ITEMS   16
 #define NGS_TILE         (NGS_SCAN_THREADS * NGS_SCAN_ITEMS)   /* 4096 difference-array elements */
@@ -911,31 +918,49 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS, NGS_SCAN_MINB) k_scan_runs(S
 		st_relaxed_u64(&A.stB[tile], (stt << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
 	}
 	if (tile > 0 && !(A.debug & 1)) {
+		/* each thread inspects NGS_LB_PER consecutive predecessors, so one round covers
+		 * NGS_SCAN_THREADS * NGS_LB_PER tiles: with ~1200 tiles in flight the nearest inclusive prefix is almost
+		 * always inside the first round (each extra round costs two block barriers plus an L2 round trip) */
 		long long base = (long long)tile - 1;
 		for (;;) {
-			const long long idx = base - t;
-			unsigned long long a = NGS_ST_INC << 62, b = NGS_ST_INC << 62;       /* virtual tiles before the launch's first: inclusive zero */
-			if (idx >= 0) {
-				do {
-					a = ld_relaxed_u64(&A.stA[idx]);
-					b = ld_relaxed_u64(&A.stB[idx]);
-				} while ((a >> 62) == NGS_ST_EMPTY || (a >> 62) != (b >> 62));
+			unsigned long long a[NGS_LB_PER], b[NGS_LB_PER];
+			#pragma unroll
+			for (int j = 0; j < NGS_LB_PER; ++j) {
+				const long long idx = base - ((long long)t * NGS_LB_PER + j);
+				a[j] = NGS_ST_INC << 62; b[j] = NGS_ST_INC << 62;        /* virtual tiles before the launch's first: inclusive zero */
+				if (idx >= 0 && t < NGS_LB_THREADS) { a[j] = ld_relaxed_u64(&A.stA[idx]); b[j] = ld_relaxed_u64(&A.stB[idx]); }
 			}
-			const unsigned int im = __ballot_sync(0xffffffffu, (a >> 62) == NGS_ST_INC);
-			if (lane == 0) s_lb_inc[warp] = im ? (unsigned)(warp * 32 + __ffs(im) - 1) : 0xffffffffu;
+			unsigned int my_inc = 0xffffffffu;                           /* position (0 = nearest tile) of this thread's first inclusive entry */
+			#pragma unroll
+			for (int j = 0; j < NGS_LB_PER; ++j) {
+				const long long idx = base - ((long long)t * NGS_LB_PER + j);
+				if (idx >= 0 && t < NGS_LB_THREADS) {
+					while ((a[j] >> 62) == NGS_ST_EMPTY || (a[j] >> 62) != (b[j] >> 62)) {
+						a[j] = ld_relaxed_u64(&A.stA[idx]); b[j] = ld_relaxed_u64(&A.stB[idx]);
+					}
+				}
+				if (t < NGS_LB_THREADS && my_inc == 0xffffffffu && (a[j] >> 62) == NGS_ST_INC) my_inc = (unsigned)(t * NGS_LB_PER + j);
+			}
+			const unsigned int wmin = __reduce_min_sync(0xffffffffu, my_inc);
+			if (lane == 0) s_lb_inc[warp] = wmin;
 			__syncthreads();
-			unsigned int first_inc = 0xffffffffu;                                /* nearest inclusive predecessor (thread index) */
+			unsigned int first_inc = 0xffffffffu;                        /* nearest inclusive predecessor (entry position) */
 			#pragma unroll
 			for (int w = 0; w < NGS_SCAN_WARPS; ++w) first_inc = s_lb_inc[w] < first_inc ? s_lb_inc[w] : first_inc;
-			const bool incl = (unsigned)t <= first_inc;
-			long long vs = incl ? (long long)(int)(uint32_t)b : 0;
-			unsigned long long vc = incl ? (a & 0x3FFFFFFFFFFFFFFFull) : 0;
-			const unsigned int vl = incl ? (unsigned int)((b >> 32) & 0x3FFFFFFFu) : 0;
+			long long vs = 0; unsigned long long vc = 0; unsigned int vl = 0;
+			#pragma unroll
+			for (int j = 0; j < NGS_LB_PER; ++j) {
+				if (t < NGS_LB_THREADS && (unsigned)(t * NGS_LB_PER + j) <= first_inc) {
+					vs += (long long)(int)(uint32_t)b[j];
+					vc += a[j] & 0x3FFFFFFFFFFFFFFFull;
+					if (vl == 0) vl = (unsigned int)((b[j] >> 32) & 0x3FFFFFFFu);   /* nearest non-zero boundary wins */
+				}
+			}
 			#pragma unroll
 			for (int o = 16; o > 0; o >>= 1) { vs += __shfl_xor_sync(0xffffffffu, vs, o); vc += __shfl_xor_sync(0xffffffffu, vc, o); }
 			const unsigned int has = __ballot_sync(0xffffffffu, vl != 0);
 			unsigned int near_l = 0;
-			if (has) near_l = __shfl_sync(0xffffffffu, vl, __ffs(has) - 1);      /* lowest lane = nearest tile */
+			if (has) near_l = __shfl_sync(0xffffffffu, vl, __ffs(has) - 1);      /* lowest lane = nearest tiles */
 			if (lane == 0) { s_lb_sum[warp] = vs; s_lb_cnt[warp] = vc; s_lb_last[warp] = near_l; }
 			__syncthreads();
 			unsigned int rl = 0;
@@ -943,7 +968,7 @@ __global__ void __launch_bounds__(NGS_SCAN_THREADS, NGS_SCAN_MINB) k_scan_runs(S
 			for (int w = 0; w < NGS_SCAN_WARPS; ++w) { tile_sum += s_lb_sum[w]; tile_cnt += s_lb_cnt[w]; if (rl == 0) rl = s_lb_last[w]; }
 			if (tile_last == 0) tile_last = rl;
 			if (first_inc != 0xffffffffu) break;
-			base -= NGS_SCAN_THREADS;
+			base -= NGS_LB_THREADS * NGS_LB_PER;
 			__syncthreads();
 		}
 		if (t == 0) {
