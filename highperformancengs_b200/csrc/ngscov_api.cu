@@ -278,10 +278,10 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	CK(cudaMalloc((void **)&h->d_ctr, NGS_CTR_STRIPES * 16 * 8));
 	CK(cudaHostAlloc((void **)&h->h_ctr, NGS_CTR_STRIPES * 16 * 8, cudaHostAllocDefault));
 	h->stage_cap = cfg->staging_bytes ? (size_t)cfg->staging_bytes : (size_t)256 << 20;
-	/* Two ingest organisations are kept, both parity-tested: the fused walk+decode kernel (default: fastest on
-	 * B200 today) and the K1 frame / K2 per-record decode split (NGSCOV_SPLIT=1), see DESIGN.md section 4. */
+	/* Two ingest organisations are kept, both parity-tested: K1 record framing + K2 per-record decode (default:
+	 * 22.7 ms on config 2) and the single fused walk+decode kernel (NGSCOV_FUSED=1: 27.1 ms), DESIGN.md section 4. */
 	h->stream_fin = cfg->slice_end == 0 && !(getenv("NGSCOV_STREAM_FINALIZE") && atoi(getenv("NGSCOV_STREAM_FINALIZE")) == 0);
-	h->fused = !(getenv("NGSCOV_SPLIT") && atoi(getenv("NGSCOV_SPLIT")) == 1);
+	h->fused = getenv("NGSCOV_FUSED") && atoi(getenv("NGSCOV_FUSED")) == 1;
 	h->shift = 0;
 	const char *env = getenv("NGSCOV_SUBCHUNK");
 	if (env && atoi(env) >= 64) { int v = atoi(env), s = 6; while ((1 << (s + 1)) <= v) ++s; h->shift = s; }
@@ -461,7 +461,7 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 	}
 	if (!h->fused && !h->p_k2_done) {
 		IngestArgs A = make_ingest_args(h, h->p_base, h->p_n, h->p_nsub, h->p_from_state, h->p_fixed0);
-		k_decode_scatter<<<(unsigned)((h->p_nsub + 7) / 8), 256, 0, h->s_main>>>(A);
+		k_decode_scatter<<<(unsigned)((((uint64_t)h->p_nsub << A.slot_shift) + 255) / 256), 256, 0, h->s_main>>>(A);
 		h->stats.launches += 1;
 		h->p_k2_done = true;
 	}
@@ -471,7 +471,14 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 	CK(cudaGetLastError());
 	h->pending = false;
 	/* sorted input: every contig below the highest refID decoded so far is complete */
-	if (allow_stream && h->stream_fin && h->fused && !(h->h_st->flags & (NGS_FLAG_EFORMAT | NGS_FLAG_ERANGE)) && h->h_st->max_ref_p1 > 1) {
+	if (allow_stream && h->stream_fin && !h->fused) {
+		/* K2 ran after the state snapshot taken by the verification: take a fresh one, fold the striped counters */
+		CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
+		CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, NGS_CTR_STRIPES * 16 * 8, cudaMemcpyDeviceToHost, h->s_main));
+		CK(cudaStreamSynchronize(h->s_main));
+		for (int i = 0; i < NGS_CTR_STRIPES; ++i) h->h_st->m_ops += h->h_ctr[i * 16 + 2];
+	}
+	if (allow_stream && h->stream_fin && !(h->h_st->flags & (NGS_FLAG_EFORMAT | NGS_FLAG_ERANGE)) && h->h_st->max_ref_p1 > 1) {
 		const size_t upto = std::min<size_t>(h->h_st->max_ref_p1 - 1, h->seg.size());
 		if (upto > h->next_fin_seg) return stream_finalize(h, upto);
 	}
@@ -484,7 +491,7 @@ static int pick_shift(ngscov *h, int32_t first_block_size)
 	int64_t rec = (int64_t)first_block_size + 4;
 	if (rec < 36) rec = 36;
 	if (rec > 4096) rec = 4096;
-	int64_t want = rec * 32; int s = 9;                       /* ~32-64 records per sub-chunk, 512 B .. 32 KiB */
+	int64_t want = rec * 128; int s = 9;                      /* ~128-256 records per sub-chunk, 512 B .. 32 KiB */
 	while (((int64_t)1 << s) < want && s < 15) ++s;
 	h->shift = s;
 	return 0;
@@ -523,7 +530,7 @@ static int submit_chunk(ngscov *h, const uint8_t *base, int64_t n, bool from_sta
 	if (!r && !h->fused) {
 		/* K2 queued optimistically behind the verification: it returns at once if a mismatch was found,
 		 * and is then launched again by resolve_pending after the repair */
-		k_decode_scatter<<<(unsigned)((n_sub + 7) / 8), 256, 0, h->s_main>>>(A);
+		k_decode_scatter<<<(unsigned)((((uint64_t)n_sub << A.slot_shift) + 255) / 256), 256, 0, h->s_main>>>(A);
 		h->stats.launches += 1;
 		h->p_k2_done = true;
 		CK(cudaGetLastError());

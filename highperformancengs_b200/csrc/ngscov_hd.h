@@ -254,7 +254,7 @@ NGS_HD void ngs_decode_record(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o
 	cnt.kept += 1;
 	const int32_t si = cfg.ctg2seg[h.ref_id];
 	if (si < 0 || h.n_cigar == 0) return;
-	const ngs_seg sg = cfg.seg[si];
+	const ngs_seg &sg = cfg.seg[si];                     /* only base / clip_lo / lim / hard_end are touched */
 	uint32_t p = (uint32_t)h.pos;
 	int64_t co = o + 36 + (int64_t)h.l_qname;
 	for (uint32_t i = 0; i < h.n_cigar; ++i, co += 4) {

@@ -47,7 +47,7 @@
 #define NGS_FMT_MINB 4
 #endif
 
-#define NGS_CTR_STRIPES  64           /* counter stripes, one 128-byte line each: same-address atomics from ~10^6
+#define NGS_CTR_STRIPES  256          /* counter stripes, one 128-byte line each: same-address atomics from ~10^6
                                          warps otherwise serialise in L2 and stall every load of the state line */
 #define NGS_FLAG_ERANGE  1u
 #define NGS_FLAG_EFORMAT 2u
@@ -381,72 +381,63 @@ struct WarpSink {
 	__device__ __forceinline__ void flag_range_error() { atomicOr(flags, NGS_FLAG_ERANGE); }
 };
 
-/* K2: core/CIGAR decode + scatter.  One warp per sub-chunk row; a lane takes slots lane and lane+32 of
- * each 64-slot batch and requests both headers before decoding either (two independent loads in
- * flight per lane, consecutive lanes = consecutive records = neighbouring cache lines). */
-__global__ void __launch_bounds__(256) k_decode_scatter(IngestArgs A)
+/* K2: core/CIGAR decode + scatter, one thread per framed record (slot).  Consecutive lanes hold
+ * consecutive records, so a warp's header loads and its +1/-1 REDs fall into a handful of neighbouring
+ * cache lines: measured 200 G RED/s for this pattern against 28-47 G RED/s when every lane walks its own
+ * sub-chunk (tools/microbench/red_bench.cu).  The chain of dependent loads is kept to three levels
+ * (slot -> header -> CIGAR + segment geometry, the latter L1-resident). */
+__global__ void __launch_bounds__(256, 8) k_decode_scatter(IngestArgs A)
 {
 	const unsigned full = 0xffffffffu;
 	const ngs_dev_state *st = A.st;
 	if (st->n_bad != 0 || (st->flags & NGS_FLAG_EFORMAT)) return;      /* launched optimistically behind the verification */
-	const int lane = threadIdx.x & 31;
-	const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t c = (int64_t)(tid >> A.slot_shift);
+	const unsigned int n_slots = 1u << A.slot_shift, k = (unsigned int)(tid & (n_slots - 1));
 	ngs_counts cnt = { 0, 0, 0, 0 };
+	unsigned int todo = 0;
+	int64_t o = 0;
 	if (c < A.n_sub) {
-		const unsigned int n_slots = 1u << A.slot_shift, have = A.count[c];
-		const unsigned int framed = have < n_slots ? have : n_slots;
-		if (framed) {
-			const long long e = A.entry[c];
-			const unsigned short *row = A.slots + ((size_t)c << A.slot_shift);
-			DevMem mem = { A.base, A.n };
-			WarpSink sink = { A.diff, &A.st->flags, A.debug, false };
-			for (unsigned int b = 0; b < framed; b += 64) {
-				const unsigned int k0 = b + lane, k1 = b + 32 + lane;
-				const bool a0 = k0 < framed, a1 = k1 < framed;
-				int64_t o0 = 0, o1 = 0;
-				ngs_hdr h0, h1;
-				h0.pos = -2 - lane; h1.pos = -2 - lane; h0.ref_id = h1.ref_id = -1;
-				if (a0) { o0 = e + row[k0]; mem.hdr_lite(o0, h0); }
-				if (a1) { o1 = e + row[k1]; mem.hdr_lite(o1, h1); }
-				/* pile-up detection: does any lane share its start with the next lane? */
-				const int p0n = __shfl_down_sync(full, h0.pos, 1), p1n = __shfl_down_sync(full, h1.pos, 1);
-				const bool d0 = __any_sync(full, a0 && lane < 31 && p0n == h0.pos);
-				const bool d1 = __any_sync(full, a1 && lane < 31 && p1n == h1.pos);
-				sink.fold = d0;
-				if (a0) ngs_decode_record(A.cfg, mem, o0, h0, sink, +1, cnt);
-				__syncwarp();
-				sink.fold = d1;
-				if (a1) ngs_decode_record(A.cfg, mem, o1, h1, sink, +1, cnt);
-				__syncwarp();
-				/* records beyond the row's capacity (only possible with pathologically small records): the lane
-				 * holding the last slot keeps walking the chain */
-				if (have > n_slots && (k0 == n_slots - 1 || k1 == n_slots - 1)) {
-					int64_t o = (k0 == n_slots - 1) ? o0 + 4 + (int64_t)h0.block_size : o1 + 4 + (int64_t)h1.block_size;
-					sink.fold = false;
-					for (unsigned int r = n_slots; r < have; ++r) {
-						ngs_hdr h;
-						mem.hdr_lite(o, h);
-						ngs_decode_record(A.cfg, mem, o, h, sink, +1, cnt);
-						o += 4 + (int64_t)h.block_size;
-					}
-				}
-			}
+		const unsigned int have = A.count[c];
+		if (k < have) {
+			o = A.entry[c] + A.slots[((size_t)c << A.slot_shift) + k];
+			todo = (k == n_slots - 1) ? have - k : 1;                    /* the last slot also owns any overflow records */
+		}
+	}
+	DevMem mem = { A.base, A.n };
+	ngs_hdr h;
+	h.pos = -2 - (int)(threadIdx.x & 31); h.ref_id = -1; h.block_size = 0;
+	if (todo) mem.hdr_lite(o, h);
+	const ngs_walk_cfg &cfg = A.cfg;                                    /* segment table: a few L1-resident lines */
+	/* pile-up detection: sorted input puts equal starts in adjacent lanes */
+	const int pn = __shfl_down_sync(full, h.pos, 1);
+	WarpSink sink = { A.diff, &A.st->flags, A.debug, false };
+	/* fold only real pile-ups (half the warp shares its start with a neighbour); at WGS depth one or two equal
+	 * neighbours per warp are normal and the warp match would cost more than the few duplicate REDs */
+	sink.fold = __popc(__ballot_sync(full, todo && (threadIdx.x & 31) < 31 && pn == h.pos)) >= 16;
+	if (todo) {
+		ngs_decode_record(cfg, mem, o, h, sink, +1, cnt);
+		for (--todo; todo; --todo) {                                      /* overflow records of a row (pathologically small records) */
+			o += 4 + (int64_t)h.block_size;
+			mem.hdr_lite(o, h);
+			sink.fold = false;
+			ngs_decode_record(cfg, mem, o, h, sink, +1, cnt);
 		}
 	}
 	{
 		const unsigned mr = __reduce_max_sync(0xffffffffu, cnt.max_ref_p1);
 		if ((threadIdx.x & 31) == 0 && mr > A.st->max_ref_p1) atomicMax(&A.st->max_ref_p1, mr);
 	}
-	/* block-level reduction, then one atomic per counter per CTA into this CTA's stripe */
-	__shared__ unsigned long long s_c[8][4];
+	/* warp-level reduction, then one atomic per counter per warp into a stripe picked by the warp index (no
+	 * block barrier: this kernel does so little per thread that the barrier was 19 % of its stall samples) */
 	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
 	                   v2 = warp_sum_u64(cnt.m_ops), v3 = warp_sum_u64(cnt.cigar_words);
-	if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5][0] = v0; s_c[threadIdx.x >> 5][1] = v1; s_c[threadIdx.x >> 5][2] = v2; s_c[threadIdx.x >> 5][3] = v3; }
-	__syncthreads();
-	if (threadIdx.x < 4) {
-		unsigned long long t = 0;
-		for (int w = 0; w < 8; ++w) t += s_c[w][threadIdx.x];
-		if (t) atomicAdd(A.ctr + (size_t)(blockIdx.x % NGS_CTR_STRIPES) * 16 + threadIdx.x, t);
+	if ((threadIdx.x & 31) == 0 && v0) {
+		unsigned long long *c4 = A.ctr + (size_t)((tid >> 5) % NGS_CTR_STRIPES) * 16;
+		atomicAdd(c4 + 0, v0);
+		if (v1) atomicAdd(c4 + 1, v1);
+		if (v2) atomicAdd(c4 + 2, v2);
+		if (v3) atomicAdd(c4 + 3, v3);
 	}
 }
 

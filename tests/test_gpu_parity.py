@@ -67,9 +67,10 @@ def test_straddling_pushes(oracle, monkeypatch, staging, sub, variant):
     """records cut by push boundaries (carry path) and tiny sub-chunks (speculation + repair path), for
     every ingest organisation: fused walk+decode, K1 frame / K2 decode split, shared-memory staged tiles"""
     monkeypatch.setenv("NGSCOV_SUBCHUNK", sub)
-    if variant == "split":
-        monkeypatch.setenv("NGSCOV_SPLIT", "1")
+    if variant == "fused":
+        monkeypatch.setenv("NGSCOV_FUSED", "1")
     if variant == "tiles":
+        monkeypatch.setenv("NGSCOV_FUSED", "1")
         monkeypatch.setenv("NGSCOV_TILES", "1")
     names, lens, reads = bamutil.random_case(7, n_reads=4000)
     recs = bamutil.records(reads)
@@ -91,8 +92,8 @@ def test_empty_input(oracle):
 @pytest.mark.parametrize("resident", [False, True])
 @pytest.mark.parametrize("variant", ["fused", "split"])
 def test_generator_configs(oracle, monkeypatch, config, scale, window, resident, variant):
-    if variant == "split":
-        monkeypatch.setenv("NGSCOV_SPLIT", "1")
+    if variant == "fused":
+        monkeypatch.setenv("NGSCOV_FUSED", "1")
     from highperformancengs_b200.gen import Generator
     g = Generator(config, scale=scale)
     recs = g.records()
