@@ -50,7 +50,8 @@ struct ngscov {
 	long long *d_entry, *d_exit, *d_bmax; size_t sub_cap, bmax_cap;
 	unsigned int *d_count; unsigned short *d_slots; size_t slots_cap;
 	unsigned long long *d_ctr, *h_ctr;        /* striped K2 counters */
-	bool fused;                               /* NGSCOV_FUSED=1: the single-kernel walk+decode variant */
+	bool fused;                               /* deltas are applied before the verification (single-pass variants) */
+	int ingest_mode;                          /* 0 K1+K2 split, 1 fused walk, 2 tiles (fused decode), 3 tiles2 (staged K1+K2) */
 	bool p_k2_done;
 	ngs_dev_state *d_st, *h_st;
 
@@ -223,6 +224,7 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	CK(cudaEventCreateWithFlags(&h->ev_finalized, cudaEventDisableTiming));
 	CK(cudaEventCreate(&h->ev_t0)); CK(cudaEventCreate(&h->ev_t1));
 	CK(cudaFuncSetAttribute(k_ingest_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)NGS_TILE_THREADS << 10) + NGS_TILE_MARGIN)));
+	CK(cudaFuncSetAttribute(k_ingest_tiles2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)NGS_T2_SUB << 10) + NGS_TILE_MARGIN + ((size_t)NGS_T2_SUB << 5) * 2)));
 	build_geometry(h);
 	CKC(dev_upload(h, &h->d_seg, h->seg));
 	CKC(dev_upload(h, &h->d_ctg2seg, h->ctg2seg));
@@ -281,7 +283,14 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	/* Two ingest organisations are kept, both parity-tested: K1 record framing + K2 per-record decode (default:
 	 * 22.7 ms on config 2) and the single fused walk+decode kernel (NGSCOV_FUSED=1: 27.1 ms), DESIGN.md section 4. */
 	h->stream_fin = cfg->slice_end == 0 && !(getenv("NGSCOV_STREAM_FINALIZE") && atoi(getenv("NGSCOV_STREAM_FINALIZE")) == 0);
-	h->fused = getenv("NGSCOV_FUSED") && atoi(getenv("NGSCOV_FUSED")) == 1;
+	h->ingest_mode = 0;
+	if (getenv("NGSCOV_FUSED") && atoi(getenv("NGSCOV_FUSED")) == 1) h->ingest_mode = 1;
+	if (h->ingest_mode == 1 && getenv("NGSCOV_TILES") && atoi(getenv("NGSCOV_TILES")) == 1) h->ingest_mode = 2;
+	if (getenv("NGSCOV_INGEST")) {
+		const char *m = getenv("NGSCOV_INGEST");
+		h->ingest_mode = !strcmp(m, "fused") ? 1 : !strcmp(m, "tiles") ? 2 : !strcmp(m, "tiles2") ? 3 : 0;
+	}
+	h->fused = h->ingest_mode != 0;
 	h->shift = 0;
 	const char *env = getenv("NGSCOV_SUBCHUNK");
 	if (env && atoi(env) >= 64) { int v = atoi(env), s = 6; while ((1 << (s + 1)) <= v) ++s; h->shift = s; }
@@ -392,7 +401,7 @@ static int ensure_sub(ngscov *h, int64_t n_sub)
 		CK(cudaMalloc((void **)&h->d_count, cap * 4));
 		h->sub_cap = cap;
 	}
-	if (!h->fused) {
+	if (h->ingest_mode == 0) {
 		const size_t need = ((size_t)n_sub << (h->shift - 5)) + 64;
 		if (need > h->slots_cap) {
 			CK(cudaStreamSynchronize(h->s_main));
@@ -471,8 +480,9 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 	CK(cudaGetLastError());
 	h->pending = false;
 	/* sorted input: every contig below the highest refID decoded so far is complete */
-	if (allow_stream && h->stream_fin && !h->fused) {
-		/* K2 ran after the state snapshot taken by the verification: take a fresh one, fold the striped counters */
+	if (allow_stream && h->stream_fin && (h->ingest_mode == 0 || h->ingest_mode == 3)) {
+		/* these variants count in striped counters (and K2 runs after the verification's state snapshot): take a
+		 * fresh snapshot and fold the stripes */
 		CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
 		CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, NGS_CTR_STRIPES * 16 * 8, cudaMemcpyDeviceToHost, h->s_main));
 		CK(cudaStreamSynchronize(h->s_main));
@@ -492,7 +502,9 @@ static int pick_shift(ngscov *h, int32_t first_block_size)
 	if (rec < 36) rec = 36;
 	if (rec > 4096) rec = 4096;
 	int64_t want = rec * 128; int s = 9;                      /* ~128-256 records per sub-chunk, 512 B .. 32 KiB */
-	while (((int64_t)1 << s) < want && s < 15) ++s;
+	int smax = 15;
+	if (h->ingest_mode >= 2) { want = rec * 16; smax = 10; }   /* staged variants: a tile of 64 sub-chunks must fit shared memory */
+	while (((int64_t)1 << s) < want && s < smax) ++s;
 	h->shift = s;
 	return 0;
 }
@@ -511,9 +523,12 @@ static int submit_chunk(ngscov *h, const uint8_t *base, int64_t n, bool from_sta
 	} else {
 		/* single-kernel variants (NGSCOV_FUSED=1; NGSCOV_TILES=1 stages tiles in shared memory): kept for A/B
 		 * measurements, see DESIGN.md section 4 */
-		const char *tenv = getenv("NGSCOV_TILES");
-		const bool tiles = tenv && atoi(tenv) == 1 && h->shift <= 10 && (((uintptr_t)base) & 15) == 0;
-		if (tiles) {
+		const bool staged_ok = h->shift <= 10 && (((uintptr_t)base) & 15) == 0;
+		if (h->ingest_mode == 3 && staged_ok) {
+			const size_t smem = ((size_t)NGS_T2_SUB << h->shift) + NGS_TILE_MARGIN + ((size_t)NGS_T2_SUB << A.slot_shift) * 2;
+			const unsigned nb = (unsigned)((n_sub + NGS_T2_SUB - 1) / NGS_T2_SUB);
+			k_ingest_tiles2<<<nb, NGS_T2_THREADS, smem, h->s_main>>>(A);
+		} else if (h->ingest_mode == 2 && staged_ok) {
 			const size_t smem = ((size_t)NGS_TILE_THREADS << h->shift) + NGS_TILE_MARGIN;
 			const unsigned nb = (unsigned)((n_sub + NGS_TILE_THREADS - 1) / NGS_TILE_THREADS);
 			k_ingest_tiles<<<nb, NGS_TILE_THREADS, smem, h->s_main>>>(A);

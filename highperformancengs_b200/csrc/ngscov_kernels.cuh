@@ -596,6 +596,127 @@ __global__ void __launch_bounds__(NGS_TILE_THREADS) k_ingest_tiles(IngestArgs A)
 }
 
 
+/* ------------------------------------------------------------------------------------------------ */
+/* K1+K2 in one pass over the stream ("tiles2"): a CTA stages a tile of NGS_T2_SUB sub-chunks in shared
+ * memory with one bulk async copy (TMA engine), frames its records there (speculative per-sub-chunk
+ * chain walk, hops at shared-memory latency, offsets into a shared slot table), then decodes them one
+ * thread per RECORD straight from shared memory, so the REDs are warp-coalesced (consecutive lanes =
+ * consecutive records) and HBM sees the stream exactly once.  Deltas are applied before the chunk-level
+ * verification, so a mis-speculated sub-chunk is repaired with the undo/redo walk of k_repair. */
+#define NGS_T2_SUB     64           /* sub-chunks (walker threads) per tile */
+#define NGS_T2_THREADS 256
+
+__global__ void __launch_bounds__(NGS_T2_THREADS) k_ingest_tiles2(IngestArgs A)
+{
+	extern __shared__ __align__(128) uint8_t s_stream[];
+	__shared__ __align__(8) unsigned long long s_bar;
+	__shared__ long long s_entry[NGS_T2_SUB];
+	__shared__ unsigned int s_count[NGS_T2_SUB];
+	const unsigned full = 0xffffffffu;
+	const int t = threadIdx.x, lane = t & 31;
+	const int64_t tile_bytes = (int64_t)NGS_T2_SUB << A.shift;
+	const int64_t t0 = (int64_t)blockIdx.x * tile_bytes;
+	int64_t t1 = t0 + tile_bytes + NGS_TILE_MARGIN;
+	if (t1 > A.n) t1 = A.n;
+	t1 = t0 + ((t1 - t0) & ~(int64_t)15);                     /* bulk copies move multiples of 16 bytes */
+	const uint32_t nbytes = (uint32_t)(t1 - t0);
+	const uint32_t n_slots = 1u << A.slot_shift;
+	unsigned short *s_slots = reinterpret_cast<unsigned short *>(s_stream + tile_bytes + NGS_TILE_MARGIN);   /* [NGS_T2_SUB][n_slots] */
+	const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+	if (t == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (t == 0 && nbytes) {
+		const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_stream);
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(nbytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		             :: "r"(dst), "l"(A.base + t0), "r"(nbytes), "r"(bar) : "memory");
+	}
+	if (nbytes) {
+		uint32_t done = 0;
+		while (!done) {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+			             : "=r"(done) : "r"(bar) : "memory");
+		}
+	}
+	TileMem mem; mem.g.base = A.base; mem.g.n = A.n; mem.sm = s_stream; mem.t0 = t0; mem.t1 = t1;
+	/* ---- phase 1 (first NGS_T2_SUB threads = two warps): frame the records of each sub-chunk */
+	if (t < NGS_T2_SUB) {
+		const int64_t c = (int64_t)blockIdx.x * NGS_T2_SUB + t;
+		const bool live = c < A.n_sub;
+		const int64_t lo = live ? (c << A.shift) : 0;
+		int64_t hi = live ? lo + ((int64_t)1 << A.shift) : 0;
+		if (hi > A.n) hi = A.n;
+		long long entry = NGS_NONE;
+		bool searching = live && c != 0;
+		if (live && c == 0) {
+			const long long e0 = A.entry0_from_state ? A.st->entry_next : A.fixed_entry0;
+			entry = e0 < hi ? e0 : NGS_NONE;
+		}
+		{
+			const int64_t end = hi < A.n - 35 ? hi : A.n - 35;
+			int64_t o = lo;
+			while (__any_sync(full, searching)) {
+				if (searching) { o = mem.next_candidate(o, end, (uint32_t)A.cfg.n_ref); if (o == NGS_NONE) searching = false; }
+				__syncwarp();
+				if (searching) {
+					if (ngs_candidate_ok(A.cfg, mem, A.ref_len, o)) { entry = o; searching = false; } else ++o;
+				}
+			}
+		}
+		unsigned int count = 0; long long ex = 0;
+		if (entry != NGS_NONE) ex = chain_walk(A.cfg, mem, entry, hi, s_slots + (size_t)t * n_slots, n_slots, count);
+		s_entry[t] = entry; s_count[t] = count;
+		if (live) { A.entry[c] = entry; A.exit[c] = ex; }
+		const unsigned long long w = warp_sum_u64(entry != NGS_NONE ? 1ull : 0ull);
+		if (lane == 0 && w) atomicAdd(&A.st->spec_walks, w);
+	}
+	__syncthreads();
+	/* ---- phase 2 (all threads): decode + scatter, one thread per framed record, straight from shared memory */
+	ngs_counts cnt = { 0, 0, 0, 0 };
+	WarpSink sink = { A.diff, &A.st->flags, A.debug, false };
+	const uint32_t total = NGS_T2_SUB * n_slots;
+	const uint32_t total_up = (total + NGS_T2_THREADS - 1) / NGS_T2_THREADS * NGS_T2_THREADS;   /* warp-uniform trip count */
+	for (uint32_t p = t; p < total_up; p += NGS_T2_THREADS) {
+		const uint32_t r = p >> A.slot_shift, k = p & (n_slots - 1);
+		unsigned int todo = 0; int64_t o = 0;
+		if (p < total) {
+			const unsigned int have = s_count[r];
+			if (k < have) { o = s_entry[r] + s_slots[(size_t)r * n_slots + k]; todo = (k == n_slots - 1) ? have - k : 1; }
+		}
+		ngs_hdr h;
+		h.pos = -2 - lane; h.ref_id = -1; h.block_size = 0;
+		if (todo) mem.hdr_lite(o, h);
+		const int pn = __shfl_down_sync(full, h.pos, 1);
+		sink.fold = __popc(__ballot_sync(full, todo && lane < 31 && pn == h.pos)) >= 16;
+		if (todo) {
+			ngs_decode_record(A.cfg, mem, o, h, sink, +1, cnt);
+			for (--todo; todo; --todo) {
+				o += 4 + (int64_t)h.block_size;
+				mem.hdr_lite(o, h);
+				sink.fold = false;
+				ngs_decode_record(A.cfg, mem, o, h, sink, +1, cnt);
+			}
+		}
+		__syncwarp();
+	}
+	{
+		const unsigned mr = __reduce_max_sync(full, cnt.max_ref_p1);
+		if (lane == 0 && mr > A.st->max_ref_p1) atomicMax(&A.st->max_ref_p1, mr);
+	}
+	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
+	                   v2 = warp_sum_u64(cnt.m_ops), v3 = warp_sum_u64(cnt.cigar_words);
+	if (lane == 0 && v0) {
+		unsigned long long *c4 = A.ctr + (size_t)((blockIdx.x * (NGS_T2_THREADS / 32) + (t >> 5)) % NGS_CTR_STRIPES) * 16;
+		atomicAdd(c4 + 0, v0);
+		if (v1) atomicAdd(c4 + 1, v1);
+		if (v2) atomicAdd(c4 + 2, v2);
+		if (v3) atomicAdd(c4 + 3, v3);
+	}
+}
+
 __device__ __forceinline__ long long block_max_ll(long long v, long long *sm)
 {
 	#pragma unroll

@@ -62,16 +62,15 @@ def test_random_cases(oracle, mode, mname, seed, window):
 
 @pytest.mark.parametrize("staging", [4096, 70000])
 @pytest.mark.parametrize("sub", ["64", "512"])
-@pytest.mark.parametrize("variant", ["fused", "split", "tiles"])
+@pytest.mark.parametrize("variant", ["fused", "split", "tiles", "tiles2"])
 def test_straddling_pushes(oracle, monkeypatch, staging, sub, variant):
     """records cut by push boundaries (carry path) and tiny sub-chunks (speculation + repair path), for
     every ingest organisation: fused walk+decode, K1 frame / K2 decode split, shared-memory staged tiles"""
     monkeypatch.setenv("NGSCOV_SUBCHUNK", sub)
     if variant == "fused":
         monkeypatch.setenv("NGSCOV_FUSED", "1")
-    if variant == "tiles":
-        monkeypatch.setenv("NGSCOV_FUSED", "1")
-        monkeypatch.setenv("NGSCOV_TILES", "1")
+    if variant in ("tiles", "tiles2"):
+        monkeypatch.setenv("NGSCOV_INGEST", variant)
     names, lens, reads = bamutil.random_case(7, n_reads=4000)
     recs = bamutil.records(reads)
     exp = oracle.run(recs, names, lens, 0, 500)
@@ -90,10 +89,12 @@ def test_empty_input(oracle):
 
 @pytest.mark.parametrize("config,scale,window", [(1, 0.05, 20000), (2, 0.0005, 20000), (4, 0.01, 100), (4, 0.01, 20000), (5, 0.002, 20000)])
 @pytest.mark.parametrize("resident", [False, True])
-@pytest.mark.parametrize("variant", ["fused", "split"])
+@pytest.mark.parametrize("variant", ["fused", "split", "tiles2"])
 def test_generator_configs(oracle, monkeypatch, config, scale, window, resident, variant):
     if variant == "fused":
         monkeypatch.setenv("NGSCOV_FUSED", "1")
+    if variant == "tiles2":
+        monkeypatch.setenv("NGSCOV_INGEST", "tiles2")
     from highperformancengs_b200.gen import Generator
     g = Generator(config, scale=scale)
     recs = g.records()
@@ -158,3 +159,16 @@ def test_streamed_per_contig_finalize(oracle, staging):
         exp = oracle.run(recs, names, lens, mode, 250)
         got = run_engine(names, lens, recs, mode, 250, staging_bytes=staging)
         check(got, exp, mode, f"streamed staging={staging} mode={mode}")
+
+
+@pytest.mark.parametrize("config,scale,mode,window", [(5, 0.1, 0, 20000), (4, 0.1, 1, 20000), (2, 0.004, 0, 20000)])
+def test_generator_configs_larger(oracle, config, scale, mode, window):
+    """a few million reads per case: extreme pile-ups (config 5: depth > 10^4 on 400 amplicons), spliced RNA-seq
+    (config 4) and WGS (config 2), streamed from host memory in 64 MiB pushes"""
+    from highperformancengs_b200.gen import Generator
+    g = Generator(config, scale=scale)
+    recs = g.records()
+    exp = oracle.run(recs, g.names, g.lens, mode, window)
+    got = run_engine(g.names, g.lens, recs, mode, window, staging_bytes=64 << 20)
+    check(got, exp, mode, f"config{config} scale={scale}")
+    assert got["stats"]["records"] == g.n_reads
