@@ -352,7 +352,7 @@ def main():
         b_fmt = float(out_b)
         stages = {"ingest": (b_ing, ms_ing / args.steps), "scan": (b_scan, ms_scan / args.steps), "format": (b_fmt, ms_fmt / args.steps)}
         dom = max(stages, key=lambda k: stages[k][1])
-        kernels = {"ingest": "k_ingest_walk", "scan": "k_scan_runs", "format": "k_format_lines"}
+        kernels = {"ingest": "k_decode_scatter", "scan": "k_scan_runs", "format": "k_format_lines"}   # ingest = K1 k_chain_walk + K2
         ach = stages[dom][0] / (stages[dom][1] * 1e-3) / 1e9 / world if stages[dom][1] > 0 else 0.0
         b_all = b_ing + b_scan + b_fmt
         # DRAM traffic of the dominant kernel per launch from the committed ncu capture (profiles/r1_traffic.json,
