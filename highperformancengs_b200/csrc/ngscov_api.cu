@@ -10,6 +10,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <type_traits>
 #include <algorithm>
 #include <chrono>
 
@@ -908,7 +909,28 @@ static int run_format(ngscov *h, int which, unsigned long long n_items, const Pr
 	FmtArgs A;
 	A.n_items = n_items; A.n_tiles = n_tiles; A.status = h->d_fmt_status; A.out = h->d_text[which] + out_off;
 	A.out_cap = h->d_text_cap[which] - out_off; A.st = h->d_st; A.stage_bytes = stage;
-	if (ipt == 4) {
+	A.debug = getenv("NGSCOV_DEBUG_FMT") ? atoi(getenv("NGSCOV_DEBUG_FMT")) : 0;
+	bool fast_bed = false;
+	if constexpr (std::is_same<Producer, BedProducer>::value) {
+		/* bedGraph: register-assembled lines (k_format_bed); NGSCOV_FMT=generic keeps the byte-wise producer path */
+		const char *e = getenv("NGSCOV_FMT");
+		fast_bed = ipt == 4 && !(e && !strcmp(e, "generic"));
+		if (fast_bed) {
+			const int minb = getenv("NGSCOV_FMT_MINB") ? atoi(getenv("NGSCOV_FMT_MINB")) : 4;
+			if (minb == 6) {
+				CK(cudaFuncSetAttribute(k_format_bed<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+				k_format_bed<4, 6><<<(unsigned)n_tiles, NGS_FMT_THREADS, stage, h->s_main>>>(A, P);
+			} else if (minb == 5) {
+				CK(cudaFuncSetAttribute(k_format_bed<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+				k_format_bed<4, 5><<<(unsigned)n_tiles, NGS_FMT_THREADS, stage, h->s_main>>>(A, P);
+			} else {
+				CK(cudaFuncSetAttribute(k_format_bed<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+				k_format_bed<4, 4><<<(unsigned)n_tiles, NGS_FMT_THREADS, stage, h->s_main>>>(A, P);
+			}
+		}
+	}
+	if (fast_bed) {
+	} else if (ipt == 4) {
 		CK(cudaFuncSetAttribute(k_format_lines<Producer, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
 		k_format_lines<Producer, 4><<<(unsigned)n_tiles, NGS_FMT_THREADS, stage, h->s_main>>>(A, P);
 	} else if (ipt == 2) {
@@ -944,13 +966,17 @@ static int format_bed_range(ngscov *h, size_t s0, size_t s1)
 	P.nt.names = h->d_names; P.nt.name_off = h->d_name_off; P.nt.name8 = h->d_name8;
 	P.drop_idx = h->drop_idx; P.mod_idx = h->mod_idx; P.mod_end = h->mod_end;
 	const uint32_t dd = std::max(dig((uint64_t)std::max(st.max_depth, 0)), 1 + dig((uint64_t)(-(int64_t)std::min(st.min_depth, 0))));
-	size_t bound = 0;
+	size_t bound = 0, max_line = 8;
 	for (size_t sg = s0; sg < s1; ++sg) {
 		const unsigned long long k = h->h_rec_base[sg - s0 + 1] - h->h_rec_base[sg - s0];
 		const uint32_t pd = dig(std::max<uint64_t>(h->seg[sg].lim, h->mod_end));
-		bound += (size_t)k * (h->ref_name[h->seg[sg].contig].size() + 1 + 2 * pd + 2 + dd + 1);
+		const size_t line = h->ref_name[h->seg[sg].contig].size() + 1 + 2 * pd + 2 + dd + 1;     /* longest possible line of the contig */
+		bound += (size_t)k * line;
+		max_line = std::max(max_line, line);
 	}
-	r = run_format(h, NGSCOV_OUT_BEDGRAPH, st.n_boundaries, P, h->max_name_tab + 10 + 1 + 10 + 1 + 11 + 1, bound, h->bed_off);
+	/* the staging tile is sized from the longest line that can occur (known depth range, contig lengths), not from
+	 * the type limits: 29 instead of 40 bytes per line on the WGS workload lets more tiles be resident per SM */
+	r = run_format(h, NGSCOV_OUT_BEDGRAPH, st.n_boundaries, P, (uint32_t)max_line, bound, h->bed_off);
 	if (r) return r;
 	h->bed_off = h->text_len[NGSCOV_OUT_BEDGRAPH];
 	if (streamed && h->bed_off > h->bed_d2h && !getenv("NGSCOV_DEBUG_NOD2H")) {

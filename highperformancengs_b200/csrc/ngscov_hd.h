@@ -18,8 +18,10 @@
 
 #if defined(__CUDACC__)
 #define NGS_HD __host__ __device__ __forceinline__
+#define NGS_HDM __host__ __device__ __forceinline__      /* member functions */
 #else
 #define NGS_HD static inline
+#define NGS_HDM inline
 #endif
 
 #define NGS_POS_MASK   0x0FFFFFFFu        /* 4 x 7 bit key of the reference */
@@ -223,6 +225,205 @@ NGS_HD uint32_t ngs_put_f2(Ptr dst, uint64_t hundredths)
 	dst[n] = '.'; dst[n + 1] = (char)('0' + f / 10); dst[n + 2] = (char)('0' + f % 10);
 	return n + 3;
 }
+
+/* ---- register line assembly (fast bedGraph path of K5, k_format_bed) ------------------------------
+ * A line is appended to a byte stream in shared memory as a few "pieces" of at most 12 bytes held in
+ * registers.  The writer keeps the stream's current partial word in a register (`carry`, `k` valid low
+ * bytes) and only ever stores whole 32-bit words, so a line costs about ten word stores instead of one
+ * store (plus extraction and a predicate) per byte.  The first word of a thread's range may be shared
+ * with the previous thread: the owner of the range's HEAD stores it (low bytes zero), the previous
+ * thread ORs its tail in after a barrier (ngs_lw::carry / k after the last piece). */
+NGS_HD uint32_t ngs_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+	return __byte_perm(a, b, sel);
+#else
+	const uint64_t pair = (uint64_t)a | ((uint64_t)b << 32);
+	uint32_t r = 0;
+	for (int j = 0; j < 4; ++j) r |= (uint32_t)((pair >> (8 * ((sel >> (4 * j)) & 7))) & 0xff) << (8 * j);
+	return r;
+#endif
+}
+/* index of the lowest non-zero byte of x (x != 0) */
+NGS_HD uint32_t ngs_low_byte_index(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)(__ffs((int)x) - 1) >> 3;
+#else
+	return (uint32_t)__builtin_ctz(x) >> 3;
+#endif
+}
+/* four decimal digits of y (< 10^4), one per byte, most significant in the LOWEST byte (no '0' offset):
+ * the 32-bit-lane form of ngs_digits8 (64-bit SWAR costs three to four IMADs per multiply on the GPU) */
+NGS_HD uint32_t ngs_digits4_raw(uint32_t y)
+{
+	const uint32_t q = (y * 5243u) >> 19;                        /* y / 100 (exact below 10^4) */
+	const uint32_t z = q + ((y - q * 100u) << 16);               /* two 2-digit numbers in 16-bit lanes */
+	const uint32_t t = ((z * 103u) >> 10) & 0x000F000Fu;         /* / 10 per lane (exact below 100) */
+	return t + ((z - t * 10u) << 8);
+}
+/* decimal ASCII of v.  n = tn & 0xff digits.  n <= 8: digits left-aligned in (lo, hi) -- first significant digit in
+ * byte 0 of lo, bytes beyond n are zero.  n == 9: the eight low digits in (lo, hi), the leading digit (ASCII) in
+ * tn >> 8.  n == 10 is only a flag (v >= 10^9): the caller takes its slow path. */
+typedef struct { uint32_t lo, hi, tn; } ngs_num;
+NGS_HD void ngs_num_conv(uint32_t v, ngs_num &o)
+{
+	const uint32_t top = v / 100000000u;
+	v -= top * 100000000u;
+	const uint32_t h4 = v / 10000u, l4 = v - h4 * 10000u;
+	const uint32_t a = ngs_digits4_raw(h4), b = ngs_digits4_raw(l4);
+	if (top) {
+		o.lo = a + 0x30303030u; o.hi = b + 0x30303030u; o.tn = ((top + 0x30u) << 8) | (top < 10u ? 9u : 10u);
+		return;
+	}
+	const uint32_t lz = a ? ngs_low_byte_index(a) : (b ? 4u + ngs_low_byte_index(b) : 7u);
+	const uint64_t d = (((uint64_t)(b + 0x30303030u) << 32) | (uint64_t)(a + 0x30303030u)) >> (8u * lz);
+	o.lo = (uint32_t)d; o.hi = (uint32_t)(d >> 32); o.tn = 8u - lz;
+}
+/* the up to ten bytes "digits, separator" of x as a 12-byte piece */
+NGS_HD void ngs_num_piece(const ngs_num &x, uint32_t sep, uint32_t &q0, uint32_t &q1, uint32_t &q2, uint32_t &cnt)
+{
+	const uint32_t n = x.tn & 0xffu;
+	if (n <= 8u) {
+		const uint32_t sv = sep << ((n & 3u) * 8u);
+		q0 = x.lo; q1 = x.hi; q2 = 0;
+		if (n < 4u) q0 |= sv; else if (n < 8u) q1 |= sv; else q2 = sep;
+		cnt = n + 1u;
+	} else {
+		q0 = (x.tn >> 8) | (x.lo << 8); q1 = (x.lo >> 24) | (x.hi << 8); q2 = (x.hi >> 24) | (sep << 8);
+		cnt = 10u;
+	}
+}
+/* Positions are written as H = p / 10^4 (thread-cached: the records of a thread lie within a few bases of each
+ * other, so H changes about once in a thousand threads) followed by the four digits of p % 10^4.  With the cache
+ * valid a position costs one 4-digit conversion and three byte permutes whose selectors only depend on the
+ * number of digits of H.  p < 10^4 (H == 0) and depths go through ngs_small_piece. */
+typedef struct {
+	uint32_t H, hlo, sh, nH, selA, selB, selC;      /* sh = '\t' | fifth digit of H << 8 */
+	uint32_t nh0, nh1, nh2, nh3;                     /* "name\tHHHHH": the constant head of every line of the thread */
+	uint32_t th0, th1;                               /* "\tHHHHH": what separates the low digits of start and end */
+} ngs_hcache;
+NGS_HD uint32_t ngs_ascii4(uint32_t y) { return ngs_digits4_raw(y) + 0x30303030u; }
+NGS_HD void ngs_hcache_fill(ngs_hcache &c, uint32_t H, uint32_t name_lo, uint32_t name_hi, uint32_t nl)   /* 1 <= H < 10^5, 1 <= nl <= 8 */
+{
+	/* byte selectors of the 12-byte piece "H digits, 4 digits, tab": sources (hlo, L4) for bytes 0-3 and (L4, sh) for
+	 * bytes 4-11; in sh byte 0 is the tab, byte 1 the fifth digit of H, byte 2 zero */
+	const uint32_t top = H / 10000u, raw = ngs_digits4_raw(H - top * 10000u), a = raw + 0x30303030u;
+	uint32_t hhi = 0, n;
+	if (top) { c.hlo = (top + 0x30u) | (a << 8); hhi = a >> 24; n = 5u; }
+	else { const uint32_t lz = ngs_low_byte_index(raw); c.hlo = a >> (8u * lz); n = 4u - lz; }
+	c.sh = 0x09u | (hhi << 8);
+	/* selectors for n = 1..5 digits of H, 16 bits each, packed into constants (a local table would live on the stack):
+	 * A: 6540 5410 4210 3210 3210   B: 6643 6432 4321 3210 2105   C: 6666 6666 6666 6664 6643 */
+	const uint32_t sh16 = 16u * (n - 1u);
+	c.H = H; c.nH = n;
+	c.selA = n < 4u ? (uint32_t)(0x421054106540ull >> sh16) & 0xffffu : 0x3210u;
+	c.selB = n < 5u ? (uint32_t)(0x3210432164326643ull >> sh16) & 0xffffu : 0x2105u;
+	c.selC = n < 4u ? 0x6666u : (n == 4u ? 0x6664u : 0x6643u);
+	const uint64_t hs = (uint64_t)c.hlo | ((uint64_t)hhi << 32), nm = (uint64_t)name_lo | ((uint64_t)name_hi << 32);
+	const uint64_t lo = nm | (nl < 8u ? hs << (8u * nl) : 0ull), hi = hs >> (64u - 8u * nl);
+	const uint64_t th = 0x09ull | (hs << 8);
+	c.nh0 = (uint32_t)lo; c.nh1 = (uint32_t)(lo >> 32); c.nh2 = (uint32_t)hi; c.nh3 = (uint32_t)(hi >> 32);
+	c.th0 = (uint32_t)th; c.th1 = (uint32_t)(th >> 32);
+}
+/* v < 10^4 followed by sep, left-aligned in (q0, q1); cnt = digits + 1 */
+NGS_HD void ngs_small_piece(uint32_t v, uint32_t sep, uint32_t &q0, uint32_t &q1, uint32_t &cnt)
+{
+	const uint32_t raw = ngs_digits4_raw(v), lz = raw ? ngs_low_byte_index(raw) : 3u;
+	const uint32_t a = (raw + 0x30303030u) >> (8u * lz);
+	q0 = lz ? (a | (sep << (32u - 8u * lz))) : a;
+	q1 = lz ? 0u : sep;
+	cnt = 5u - lz;
+}
+/* p = H * 10^4 + L with the cache holding H (H >= 1), L4 = ngs_ascii4(L) */
+NGS_HD void ngs_pos_piece(const ngs_hcache &c, uint32_t L4, uint32_t &q0, uint32_t &q1, uint32_t &q2, uint32_t &cnt)
+{
+	q0 = ngs_prmt(c.hlo, L4, c.selA); q1 = ngs_prmt(L4, c.sh, c.selB); q2 = ngs_prmt(L4, c.sh, c.selC);
+	cnt = c.nH + 5u;
+}
+
+/* stream writer: W is a pointer-like type to 32-bit words (shared memory on the device) */
+template <class W>
+struct ngs_lw {
+	W w;                 /* word the next byte goes to */
+	uint32_t carry, k;   /* the k (0..3) low bytes of that word already produced */
+	NGS_HDM void begin(W base_words, uint32_t byte_off) { w = base_words + (byte_off >> 2); k = byte_off & 3u; carry = 0; }
+	NGS_HDM void put8(uint32_t q0, uint32_t q1, uint32_t cnt)        /* cnt in 1..8, bytes beyond cnt zero */
+	{
+		const uint32_t sel = 0x7654u - 0x1111u * k;
+		const uint32_t x0 = ngs_prmt(0u, q0, sel) | carry, x1 = ngs_prmt(q0, q1, sel), x2 = ngs_prmt(q1, 0u, sel);
+		const uint32_t tot = k + cnt, nw = tot >> 2;
+		if (nw > 0u) w[0] = x0;
+		if (nw > 1u) w[1] = x1;
+		carry = nw == 0u ? x0 : (nw == 1u ? x1 : x2);
+		w += nw; k = tot & 3u;
+	}
+	NGS_HDM void put12(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t cnt)   /* cnt in 1..12 */
+	{
+		const uint32_t sel = 0x7654u - 0x1111u * k;
+		const uint32_t x0 = ngs_prmt(0u, q0, sel) | carry, x1 = ngs_prmt(q0, q1, sel), x2 = ngs_prmt(q1, q2, sel), x3 = ngs_prmt(q2, 0u, sel);
+		const uint32_t tot = k + cnt, nw = tot >> 2;
+		if (nw > 0u) w[0] = x0;
+		if (nw > 1u) w[1] = x1;
+		if (nw > 2u) w[2] = x2;
+		carry = nw < 2u ? (nw == 0u ? x0 : x1) : (nw == 2u ? x2 : x3);
+		w += nw; k = tot & 3u;
+	}
+	NGS_HDM void put16(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, uint32_t cnt)   /* cnt in 1..16 */
+	{
+		const uint32_t sel = 0x7654u - 0x1111u * k;
+		const uint32_t x0 = ngs_prmt(0u, q0, sel) | carry, x1 = ngs_prmt(q0, q1, sel), x2 = ngs_prmt(q1, q2, sel), x3 = ngs_prmt(q2, q3, sel), x4 = ngs_prmt(q3, 0u, sel);
+		const uint32_t tot = k + cnt, nw = tot >> 2;
+		if (nw > 0u) w[0] = x0;
+		if (nw > 1u) w[1] = x1;
+		if (nw > 2u) w[2] = x2;
+		if (nw > 3u) w[3] = x3;
+		carry = nw < 2u ? (nw == 0u ? x0 : x1) : (nw == 2u ? x2 : (nw == 3u ? x3 : x4));
+		w += nw; k = tot & 3u;
+	}
+	/* One bedGraph line.  L4s / L4e = ngs_ascii4(s % 10^4), ngs_ascii4(e % 10^4); d >= 1.  When start and end share
+	 * the cached H and the depth has at most four digits the line is three pieces: the thread-constant head
+	 * "name\tH", "ssss\tH" and "eeee\tdepth\n"; everything else goes piece by piece. */
+	NGS_HDM void bed_line_cached(ngs_hcache &c, uint32_t name_lo, uint32_t name_hi, uint32_t nl,
+	                             uint32_t s, uint32_t L4s, uint32_t e, uint32_t L4e, uint32_t d)
+	{
+		const uint32_t Hs = s / 10000u, He = e / 10000u;
+		if (Hs != 0u && Hs == He && d < 10000u) {
+			if (Hs != c.H) ngs_hcache_fill(c, Hs, name_lo, name_hi, nl);
+			uint32_t dq0, dq1, dc;
+			ngs_small_piece(d, 0x0Au, dq0, dq1, dc);
+			put16(c.nh0, c.nh1, c.nh2, c.nh3, nl + c.nH);
+			put12(L4s, c.th0, c.th1, 5u + c.nH);
+			put12(L4e, 0x09u | (dq0 << 8), (dq0 >> 24) | (dq1 << 8), 5u + dc);
+			return;
+		}
+		put8(name_lo, name_hi, nl);
+		put_pos(c, s, name_lo, name_hi, nl);
+		put_pos(c, e, name_lo, name_hi, nl);
+		if (d < 10000u) { uint32_t q0, q1, cnt; ngs_small_piece(d, 0x0Au, q0, q1, cnt); put8(q0, q1, cnt); }
+		else { ngs_num x; uint32_t q0, q1, q2, cnt; ngs_num_conv(d, x); ngs_num_piece(x, 0x0Au, q0, q1, q2, cnt); put12(q0, q1, q2, cnt); }
+	}
+	/* position p followed by a tab */
+	NGS_HDM void put_pos(ngs_hcache &c, uint32_t p, uint32_t name_lo, uint32_t name_hi, uint32_t nl)
+	{
+		const uint32_t H = p / 10000u, Lo = p - H * 10000u;
+		uint32_t q0, q1, q2 = 0, cnt;
+		if (H) {
+			if (H != c.H) ngs_hcache_fill(c, H, name_lo, name_hi, nl);
+			ngs_pos_piece(c, ngs_ascii4(Lo), q0, q1, q2, cnt);
+		} else ngs_small_piece(Lo, 0x09u, q0, q1, cnt);
+		put12(q0, q1, q2, cnt);
+	}
+	/* "name\tstart\tend\tdepth\n": name8 = the first eight bytes of "name\t" (nl <= 8 of them valid, rest zero) */
+	NGS_HDM void bed_line(uint32_t name_lo, uint32_t name_hi, uint32_t nl, const ngs_num &s, const ngs_num &e, const ngs_num &d)
+	{
+		uint32_t q0, q1, q2, cnt;
+		put8(name_lo, name_hi, nl);
+		ngs_num_piece(s, 0x09u, q0, q1, q2, cnt); put12(q0, q1, q2, cnt);
+		ngs_num_piece(e, 0x09u, q0, q1, q2, cnt); put12(q0, q1, q2, cnt);
+		ngs_num_piece(d, 0x0Au, q0, q1, q2, cnt); put12(q0, q1, q2, cnt);
+	}
+};
 
 /* ---- the record walk -----------------------------------------------------------------------------
  * Policy `Mem` supplies the loads:  void hdr_lite(int64 o, ngs_hdr&)  first 24 bytes of the record,

@@ -1319,6 +1319,7 @@ struct FmtArgs {
 	char *out; unsigned long long out_cap;
 	ngs_dev_state *st;
 	uint32_t stage_bytes;              /* dynamic shared memory for line staging */
+	int debug;                         /* bit 0: skip the look-back wait (timing experiments only, wrong output) */
 };
 
 template <class Producer, int IPT>
@@ -1402,6 +1403,222 @@ __global__ void __launch_bounds__(NGS_FMT_THREADS, NGS_FMT_MINB) k_format_lines(
 		#pragma unroll
 		for (int i = 0; i < IPT; ++i) { if (len[i]) P.write(A.out + goff + off, it[i], cache); off += len[i]; }
 	}
+}
+
+/* K5, bedGraph fast path.  Same tiling, byte-offset look-back and aligned copy-out as k_format_lines, but the
+ * lines are assembled in registers and leave the thread as whole 32-bit words (ngs_lw in ngscov_hd.h):
+ *   - the IPT consecutive boundary records of a thread are loaded with 128-bit loads; record r starts where
+ *     record r-1 ends, so each position is converted to ASCII once and used for both lines;
+ *   - the digit count falls out of the conversion (lowest non-zero byte), no separate compare tree;
+ *   - the contig is found once per warp (a tile inside one contig is the only case on this path).
+ * Tiles that straddle two contigs, hold the halo-dropped / halo-extended run, have a "name\t" longer than
+ * eight bytes or a depth outside [0, 10^9) take the generic BedProducer code (bed_slow_*), which produces the
+ * same lengths by construction. */
+__device__ __noinline__ uint4 bed_slow_len4(const BedProducer &P, unsigned long long r0, unsigned long long n_items)
+{
+	BedProducer::Cache c; P.init(c);
+	BedProducer::Item it;
+	uint4 l;
+	l.x = (r0 + 0 < n_items) ? P.length(r0 + 0, it, c) : 0;
+	l.y = (r0 + 1 < n_items) ? P.length(r0 + 1, it, c) : 0;
+	l.z = (r0 + 2 < n_items) ? P.length(r0 + 2, it, c) : 0;
+	l.w = (r0 + 3 < n_items) ? P.length(r0 + 3, it, c) : 0;
+	return l;
+}
+__device__ __noinline__ void bed_slow_write(const BedProducer &P, unsigned long long r0, unsigned long long n_items, int ipt, char *dst)
+{
+	BedProducer::Cache c; P.init(c);
+	for (int i = 0; i < ipt; ++i) {
+		BedProducer::Item it;
+		const uint32_t l = (r0 + i < n_items) ? P.length(r0 + i, it, c) : 0;
+		if (l) P.write(dst, it, c);
+		dst += l;
+	}
+}
+
+template <int IPT, int MINB>
+__global__ void __launch_bounds__(NGS_FMT_THREADS, MINB) k_format_bed(const __grid_constant__ FmtArgs A, const __grid_constant__ BedProducer P)
+{
+	extern __shared__ __align__(16) char s_stage[];
+	__shared__ unsigned int s_w[8], s_li[8];
+	__shared__ unsigned long long s_lb[8];
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const unsigned long long tile = blockIdx.x;
+	if (tile >= A.n_tiles) return;
+	const unsigned long long tr0 = tile * (unsigned long long)(NGS_FMT_THREADS * IPT), r0 = tr0 + (unsigned long long)t * IPT;
+	uint32_t S[IPT], E[IPT]; int D[IPT];
+	if (r0 + IPT <= A.n_items) {
+		#pragma unroll
+		for (int j = 0; j < IPT / 4; ++j) {
+			const uint4 a = reinterpret_cast<const uint4 *>(P.run_start + r0)[j], b = reinterpret_cast<const uint4 *>(P.run_end + r0)[j];
+			const int4 c = reinterpret_cast<const int4 *>(P.run_depth + r0)[j];
+			S[4 * j] = a.x; S[4 * j + 1] = a.y; S[4 * j + 2] = a.z; S[4 * j + 3] = a.w;
+			E[4 * j] = b.x; E[4 * j + 1] = b.y; E[4 * j + 2] = b.z; E[4 * j + 3] = b.w;
+			D[4 * j] = c.x; D[4 * j + 1] = c.y; D[4 * j + 2] = c.z; D[4 * j + 3] = c.w;
+		}
+	} else {
+		#pragma unroll
+		for (int i = 0; i < IPT; ++i) {
+			const bool in = r0 + i < A.n_items;
+			S[i] = in ? P.run_start[r0 + i] : 0; E[i] = in ? P.run_end[r0 + i] : 0; D[i] = in ? P.run_depth[r0 + i] : 0;
+		}
+	}
+	/* contig of the tile: last segment whose first record is <= the tile's first (rec_base is non-decreasing) */
+	uint32_t sgi;
+	if (P.n_seg <= 32u) {
+		const bool le = (uint32_t)lane < P.n_seg && P.rec_base[lane] <= tr0;          /* rec_base[0] = 0: lane 0 always votes */
+		sgi = 31u - (uint32_t)__clz((int)__ballot_sync(0xffffffffu, le));
+	} else {
+		sgi = 0;
+		for (uint32_t i = lane; i < P.n_seg; i += 32) if (P.rec_base[i] <= tr0) sgi = i;
+		sgi = __reduce_max_sync(0xffffffffu, sgi);
+	}
+	unsigned long long tr1 = tr0 + (unsigned long long)(NGS_FMT_THREADS * IPT);
+	if (tr1 > A.n_items) tr1 = A.n_items;
+	const uint32_t ctg = P.seg[sgi].contig;
+	const uint32_t nl = P.nt.name_off[ctg + 1] - P.nt.name_off[ctg];
+	const unsigned long long name8 = P.nt.name8[ctg];
+	const bool slow_u = tr1 > P.rec_base[sgi + 1] || nl > 8u || (P.drop_idx >= tr0 && P.drop_idx < tr1) || (P.mod_idx >= tr0 && P.mod_idx < tr1);
+
+	/* ---- lengths.  Positions: p = H * 10^4 + L, H cached per thread (ngs_hcache), L converted once per distinct
+	 * position (record i starts where record i-1 ends).  Depths below 10^4 are converted here and kept as a
+	 * ready piece; larger ones are converted again when written. */
+	ngs_hcache hc; hc.H = 0xffffffffu; hc.hlo = hc.sh = hc.nH = hc.selA = hc.selB = hc.selC = 0;
+	hc.nh0 = hc.nh1 = hc.nh2 = hc.nh3 = hc.th0 = hc.th1 = 0;
+	const uint32_t n_lo = (uint32_t)name8, n_hi = (uint32_t)(name8 >> 32);
+	uint32_t L4e[IPT], L4s0 = 0;
+	uint32_t len[IPT], tlen = 0;
+	int bad = 0;
+	auto pos_digits = [&](uint32_t p, uint32_t &L4) -> uint32_t {
+		const uint32_t H = p / 10000u, raw = ngs_digits4_raw(p - H * 10000u);
+		L4 = raw + 0x30303030u;
+		if (H == 0) return raw ? 4u - ngs_low_byte_index(raw) : 1u;
+		if (H >= 100000u) { bad = 1; return 10u; }
+		if (H != hc.H) ngs_hcache_fill(hc, H, n_lo, n_hi, nl);
+		return hc.nH + 4u;
+	};
+	if (!slow_u) {
+		bool any = false;
+		#pragma unroll
+		for (int i = 0; i < IPT; ++i) { any |= D[i] != 0; len[i] = 0; L4e[i] = 0; }
+		if (any) {
+			uint32_t n_prev = pos_digits(S[0], L4s0);
+			#pragma unroll
+			for (int i = 0; i < IPT; ++i) {
+				uint32_t ns = n_prev;
+				if (i > 0 && S[i] != E[i - 1] && D[i] != 0) { uint32_t tmp; ns = pos_digits(S[i], tmp); }
+				const uint32_t ne = pos_digits(E[i], L4e[i]);
+				n_prev = ne;
+				if (D[i] != 0) {
+					uint32_t nd;
+					if ((uint32_t)D[i] < 10000u) nd = 1u + ((uint32_t)D[i] >= 10u) + ((uint32_t)D[i] >= 100u) + ((uint32_t)D[i] >= 1000u);
+					else if ((uint32_t)D[i] < 1000000000u) nd = ngs_ndigits((uint32_t)D[i]);
+					else { bad = 1; nd = ngs_len_i32(D[i]); }
+					len[i] = nl + ns + ne + nd + 3u;
+				}
+				tlen += len[i];
+			}
+		}
+	} else {
+		#pragma unroll
+		for (int j = 0; j < IPT / 4; ++j) {
+			const uint4 l = bed_slow_len4(P, r0 + 4 * j, A.n_items);
+			len[4 * j] = l.x; len[4 * j + 1] = l.y; len[4 * j + 2] = l.z; len[4 * j + 3] = l.w;
+			tlen += l.x + l.y + l.z + l.w;
+		}
+	}
+
+	/* block exclusive scan of tlen; the barrier also tells every thread whether the tile must go the slow way */
+	uint32_t inc = tlen;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+	if (lane == 31) s_w[warp] = inc;
+	const bool slow = __syncthreads_or(bad) != 0 || slow_u;
+	uint32_t wpre = 0, total = 0;
+	#pragma unroll
+	for (int w = 0; w < 8; ++w) { if (w < warp) wpre += s_w[w]; total += s_w[w]; }
+	const uint32_t off = wpre + inc - tlen;
+	/* look-back over tile byte totals, block-wide (thread i inspects tile-1-i).  A variant with the look-back done by
+	 * warp 0 alone while warps 1..7 assemble their lines (lines laid out from byte 0, copy-out realigning them with
+	 * byte permutes) was measured slower: 2.18 vs 1.85 ms at 62 M reads -- the look-back stays on warp 0's critical
+	 * path and the other warps wait for it at the barrier instead (44 % of the stall samples). */
+	unsigned long long run = 0;
+	if (t == 0) st_relaxed_u64(&A.status[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | total);
+	if (tile > 0 && !(A.debug & 1)) {
+		long long base = (long long)tile - 1;
+		for (;;) {
+			const long long idx = base - t;
+			unsigned long long a = NGS_ST_INC << 62;
+			if (idx >= 0) { do { a = ld_relaxed_u64(&A.status[idx]); } while ((a >> 62) == NGS_ST_EMPTY); }
+			const unsigned int im = __ballot_sync(0xffffffffu, (a >> 62) == NGS_ST_INC);
+			if (lane == 0) s_li[warp] = im ? (unsigned)(warp * 32 + __ffs(im) - 1) : 0xffffffffu;
+			__syncthreads();
+			unsigned int first_inc = 0xffffffffu;
+			#pragma unroll
+			for (int w = 0; w < 8; ++w) first_inc = s_li[w] < first_inc ? s_li[w] : first_inc;
+			unsigned long long v = (unsigned)t <= first_inc ? (a & 0x3FFFFFFFFFFFFFFFull) : 0;
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+			if (lane == 0) s_lb[warp] = v;
+			__syncthreads();
+			#pragma unroll
+			for (int w = 0; w < 8; ++w) run += s_lb[w];
+			if (first_inc != 0xffffffffu) break;
+			base -= NGS_FMT_THREADS;
+			__syncthreads();
+		}
+		if (t == 0) st_relaxed_u64(&A.status[tile], (NGS_ST_INC << 62) | (run + total));
+	}
+	if (A.debug & 1) run = tile * 24000ull;              /* timing experiment only: no wait, wrong offsets */
+	if (t == 0 && tile == A.n_tiles - 1) A.st->fmt_bytes = run + total;
+	const unsigned long long goff = run;
+	if (total == 0 || goff + total > A.out_cap) return;
+	const uint32_t mis = (uint32_t)((uintptr_t)(A.out + goff) & 15);
+	if (total + mis + 4u > A.stage_bytes) {           /* lines too long for the staging area: straight to global */
+		bed_slow_write(P, r0, A.n_items, IPT, A.out + goff + off);
+		return;
+	}
+	uint32_t *sw = reinterpret_cast<uint32_t *>(s_stage);
+	if (slow) bed_slow_write(P, r0, A.n_items, IPT, s_stage + mis + off);
+	else {
+		/* the tile's last, partial word is only ever OR-ed into: clear it (tile 0 skipped the look-back barriers,
+		 * the barrier below orders this store before the ORs in every case) */
+		if (t == 0) sw[(mis + total) >> 2] = 0;
+		ngs_lw<uint32_t *> L;
+		L.begin(sw, mis + off);
+		if (tlen) {
+			#pragma unroll
+			for (int i = 0; i < IPT; ++i) {
+				if (len[i]) {
+					if (i == 0) L.bed_line_cached(hc, n_lo, n_hi, nl, S[0], L4s0, E[0], L4e[0], (uint32_t)D[0]);
+					else if (S[i] == E[i - 1]) L.bed_line_cached(hc, n_lo, n_hi, nl, E[i - 1], L4e[i - 1], E[i], L4e[i], (uint32_t)D[i]);
+					else L.bed_line_cached(hc, n_lo, n_hi, nl, S[i], ngs_ascii4(S[i] % 10000u), E[i], L4e[i], (uint32_t)D[i]);
+				}
+			}
+		}
+		__syncthreads();
+		if (tlen && L.k) atomicOr(L.w, L.carry);      /* tail bytes into the word whose owner stored its head part above */
+	}
+	__syncthreads();
+	char *g = A.out + goff - mis;                       /* 16-byte aligned */
+	const uint32_t end = mis + total;
+	uint32_t a0 = (mis + 15u) & ~15u;                   /* head bytes [mis,a0), 128-bit body [a0,a1), tail [a1,end) */
+	if (a0 > end) a0 = end;
+	uint32_t a1 = end & ~15u;
+	if (a1 < a0) a1 = a0;
+	for (uint32_t i = mis + t; i < a0; i += NGS_FMT_THREADS) g[i] = s_stage[i];
+	{
+		const int4 *src = reinterpret_cast<const int4 *>(s_stage + a0) + t;
+		int4 *dst = reinterpret_cast<int4 *>(g + a0) + t;
+		const uint32_t nv = (a1 - a0) >> 4;                 /* 128-bit words of the body */
+		uint32_t i = t;
+		for (; i + 3 * NGS_FMT_THREADS < nv; i += 4 * NGS_FMT_THREADS, src += 4 * NGS_FMT_THREADS, dst += 4 * NGS_FMT_THREADS) {
+			const int4 v0 = src[0], v1 = src[NGS_FMT_THREADS], v2 = src[2 * NGS_FMT_THREADS], v3 = src[3 * NGS_FMT_THREADS];
+			dst[0] = v0; dst[NGS_FMT_THREADS] = v1; dst[2 * NGS_FMT_THREADS] = v2; dst[3 * NGS_FMT_THREADS] = v3;
+		}
+		for (; i < nv; i += NGS_FMT_THREADS, src += NGS_FMT_THREADS, dst += NGS_FMT_THREADS) *dst = *src;
+	}
+	for (uint32_t i = a1 + t; i < end; i += NGS_FMT_THREADS) g[i] = s_stage[i];
 }
 
 /* reset of look-back status words and tickets before a scan / format launch */

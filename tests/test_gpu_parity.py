@@ -172,3 +172,24 @@ def test_generator_configs_larger(oracle, config, scale, mode, window):
     got = run_engine(g.names, g.lens, recs, mode, window, staging_bytes=64 << 20)
     check(got, exp, mode, f"config{config} scale={scale}")
     assert got["stats"]["records"] == g.n_reads
+
+
+@pytest.mark.parametrize("fmt", ["fast", "generic"])
+def test_nine_digit_positions_and_name_lengths(oracle, monkeypatch, fmt):
+    """bedGraph formatting across the 8 -> 9 digit boundary of positions, with "name\\t" of exactly eight bytes (the
+    register-assembled fast path), nine bytes and longer (the generic producer path), for both K5 variants"""
+    if fmt == "generic":
+        monkeypatch.setenv("NGSCOV_FMT", "generic")
+    names = [b"chr1", b"sevench", b"eightchr", b"a_rather_long_contig_name_42"]
+    lens = [100001000, 5000, 5000, 3000]
+    reads = []
+    for p in list(range(99999700, 100000400, 7)) + [0, 1, 9, 10, 99, 100, 999, 1000, 99999, 100000, 9999999, 10000000]:
+        reads.append((0, p, 0, "150M"))
+    reads.sort(key=lambda r: r[1])
+    for c in (1, 2, 3):
+        reads += [(c, p, 16 if p % 3 else 0, "37M5D20M") for p in range(0, 2500, 11)]
+    recs = bamutil.records(reads, seq=False)
+    exp = oracle.run(recs, names, lens, 0, 20000)
+    got = run_engine(names, lens, recs, 0, 20000)
+    check(got, exp, 0, f"nine digits fmt={fmt}")
+    assert b"\t100000" in got["bedgraph"] and b"\t99999" in got["bedgraph"]

@@ -62,6 +62,12 @@ def test_kernel_logic_model_matches_oracle(hd_check, tmp_path, case, mode, windo
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_register_line_assembly_known_answers(hd_check):
+    """ngs_lw / ngs_num_conv (the K5 fast path) against snprintf: all digit counts, name lengths, alignments"""
+    r = subprocess.run([hd_check, "--selftest-lines"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_python_cli_atoi_and_usage(capsys):
     from highperformancengs_b200 import cli
     assert cli._atoi("20000") == 20000 and cli._atoi(" 12abc") == 12 and cli._atoi("x") == 0 and cli._atoi("-5") == -5
