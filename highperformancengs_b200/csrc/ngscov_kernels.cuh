@@ -1538,12 +1538,41 @@ __global__ void __launch_bounds__(NGS_FMT_THREADS, MINB) k_format_bed(const __gr
 	#pragma unroll
 	for (int w = 0; w < 8; ++w) { if (w < warp) wpre += s_w[w]; total += s_w[w]; }
 	const uint32_t off = wpre + inc - tlen;
-	/* look-back over tile byte totals, block-wide (thread i inspects tile-1-i).  A variant with the look-back done by
-	 * warp 0 alone while warps 1..7 assemble their lines (lines laid out from byte 0, copy-out realigning them with
-	 * byte permutes) was measured slower: 2.18 vs 1.85 ms at 62 M reads -- the look-back stays on warp 0's critical
-	 * path and the other warps wait for it at the barrier instead (44 % of the stall samples). */
+	/* ---- order of the remaining work: publish the tile's byte count, ASSEMBLE the lines, and only then look back.
+	 * Looking back right after the lengths (as k_format_lines does) makes every tile wait for neighbours that were
+	 * dispatched a moment earlier and are still computing their own lengths: 37 % of the stall samples, and 1.86 ms
+	 * instead of 1.19 ms with the wait removed (62 M reads).  After the assembly the predecessors' counts exist and a
+	 * tile dispatched a microsecond earlier already holds an inclusive prefix, so one round almost always suffices.
+	 * The price: the tile's global offset -- its 16-byte misalignment -- is not known while the lines are laid out,
+	 * so they start at byte 0 of the staging area and the copy-out realigns them with byte permutes.
+	 * (Also measured: look-back by warp 0 alone while warps 1..7 assemble -- 2.18 ms, the look-back stays on warp 0's
+	 * critical path and the others wait for it at the barrier.) */
+	uint32_t *sw = reinterpret_cast<uint32_t *>(s_stage);
+	const bool staged = total + 32u <= A.stage_bytes;
+	if (t == 0) {
+		st_relaxed_u64(&A.status[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | total);
+		if (staged && !slow) sw[total >> 2] = 0;         /* the tile's last, partial word is only ever OR-ed into */
+	}
+	ngs_lw<uint32_t *> L;
+	L.begin(sw, off);
+	if (staged && total) {
+		if (slow) bed_slow_write(P, r0, A.n_items, IPT, s_stage + off);
+		else if (tlen) {
+			#pragma unroll
+			for (int i = 0; i < IPT; ++i) {
+				if (len[i]) {
+					if (i == 0) L.bed_line_cached(hc, n_lo, n_hi, nl, S[0], L4s0, E[0], L4e[0], (uint32_t)D[0]);
+					else if (S[i] == E[i - 1]) L.bed_line_cached(hc, n_lo, n_hi, nl, E[i - 1], L4e[i - 1], E[i], L4e[i], (uint32_t)D[i]);
+					else L.bed_line_cached(hc, n_lo, n_hi, nl, S[i], ngs_ascii4(S[i] % 10000u), E[i], L4e[i], (uint32_t)D[i]);
+				}
+			}
+		}
+	}
+	__syncthreads();                                        /* every head word stored */
+	if (staged && !slow && tlen && L.k) atomicOr(L.w, L.carry);   /* tail bytes into the word whose owner stored its head part */
+	/* look-back over tile byte totals, block-wide (thread i inspects tile-1-i); its barriers also order the ORs
+	 * above before the copy-out (tile 0 gets an explicit one) */
 	unsigned long long run = 0;
-	if (t == 0) st_relaxed_u64(&A.status[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | total);
 	if (tile > 0 && !(A.debug & 1)) {
 		long long base = (long long)tile - 1;
 		for (;;) {
@@ -1568,57 +1597,44 @@ __global__ void __launch_bounds__(NGS_FMT_THREADS, MINB) k_format_bed(const __gr
 			__syncthreads();
 		}
 		if (t == 0) st_relaxed_u64(&A.status[tile], (NGS_ST_INC << 62) | (run + total));
-	}
+	} else __syncthreads();
 	if (A.debug & 1) run = tile * 24000ull;              /* timing experiment only: no wait, wrong offsets */
 	if (t == 0 && tile == A.n_tiles - 1) A.st->fmt_bytes = run + total;
 	const unsigned long long goff = run;
 	if (total == 0 || goff + total > A.out_cap) return;
-	const uint32_t mis = (uint32_t)((uintptr_t)(A.out + goff) & 15);
-	if (total + mis + 4u > A.stage_bytes) {           /* lines too long for the staging area: straight to global */
+	if (!staged) {                                      /* lines too long for the staging area: straight to global */
 		bed_slow_write(P, r0, A.n_items, IPT, A.out + goff + off);
 		return;
 	}
-	uint32_t *sw = reinterpret_cast<uint32_t *>(s_stage);
-	if (slow) bed_slow_write(P, r0, A.n_items, IPT, s_stage + mis + off);
-	else {
-		/* the tile's last, partial word is only ever OR-ed into: clear it (tile 0 skipped the look-back barriers,
-		 * the barrier below orders this store before the ORs in every case) */
-		if (t == 0) sw[(mis + total) >> 2] = 0;
-		ngs_lw<uint32_t *> L;
-		L.begin(sw, mis + off);
-		if (tlen) {
-			#pragma unroll
-			for (int i = 0; i < IPT; ++i) {
-				if (len[i]) {
-					if (i == 0) L.bed_line_cached(hc, n_lo, n_hi, nl, S[0], L4s0, E[0], L4e[0], (uint32_t)D[0]);
-					else if (S[i] == E[i - 1]) L.bed_line_cached(hc, n_lo, n_hi, nl, E[i - 1], L4e[i - 1], E[i], L4e[i], (uint32_t)D[i]);
-					else L.bed_line_cached(hc, n_lo, n_hi, nl, S[i], ngs_ascii4(S[i] % 10000u), E[i], L4e[i], (uint32_t)D[i]);
-				}
-			}
+	/* ---- copy-out: head bytes up to the first 16-byte boundary of the output, then aligned 128-bit stores whose
+	 * source starts (16 - mis) bytes into the staging area, then the tail bytes */
+	char *g = A.out + goff;
+	const uint32_t mis = (uint32_t)((uintptr_t)g & 15);
+	uint32_t hb = (16u - mis) & 15u;
+	if (hb > total) hb = total;
+	if ((uint32_t)t < hb) g[t] = s_stage[t];
+	const uint32_t nv = (total - hb) >> 4;
+	int4 *dst = reinterpret_cast<int4 *>(g + hb);
+	const int4 *src = reinterpret_cast<const int4 *>(s_stage);
+	if (hb == 0) {
+		for (uint32_t c = t; c < nv; c += NGS_FMT_THREADS) dst[c] = src[c];
+	} else {
+		const uint32_t wsh = hb >> 2, sel = 0x3210u + 0x1111u * (hb & 3u);
+		for (uint32_t c = t; c < nv; c += NGS_FMT_THREADS) {
+			const int4 a = src[c], b = src[c + 1];
+			uint32_t v0, v1, v2, v3, v4;
+			if (wsh == 0) { v0 = a.x; v1 = a.y; v2 = a.z; v3 = a.w; v4 = b.x; }
+			else if (wsh == 1) { v0 = a.y; v1 = a.z; v2 = a.w; v3 = b.x; v4 = b.y; }
+			else if (wsh == 2) { v0 = a.z; v1 = a.w; v2 = b.x; v3 = b.y; v4 = b.z; }
+			else { v0 = a.w; v1 = b.x; v2 = b.y; v3 = b.z; v4 = b.w; }
+			int4 o;
+			o.x = (int)__byte_perm(v0, v1, sel); o.y = (int)__byte_perm(v1, v2, sel);
+			o.z = (int)__byte_perm(v2, v3, sel); o.w = (int)__byte_perm(v3, v4, sel);
+			dst[c] = o;
 		}
-		__syncthreads();
-		if (tlen && L.k) atomicOr(L.w, L.carry);      /* tail bytes into the word whose owner stored its head part above */
 	}
-	__syncthreads();
-	char *g = A.out + goff - mis;                       /* 16-byte aligned */
-	const uint32_t end = mis + total;
-	uint32_t a0 = (mis + 15u) & ~15u;                   /* head bytes [mis,a0), 128-bit body [a0,a1), tail [a1,end) */
-	if (a0 > end) a0 = end;
-	uint32_t a1 = end & ~15u;
-	if (a1 < a0) a1 = a0;
-	for (uint32_t i = mis + t; i < a0; i += NGS_FMT_THREADS) g[i] = s_stage[i];
-	{
-		const int4 *src = reinterpret_cast<const int4 *>(s_stage + a0) + t;
-		int4 *dst = reinterpret_cast<int4 *>(g + a0) + t;
-		const uint32_t nv = (a1 - a0) >> 4;                 /* 128-bit words of the body */
-		uint32_t i = t;
-		for (; i + 3 * NGS_FMT_THREADS < nv; i += 4 * NGS_FMT_THREADS, src += 4 * NGS_FMT_THREADS, dst += 4 * NGS_FMT_THREADS) {
-			const int4 v0 = src[0], v1 = src[NGS_FMT_THREADS], v2 = src[2 * NGS_FMT_THREADS], v3 = src[3 * NGS_FMT_THREADS];
-			dst[0] = v0; dst[NGS_FMT_THREADS] = v1; dst[2 * NGS_FMT_THREADS] = v2; dst[3 * NGS_FMT_THREADS] = v3;
-		}
-		for (; i < nv; i += NGS_FMT_THREADS, src += NGS_FMT_THREADS, dst += NGS_FMT_THREADS) *dst = *src;
-	}
-	for (uint32_t i = a1 + t; i < end; i += NGS_FMT_THREADS) g[i] = s_stage[i];
+	const uint32_t tb = hb + (nv << 4);
+	if (tb + (uint32_t)t < total) g[tb + t] = s_stage[tb + t];
 }
 
 /* reset of look-back status words and tickets before a scan / format launch */
