@@ -78,6 +78,7 @@ struct ngscov {
 	 * as a higher refID has been decoded, so the device->host copy of the text overlaps the host->device copy
 	 * of the rest of the stream */
 	bool stream_fin; size_t next_fin_seg; unsigned long long mops_fin; bool bins_zeroed;
+	int32_t end_ctg; uint32_t end_pos;          /* first position behind the slice (end_ctg = -2: whole genome) */
 	size_t bed_off;                          /* bedGraph bytes produced so far */
 	size_t bed_d2h;                          /* ... of which already queued for D2H */
 	ngs_dev_state *h_st2;                    /* pinned read-back of the state block after scan / format launches */
@@ -283,6 +284,15 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	h->stage_cap = cfg->staging_bytes ? (size_t)cfg->staging_bytes : (size_t)256 << 20;
 	/* Two ingest organisations are kept, both parity-tested: K1 record framing + K2 per-record decode (default:
 	 * 22.7 ms on config 2) and the single fused walk+decode kernel (NGSCOV_FUSED=1: 27.1 ms), DESIGN.md section 4. */
+	h->end_ctg = -2; h->end_pos = 0;
+	if (cfg->slice_end) {
+		uint64_t acc = 0;
+		h->end_ctg = cfg->n_ref;                  /* slice reaches the end of the genome: only the unmapped tail lies behind */
+		for (int i = 0; i < cfg->n_ref; ++i) {
+			if (cfg->slice_end < acc + cfg->ref_len[i]) { h->end_ctg = i; h->end_pos = (uint32_t)(cfg->slice_end - acc); break; }
+			acc += cfg->ref_len[i];
+		}
+	}
 	h->stream_fin = cfg->slice_end == 0 && !(getenv("NGSCOV_STREAM_FINALIZE") && atoi(getenv("NGSCOV_STREAM_FINALIZE")) == 0);
 	h->ingest_mode = 0;
 	if (getenv("NGSCOV_FUSED") && atoi(getenv("NGSCOV_FUSED")) == 1) h->ingest_mode = 1;
@@ -428,7 +438,7 @@ static IngestArgs make_ingest_args(ngscov *h, const uint8_t *base, int64_t n, in
 	IngestArgs A;
 	A.base = base; A.n = n; A.shift = h->shift; A.n_sub = n_sub; A.entry = h->d_entry; A.exit = h->d_exit;
 	A.cfg.n_ref = h->n_ref; A.cfg.flag_mask = h->cfg.mode == NGSCOV_MODE_DEPTH ? 0x704u : 0x4u;
-	A.cfg.ctg2seg = h->d_ctg2seg; A.cfg.seg = h->d_seg;
+	A.cfg.ctg2seg = h->d_ctg2seg; A.cfg.seg = h->d_seg; A.cfg.end_ctg = h->end_ctg; A.cfg.end_pos = h->end_pos;
 	A.ref_len = h->d_ref_len; A.diff = h->d_diff; A.st = h->d_st;
 	A.count = h->d_count; A.slots = h->d_slots; A.slot_shift = h->shift - 5; A.ctr = h->d_ctr;
 	A.fixed_entry0 = fixed0; A.entry0_from_state = from_state ? 1 : 0;
@@ -799,6 +809,23 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 	}
 	if (getenv("NGSCOV_DEBUG")) { fprintf(stderr, "ngscov: streamed finalize: %d calls, %.3f s host wall\n", g_fin_calls, g_fin_wall); g_fin_wall = 0; g_fin_calls = 0; }
 	h->runs_done = true;
+	return 0;
+}
+
+extern "C" int ngscov_slice_done(ngscov_t *h, int *done)
+{
+	if (!h || !done) return NGSCOV_EINVAL;
+	*done = 0;
+	if (h->sticky_err) return h->sticky_err;
+	if (h->end_ctg < 0) return 0;                                  /* no slice: never done before the last push */
+	CK(cudaSetDevice(h->device));
+	int r = resolve_pending(h);
+	if (r) return r;
+	unsigned int mr = 0;
+	CK(cudaMemcpyAsync(&h->h_st->max_ref_p1, &h->d_st->max_ref_p1, sizeof mr, cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	mr = h->h_st->max_ref_p1;
+	*done = mr >= (unsigned int)h->end_ctg + 2u ? 1 : 0;
 	return 0;
 }
 

@@ -442,6 +442,8 @@ typedef struct {
 	uint32_t flag_mask;
 	const int32_t *ctg2seg;      /* [n_ref] segment index of a contig or -1 (outside the shard) */
 	const ngs_seg *seg;
+	int32_t  end_ctg;            /* region shard: a record of this contig at or beyond end_pos lies behind the slice */
+	uint32_t end_pos;            /* (end_ctg = -2: no slice).  Such a record counts as "the next contig has begun" */
 } ngs_walk_cfg;
 
 /* decode one (already validated) record at offset o and emit its deltas with weight `sign` */
@@ -450,7 +452,12 @@ NGS_HD void ngs_decode_record(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o
                               Sink &sink, int sign, ngs_counts &cnt)
 {
 	cnt.records += 1; cnt.cigar_words += h.n_cigar;
-	if ((uint32_t)(h.ref_id + 1) > cnt.max_ref_p1) cnt.max_ref_p1 = (uint32_t)(h.ref_id + 1);
+	{	/* sorted input: once refID (or, for a shard, the position inside the slice's last contig) has moved on,
+		 * everything before is complete -- streamed finalize and ngscov_slice_done rely on this mark */
+		uint32_t r1 = (uint32_t)(h.ref_id + 1);
+		if (h.ref_id == cfg.end_ctg && (uint32_t)h.pos >= cfg.end_pos) r1 += 1;
+		if (r1 > cnt.max_ref_p1) cnt.max_ref_p1 = r1;
+	}
 	if ((h.flag & cfg.flag_mask) || h.ref_id < 0 || h.pos >= (1 << 29)) return;
 	cnt.kept += 1;
 	const int32_t si = cfg.ctg2seg[h.ref_id];

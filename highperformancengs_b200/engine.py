@@ -150,6 +150,12 @@ class CoverageEngine:
         self._check(self.lib.ngscov_runs_get(self.h, arr, n.value, C.byref(n)), "ngscov_runs_get")
         return [(r.contig, r.start, r.end, r.depth) for r in arr[:n.value]]
 
+    def slice_done(self):
+        """region shard: True once a record at or beyond the end of the slice has been decoded (synchronises)"""
+        d = C.c_int(0)
+        self._check(self.lib.ngscov_slice_done(self.h, C.byref(d)), "ngscov_slice_done")
+        return bool(d.value)
+
     def halo(self):
         h = L.Halo()
         self._check(self.lib.ngscov_halo_get(self.h, C.byref(h)), "ngscov_halo_get")

@@ -85,7 +85,7 @@ static int have_bai(const char *fn)
 }
 
 /* ------------------------------------------------------------------ parallel BGZF inflate */
-typedef struct { const uint8_t *src; uint32_t clen, ulen; uint8_t *dst; } blk_t;
+typedef struct { const uint8_t *src; uint32_t clen, ulen; uint8_t *dst; uint64_t foff; } blk_t;
 typedef struct { blk_t *b; size_t n; volatile size_t next; int err; pthread_mutex_t mu; } job_t;
 
 static void *inflate_worker(void *arg)
@@ -122,6 +122,188 @@ static int inflate_blocks(blk_t *b, size_t n, int nthreads)
 }
 
 #define DIE(...) do { fprintf(stderr, __VA_ARGS__); exit(1); } while (0)
+
+/* ------------------------------------------------------------------ region shards (NGSCOV_GPUS=N)
+ * No counterpart in the single-process reference.  The genome is cut at multiples of 16 384 bp (the BAI linear
+ * index granularity, samtools bam_index.c:43); shard g reads the file from the linear-index offset of its first
+ * tile -- the first record OVERLAPPING that tile (bam_index.c:92-111,605-615), so reads hanging in from the left
+ * are included -- up to the offset of a tile a little behind its end, and then keeps reading until the engine has
+ * seen a record that starts behind the slice (ngscov_slice_done; coordinate-sorted input).  Each shard owns an
+ * engine handle on its own GPU; deltas are clipped to the slice on the device.  Afterwards the runs cut by shard
+ * boundaries are stitched (halo exchange through the host: 72 bytes per shard), window bins are corrected for the
+ * merged runs and summed, and the bedGraph texts are concatenated in shard order. */
+#define NGS_TILE_BP 16384u
+#define NGS_END_MARGIN_TILES 4u
+
+typedef struct {
+	int n_ref;
+	uint64_t **lin; int *n_lin;          /* linear index per contig: virtual offsets */
+	uint64_t *first;                     /* smallest chunk begin of a contig (0: no records) */
+} bai_t;
+
+static int bai_load(const char *bam, bai_t *b)
+{
+	size_t l = strlen(bam);
+	char *a = (char *)malloc(l + 8);
+	sprintf(a, "%s.bai", bam);
+	FILE *f = fopen(a, "rb");
+	if (!f && l > 4 && !strcmp(bam + l - 4, ".bam")) { strcpy(a, bam); strcpy(a + l - 3, "bai"); f = fopen(a, "rb"); }
+	free(a);
+	if (!f) return -1;
+	char magic[4]; int32_t n_ref;
+	if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "BAI\1", 4) || fread(&n_ref, 4, 1, f) != 1 || n_ref < 0) { fclose(f); return -1; }
+	b->n_ref = n_ref;
+	b->lin = (uint64_t **)calloc((size_t)n_ref + 1, sizeof(uint64_t *)); b->n_lin = (int *)calloc((size_t)n_ref + 1, sizeof(int));
+	b->first = (uint64_t *)calloc((size_t)n_ref + 1, 8);
+	for (int i = 0; i < n_ref; ++i) {
+		int32_t n_bin;
+		if (fread(&n_bin, 4, 1, f) != 1) { fclose(f); return -1; }
+		for (int k = 0; k < n_bin; ++k) {
+			uint32_t bin; int32_t n_chunk;
+			if (fread(&bin, 4, 1, f) != 1 || fread(&n_chunk, 4, 1, f) != 1) { fclose(f); return -1; }
+			for (int c = 0; c < n_chunk; ++c) {
+				uint64_t ch[2];
+				if (fread(ch, 8, 2, f) != 2) { fclose(f); return -1; }
+				if (bin != 37450u && (b->first[i] == 0 || ch[0] < b->first[i])) b->first[i] = ch[0];   /* 37450: samtools' metadata pseudo-bin */
+			}
+		}
+		int32_t n_intv;
+		if (fread(&n_intv, 4, 1, f) != 1 || n_intv < 0) { fclose(f); return -1; }
+		b->n_lin[i] = n_intv;
+		b->lin[i] = (uint64_t *)calloc((size_t)n_intv + 1, 8);
+		if (n_intv && fread(b->lin[i], 8, (size_t)n_intv, f) != (size_t)n_intv) { fclose(f); return -1; }
+	}
+	fclose(f);
+	return 0;
+}
+
+/* virtual offset of the first record that can matter from contig c, position p on (0: nothing follows) */
+static uint64_t bai_seek(const bai_t *b, int c, uint32_t p)
+{
+	if (c >= b->n_ref) return 0;
+	for (int w = (int)(p >> 14); w < b->n_lin[c]; ++w) if (b->lin[c][w]) return b->lin[c][w];
+	for (int c2 = c + 1; c2 < b->n_ref; ++c2) if (b->first[c2]) return b->first[c2];
+	return 0;
+}
+
+typedef struct { uint64_t beg, end; } slice_t;
+
+/* same cuts as highperformancengs_b200/shard.py plan_slices */
+static void plan_slices(const uint32_t *len, int n_ref, int n, slice_t *out)
+{
+	uint64_t G = 0, prev = 0;
+	for (int i = 0; i < n_ref; ++i) G += len[i];
+	for (int r = 1; r <= n; ++r) {
+		uint64_t cut = G;
+		if (r < n) {
+			const uint64_t g = (uint64_t)(((unsigned __int128)G * (unsigned)r) / (unsigned)n);
+			uint64_t acc = 0; int c = 0;
+			while (c + 1 < n_ref && acc + len[c] <= g) { acc += len[c]; ++c; }
+			cut = acc + (g - acc) / NGS_TILE_BP * NGS_TILE_BP;
+			if (cut < prev) cut = prev;
+		}
+		out[r - 1].beg = prev; out[r - 1].end = cut; prev = cut;
+	}
+}
+
+static void locate(const uint32_t *len, int n_ref, uint64_t g, int *c, uint32_t *p)
+{
+	uint64_t acc = 0;
+	for (int i = 0; i < n_ref; ++i) { if (g < acc + len[i]) { *c = i; *p = (uint32_t)(g - acc); return; } acc += len[i]; }
+	*c = n_ref; *p = 0;
+}
+
+static size_t block_of(const blk_t *blk, size_t nblk, uint64_t coff)
+{
+	size_t lo = 0, hi = nblk;                  /* first block with foff >= coff */
+	while (lo < hi) { size_t mid = (lo + hi) / 2; if (blk[mid].foff < coff) lo = mid + 1; else hi = mid; }
+	return lo;
+}
+
+typedef struct {
+	/* in */
+	ngscov_cfg cfg; blk_t *blk; size_t nblk; size_t b_first, b_bound; uint32_t uoff; int to_eof, empty; int nthreads; const char *fn;
+	/* out */
+	ngscov_t *h; int rc; char err[256]; long long t_io;
+} shard_t;
+
+static void *shard_worker(void *arg)
+{
+	shard_t *s = (shard_t *)arg;
+	int rc;
+	if ((rc = ngscov_create(&s->h, &s->cfg))) { snprintf(s->err, sizeof s->err, "GPU engine unavailable on device %d: %s", s->cfg.device, ngscov_strerror(rc)); s->rc = rc; return NULL; }
+	void *stage[2]; size_t scap[2];
+	for (int i = 0; i < 2; ++i) if ((rc = ngscov_staging(s->h, i, &stage[i], &scap[i]))) { snprintf(s->err, sizeof s->err, "%s", ngscov_strerror(rc)); s->rc = rc; return NULL; }
+	/* blocks are inflated by a private copy of the table entries (dst differs per shard; shards may overlap at their ends) */
+	size_t b = s->b_first, limit = s->to_eof ? s->nblk : (s->b_bound + 1 < s->nblk ? s->b_bound + 1 : s->nblk);
+	int idx = 0, first = 1, last = s->empty;
+	if (s->empty) { rc = ngscov_push(s->h, 0, 0, NGSCOV_PUSH_LAST); if (rc) { snprintf(s->err, sizeof s->err, "%s", ngscov_strerror(rc)); s->rc = rc; return NULL; } }
+	uint8_t *tmp = (uint8_t *)malloc(65536);
+	blk_t *mine = (blk_t *)malloc(4096 * sizeof(blk_t));
+	while (!last) {
+		const long long t0 = usec();
+		if ((rc = ngscov_staging_wait(s->h, idx))) break;
+		uint8_t *dst = (uint8_t *)stage[idx];
+		size_t fill = 0;
+		if (first && b < limit) {                     /* the slice starts uoff bytes into its first block */
+			blk_t one = s->blk[b]; one.dst = tmp;
+			if (inflate_blocks(&one, 1, 1) || s->uoff > one.ulen) { snprintf(s->err, sizeof s->err, "inflate failed in %s", s->fn); rc = NGSCOV_EFORMAT; break; }
+			memcpy(dst, tmp + s->uoff, one.ulen - s->uoff); fill = one.ulen - s->uoff; ++b;
+		}
+		first = 0;
+		int bad = 0;
+		while (b < limit && fill + s->blk[b].ulen <= scap[idx]) {
+			size_t m = 0;
+			while (m < 4096 && b < limit && fill + s->blk[b].ulen <= scap[idx]) { mine[m] = s->blk[b]; mine[m].dst = dst + fill; fill += s->blk[b].ulen; ++m; ++b; }
+			if (m && inflate_blocks(mine, m, s->nthreads)) { bad = 1; break; }
+		}
+		if (bad) { snprintf(s->err, sizeof s->err, "inflate failed in %s", s->fn); rc = NGSCOV_EFORMAT; break; }
+		s->t_io += usec() - t0;
+		const int at_limit = b >= limit;
+		if (at_limit && limit >= s->nblk) {            /* end of file: records are complete */
+			rc = ngscov_push(s->h, idx, fill, NGSCOV_PUSH_LAST); last = 1;
+		} else {
+			if ((rc = ngscov_push(s->h, idx, fill, 0))) break;
+			if (at_limit) {
+				int done = 0;
+				if ((rc = ngscov_slice_done(s->h, &done))) break;
+				if (done) { rc = ngscov_push(s->h, idx ^ 1, 0, NGSCOV_PUSH_LAST | NGSCOV_PUSH_TRUNCATED_OK); last = 1; }
+				else limit = limit + 64 < s->nblk ? limit + 64 : s->nblk;      /* a long read still spans the cut: read on */
+			}
+		}
+		if (rc) break;
+		idx ^= 1;
+	}
+	free(tmp); free(mine);
+	if (!rc) rc = ngscov_finish_runs(s->h);
+	if (rc && !s->err[0]) snprintf(s->err, sizeof s->err, "%s: %s (%s)", s->fn, ngscov_strerror(rc), ngscov_last_cuda_error(s->h));
+	s->rc = rc;
+	return NULL;
+}
+
+/* decisions for ngscov_halo_put and the window-bin corrections; same rule as shard.py stitch() */
+typedef struct { ngscov_run run; int sign; } corr_t;
+static size_t stitch(const ngscov_halo *halo, int n, int *drop_first, uint32_t *new_last_end, corr_t *corr)
+{
+	size_t nc = 0; int have = 0, owner = 0; ngscov_run carry; memset(&carry, 0, sizeof carry);
+	for (int r = 0; r < n; ++r) { drop_first[r] = 0; new_last_end[r] = 0; }
+	for (int r = 0; r < n; ++r) {
+		if (halo[r].n_runs == 0) { have = 0; continue; }
+		const ngscov_run f = halo[r].first;
+		int merged = 0;
+		if (have && carry.contig == f.contig && carry.end == f.start && carry.depth == f.depth) {
+			merged = 1;
+			corr[nc].run = carry; corr[nc++].sign = -1;
+			corr[nc].run = f; corr[nc++].sign = -1;
+			carry.end = f.end;
+			corr[nc].run = carry; corr[nc++].sign = +1;
+			drop_first[r] = 1; new_last_end[owner] = carry.end;
+		}
+		if (merged && halo[r].n_runs == 1) continue;       /* the whole shard was one run: it stays open into the next */
+		carry = halo[r].last; owner = r; have = 1;
+	}
+	return nc;
+}
 
 int main(int argc, char *argv[])
 {
@@ -179,7 +361,7 @@ int main(int argc, char *argv[])
 			const size_t bsize = (size_t)(p[16] | p[17] << 8) + 1;
 			if (bsize < 26 || off + bsize > fsz) DIE("bam2bed: truncated BGZF block in %s\n", fn);
 			if (nblk == cap) { cap *= 2; blk = (blk_t *)realloc(blk, cap * sizeof(blk_t)); }
-			blk[nblk].src = p + 18; blk[nblk].clen = (uint32_t)(bsize - 26);
+			blk[nblk].src = p + 18; blk[nblk].clen = (uint32_t)(bsize - 26); blk[nblk].foff = off;
 			memcpy(&blk[nblk].ulen, p + bsize - 4, 4);
 			if (blk[nblk].ulen > 65536) DIE("bam2bed: bad BGZF block size in %s\n", fn);
 			++nblk; off += bsize;
@@ -230,6 +412,90 @@ int main(int argc, char *argv[])
 			if (want > (256ull << 20)) want = 256ull << 20;
 			cfg.staging_bytes = want;
 			if (getenv("NGSCOV_STAGING_MB")) cfg.staging_bytes = (uint64_t)atoll(getenv("NGSCOV_STAGING_MB")) << 20;
+		}
+		int n_shards = getenv("NGSCOV_GPUS") ? atoi(getenv("NGSCOV_GPUS")) : 1;
+		if (n_shards > 64) n_shards = 64;
+		if (n_shards > 1) {
+			/* ---- region-sharded run: one engine per GPU (NGSCOV_DEVICES="0,1,.." overrides the default 0..N-1) */
+			int devs[64];
+			for (int g = 0; g < n_shards; ++g) devs[g] = g;
+			if (getenv("NGSCOV_DEVICES")) { const char *q = getenv("NGSCOV_DEVICES"); for (int g = 0; g < n_shards && *q; ++g) { devs[g] = atoi(q); while (*q && *q != ',') ++q; if (*q) ++q; } }
+			bai_t bai; memset(&bai, 0, sizeof bai);
+			if (bai_load(fn, &bai) || bai.n_ref != n_ref) DIE("bam2bed: BAM indexing file is not available.\n");
+			slice_t sl[64]; plan_slices(ref_len, n_ref, n_shards, sl);
+			shard_t sh[64]; memset(sh, 0, sizeof sh);
+			pthread_t th[64];
+			int ns = 0;
+			for (int g = 0; g < n_shards; ++g) {
+				if (sl[g].end <= sl[g].beg) continue;          /* more shards than 16 kb tiles */
+				shard_t *s = &sh[ns];
+				s->cfg = cfg; s->cfg.device = devs[g]; s->cfg.slice_beg = sl[g].beg; s->cfg.slice_end = sl[g].end;
+				s->blk = blk; s->nblk = nblk; s->fn = fn; s->nthreads = nthreads / n_shards > 0 ? nthreads / n_shards : 1;
+				int cb, ce; uint32_t pb, pe;
+				locate(ref_len, n_ref, sl[g].beg, &cb, &pb); locate(ref_len, n_ref, sl[g].end, &ce, &pe);
+				const uint64_t v0 = bai_seek(&bai, cb, pb);
+				if (v0 == 0) s->empty = 1;                     /* no mapped record from here on */
+				else { s->b_first = block_of(blk, nblk, v0 >> 16); s->uoff = (uint32_t)(v0 & 0xffff); if (s->b_first >= nblk) s->empty = 1; }
+				if (ce >= n_ref) s->to_eof = 1;                /* the last shard also walks the unmapped tail */
+				else {
+					const uint64_t v1 = bai_seek(&bai, ce, pe + NGS_END_MARGIN_TILES * NGS_TILE_BP);
+					if (v1 == 0) s->to_eof = 1; else s->b_bound = block_of(blk, nblk, v1 >> 16);
+				}
+				{	uint64_t want = (64u << 20); if (getenv("NGSCOV_STAGING_MB")) want = (uint64_t)atoll(getenv("NGSCOV_STAGING_MB")) << 20; s->cfg.staging_bytes = want; }
+				++ns;
+			}
+			for (int g = 0; g < ns; ++g) if (pthread_create(&th[g], NULL, shard_worker, &sh[g])) DIE("bam2bed: cannot start shard thread\n");
+			for (int g = 0; g < ns; ++g) pthread_join(th[g], NULL);
+			for (int g = 0; g < ns; ++g) if (sh[g].rc) DIE("bam2bed: shard %d: %s\n", g, sh[g].err);
+			/* halo stitch + window bins */
+			ngscov_halo halo[64]; int drop[64]; uint32_t nle[64]; corr_t corr[3 * 64];
+			int rc2;
+			for (int g = 0; g < ns; ++g) if ((rc2 = ngscov_halo_get(sh[g].h, &halo[g]))) DIE("bam2bed: %s\n", ngscov_strerror(rc2));
+			const size_t ncorr = stitch(halo, ns, drop, nle, corr);
+			for (int g = 0; g < ns; ++g) if ((rc2 = ngscov_halo_put(sh[g].h, drop[g], nle[g]))) DIE("bam2bed: %s\n", ngscov_strerror(rc2));
+			uint64_t nb = 0; ngscov_bins_count(sh[0].h, &nb);
+			uint64_t *sum = (uint64_t *)calloc(nb + 1, 8), *one = (uint64_t *)calloc(nb + 1, 8);
+			for (int g = 0; g < ns; ++g) {
+				if ((rc2 = ngscov_bins_get(sh[g].h, one, nb))) DIE("bam2bed: %s\n", ngscov_strerror(rc2));
+				for (uint64_t k = 0; k < nb; ++k) sum[k] += one[k];
+			}
+			for (size_t k = 0; k < ncorr; ++k) if ((rc2 = ngscov_bins_apply_run(sh[0].h, &corr[k].run, corr[k].sign, sum, nb))) DIE("bam2bed: %s\n", ngscov_strerror(rc2));
+			if ((rc2 = ngscov_bins_put(sh[0].h, sum, nb))) DIE("bam2bed: %s\n", ngscov_strerror(rc2));
+			free(sum); free(one);
+			const uint32_t all = (TOOL_DEPTH ? (1u << NGSCOV_OUT_BEDGRAPH) | (1u << NGSCOV_OUT_DEPTH) : 0u) |
+			                     ((wig || !TOOL_DEPTH) ? (1u << NGSCOV_OUT_WIG) | (1u << NGSCOV_OUT_CHROMSIZE) : 0u);
+			for (int g = 0; g < ns; ++g) {
+				const uint32_t mask = g == 0 ? all : (TOOL_DEPTH ? (1u << NGSCOV_OUT_BEDGRAPH) : 0u);
+				if (mask && (rc2 = ngscov_format(sh[g].h, mask))) DIE("bam2bed: %s: %s\n", fn, ngscov_strerror(rc2));
+			}
+			const int which2[4] = { NGSCOV_OUT_BEDGRAPH, NGSCOV_OUT_DEPTH, NGSCOV_OUT_WIG, NGSCOV_OUT_CHROMSIZE };
+			FILE *outs2[4] = { f_bed, f_depth, f_wig, f_chr };
+			for (int k = 0; k < 4; ++k) {
+				if (!outs2[k]) continue;
+				for (int g = 0; g < (k == 0 ? ns : 1); ++g) {
+					const char *buf; size_t len;
+					if ((rc2 = ngscov_output(sh[g].h, which2[k], &buf, &len))) DIE("bam2bed: %s\n", ngscov_strerror(rc2));
+					if (len && fwrite(buf, 1, len, outs2[k]) != len) DIE("bam2bed: write failed\n");
+				}
+			}
+			for (int j = 0; j < n_ref; ++j) fprintf(stderr, "%s at %.3f s\n", ref_name[j], (double)(usec() - begin) / 1e6);
+			if (verbose) {
+				for (int g = 0; g < ns; ++g) {
+					ngscov_stats_t st; ngscov_stats(sh[g].h, &st);
+					fprintf(stderr, "ngscov: shard %d (device %d, slice [%llu,%llu)): %llu records, %llu runs; host read+inflate %.3f s (%d threads); "
+					        "device: ingest %.3f ms scan %.3f ms format %.3f ms\n", g, sh[g].cfg.device, (unsigned long long)sh[g].cfg.slice_beg,
+					        (unsigned long long)sh[g].cfg.slice_end, (unsigned long long)st.records, (unsigned long long)st.runs, sh[g].t_io / 1e6,
+					        sh[g].nthreads, st.ms_ingest, st.ms_scan, st.ms_format);
+				}
+			}
+			for (int g = 0; g < ns; ++g) ngscov_destroy(sh[g].h);
+			for (int k = 0; k < 4; ++k) if (outs2[k]) fclose(outs2[k]);
+			for (int j = 0; j < n_ref; ++j) { free(ref_name[j]); free(bai.lin[j]); }
+			free(bai.lin); free(bai.n_lin); free(bai.first);
+			free(ref_name); free(ref_len); free(hbuf); free(blk);
+			munmap((void *)file, fsz); close(fd);
+			fprintf(stderr, "Converted %s to wig format at %.3f s\n", fn, (double)(usec() - begin) / 1e6);
+			continue;
 		}
 		ngscov_t *h = NULL;
 		int rc = ngscov_create(&h, &cfg);

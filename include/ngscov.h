@@ -148,6 +148,12 @@ int ngscov_finish_runs(ngscov_t *h);
 /* Shard stitching.  halo_get returns the first / last run of this shard.  halo_put tells the shard that
  * its first run was merged into the previous shard's last run (drop_first) and/or that its last run now
  * ends at new_last_end (0 = unchanged) before text is formatted. */
+/* Region shards read the BAM from the BAI linear-index offset of their first 16 kb tile (samtools bam_index.c:605-615)
+ * and must consume every record that starts before the end of the slice.  *done becomes 1 once a record at or beyond
+ * the slice end (or of a later contig) has been decoded: the input is coordinate sorted, so the caller can stop
+ * pushing and close the input with NGSCOV_PUSH_LAST | NGSCOV_PUSH_TRUNCATED_OK.  Completes the pending push first
+ * (synchronises); call it only near the expected end.  Always 0 for a handle without a slice. */
+int ngscov_slice_done(ngscov_t *h, int *done);
 int ngscov_halo_get(ngscov_t *h, ngscov_halo *halo);
 int ngscov_halo_put(ngscov_t *h, int drop_first, uint32_t new_last_end);
 

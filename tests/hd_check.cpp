@@ -117,7 +117,7 @@ int main(int argc, char **argv)
 	}
 	std::vector<int> diff(elems, 0);
 	int range_err = 0;
-	ngs_walk_cfg cfg = { bam.n_ref, mode ? 0x4u : 0x704u, c2s.data(), seg.data() };
+	ngs_walk_cfg cfg = { bam.n_ref, mode ? 0x4u : 0x704u, c2s.data(), seg.data(), -2, 0 };
 	ngs_counts cnt = { 0, 0, 0, 0 };
 	long long mismatches = 0, walks = 0;
 

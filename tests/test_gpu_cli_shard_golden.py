@@ -48,6 +48,32 @@ def test_c_driver_writes_reference_identical_files(tmp_path, case, tool, window)
     check_against_gold(got, f"{case}|{tool}|{window}")
 
 
+@pytest.mark.parametrize("case,tool,window", [("random1", "depth", 150), ("random1", "wig", 150), ("c2_s0.0005", "depth", 20000),
+                                              ("c4_s0.01", "wig", 100), ("c4_s0.01", "wig", 20000)])
+@pytest.mark.parametrize("shards", [2, 3, 7])
+def test_c_driver_region_shards_from_bai(tmp_path, case, tool, window, shards):
+    """NGSCOV_GPUS=N: every shard reads the BAM from the BAI linear-index offset of its slice, stops once the engine has
+    seen a record behind the slice, and the stitched files equal the reference's (all shards on device 0 here)"""
+    exe = os.path.join(ROOT, "highperformancengs_b200", "host", "bam2depth" if tool == "depth" else "bam2wig")
+    spec = [c for c in cases.CASES if c[0] == case][0]
+    names, lens, recs, g = cases.case_input(spec[1], spec[2])
+    bam = str(tmp_path / (case + ".bam"))
+    if g is not None:
+        g.write_bam(bam)
+    else:
+        bamutil.write_bam(bam, names, lens, recs)
+    args = [exe, "-o", str(tmp_path / "o"), "-w", str(window)] + (["-W"] if tool == "depth" else []) + [bam]
+    env = dict(os.environ, NGSCOV_STAGING_MB="1", NGSCOV_GPUS=str(shards), NGSCOV_DEVICES=",".join(["0"] * shards), NGSCOV_VERBOSE="1")
+    r = subprocess.run(args, cwd=str(tmp_path), capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert r.stderr.count("ngscov: shard ") >= 2, r.stderr
+    files = {"wig": "o.1.wig", "chromsize": "o.1.chromSize.txt"}
+    if tool == "depth":
+        files.update(bedgraph=os.path.basename(bam) + ".1.bedGraph", depth="o.1.depth")
+    got = {k: open(str(tmp_path / p), "rb").read() for k, p in files.items()}
+    check_against_gold(got, f"{case}|{tool}|{window}")
+
+
 def _sharded(names, lens, recs, mode, window, n):
     """n engines on one GPU, each owning a genome slice but fed the whole stream (deltas are clipped)."""
     from highperformancengs_b200 import CoverageEngine, shard
