@@ -34,7 +34,7 @@ class Stats(C.Structure):
                 ("stream_bytes", C.c_uint64), ("boundaries", C.c_uint64), ("runs", C.c_uint64), ("positions", C.c_uint64),
                 ("out_bytes", C.c_uint64 * 4), ("spec_subchunks", C.c_uint64), ("spec_repaired", C.c_uint64),
                 ("ms_zero", C.c_float), ("ms_ingest", C.c_float), ("ms_scan", C.c_float), ("ms_format", C.c_float),
-                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("launches", C.c_uint32), ("ms_inflate", C.c_float)]
 
 
 # every symbol include/ngscov.h declares: (restype, argtypes)
@@ -52,6 +52,7 @@ SYMBOLS = {
     "ngscov_push_device": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_int]),
     "ngscov_finish_runs": (C.c_int, [_H]),
     "ngscov_slice_done": (C.c_int, [_H, C.POINTER(C.c_int)]),
+    "ngscov_push_bgzf": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     "ngscov_halo_get": (C.c_int, [_H, C.POINTER(Halo)]),
     "ngscov_halo_put": (C.c_int, [_H, C.c_int, C.c_uint32]),
     "ngscov_bins_count": (C.c_int, [_H, C.POINTER(C.c_uint64)]),

@@ -89,7 +89,8 @@ struct ngscov {
 	ngscov_stats_t stats;
 	int sm_count;
 	/* per-push timing events (start/end pairs), reused across inputs */
-	std::vector<cudaEvent_t> ev_ing, ev_cp; size_t n_ing, n_cp;
+	std::vector<cudaEvent_t> ev_ing, ev_cp, ev_inf; size_t n_ing, n_cp, n_inf;
+	uint8_t *d_comp[2]; size_t comp_cap[2]; ngs_bgzf_desc *d_desc[2]; size_t desc_cap[2];   /* BGZF blocks awaiting the device inflate */
 };
 
 static cudaEvent_t next_event(std::vector<cudaEvent_t> &pool, size_t &used)
@@ -334,6 +335,8 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
 	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
 	for (cudaEvent_t e : h->ev_ing) cudaEventDestroy(e);
+	for (cudaEvent_t e : h->ev_inf) cudaEventDestroy(e);
+	for (int i = 0; i < 2; ++i) { if (h->d_comp[i]) cudaFree(h->d_comp[i]); if (h->d_desc[i]) cudaFree(h->d_desc[i]); }
 	for (cudaEvent_t e : h->ev_cp) cudaEventDestroy(e);
 	delete h;
 }
@@ -361,7 +364,7 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	memset(&h->halo, 0, sizeof h->halo); h->halo.first.contig = h->halo.last.contig = -1;
 	for (int i = 0; i < 4; ++i) { h->text_len[i] = 0; h->text_ready[i] = false; h->h_text_valid[i] = false; }
 	h->stage_busy[0] = h->stage_busy[1] = false;
-	h->n_ing = 0; h->n_cp = 0;
+	h->n_ing = 0; h->n_cp = 0; h->n_inf = 0;
 	CK(cudaStreamSynchronize(h->s_out));
 	h->next_fin_seg = 0; h->mops_fin = 0; h->bins_zeroed = false; h->bed_off = 0; h->bed_d2h = 0;
 	h->acc_boundaries = h->acc_runs = 0; h->acc_max = h->acc_min = 0;
@@ -639,6 +642,103 @@ extern "C" int ngscov_push_host(ngscov_t *h, const void *host, size_t nbytes, in
 	return 0;
 }
 
+/* BGZF blocks as they lie in the file -> device inflate -> the same chunk pipeline as ngscov_push_host.  The host only
+ * walks the 18-byte block headers (BSIZE) and 8-byte footers (ISIZE); samtools bgzf.c:214-238 (inflate_block) runs on
+ * the GPU (k_bgzf_inflate).  Compressed bytes of chunk k+1 are copied while chunk k is inflated and ingested. */
+extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, size_t skip, int flags)
+{
+	if (!h || (!blocks && nbytes)) return NGSCOV_EINVAL;
+	if (h->runs_done || h->last_pushed) return NGSCOV_ESTATE;
+	if (h->sticky_err) return h->sticky_err;
+	CK(cudaSetDevice(h->device));
+	int r;
+	if ((r = ensure_chunk(h, 0)) || (r = ensure_chunk(h, 1))) return r;
+	/* block table and chunk plan: whole blocks, at most stage_cap inflated bytes per chunk */
+	const uint8_t *src = (const uint8_t *)blocks;
+	struct Chunk { size_t b0, b1, c0, c1; size_t ulen; };
+	std::vector<ngs_bgzf_desc> desc; std::vector<Chunk> chunks;
+	{
+		size_t off = 0; Chunk c = { 0, 0, 0, 0, 0 };
+		while (off < nbytes) {
+			if (off + 18 > nbytes) return NGSCOV_EFORMAT;
+			const uint8_t *p = src + off;
+			if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4) || p[12] != 'B' || p[13] != 'C') return NGSCOV_EFORMAT;
+			const size_t bsize = (size_t)(p[16] | p[17] << 8) + 1;
+			if (bsize < 26 || off + bsize > nbytes) return NGSCOV_EFORMAT;
+			uint32_t isize; memcpy(&isize, p + bsize - 4, 4);
+			if (isize > 65536 || isize > h->stage_cap) return NGSCOV_EFORMAT;
+			if (c.ulen + isize > h->stage_cap) { c.b1 = desc.size(); c.c1 = off; chunks.push_back(c); c.b0 = desc.size(); c.c0 = off; c.ulen = 0; }
+			ngs_bgzf_desc d; d.src = off + 18 - c.c0; d.dst = c.ulen; d.clen = (uint32_t)(bsize - 26); d.ulen = isize;
+			desc.push_back(d); c.ulen += isize; off += bsize;
+		}
+		c.b1 = desc.size(); c.c1 = off;
+		if (c.b1 > c.b0) chunks.push_back(c);
+	}
+	size_t total_u = 0;
+	for (const Chunk &c : chunks) total_u += c.ulen;
+	if (skip > total_u) return NGSCOV_EINVAL;
+	if (flags & NGSCOV_PUSH_LAST) { h->last_pushed = true; h->last_flags = flags; }
+	h->stats.stream_bytes += total_u - skip;
+	if ((r = resolve_pending(h))) return r;
+	if (chunks.empty()) return 0;
+	auto stage_in = [&](size_t k, int idx) -> int {               /* compressed bytes + descriptors of chunk k -> device */
+		const Chunk &c = chunks[k];
+		const size_t cb = c.c1 - c.c0, nb = c.b1 - c.b0;
+		if (cb + 16 > h->comp_cap[idx]) {
+			CK(cudaStreamSynchronize(h->s_main)); CK(cudaStreamSynchronize(h->s_copy));
+			if (h->d_comp[idx]) cudaFree(h->d_comp[idx]);
+			h->d_comp[idx] = nullptr; h->comp_cap[idx] = 0;
+			const size_t want = cb + cb / 8 + 4096;
+			CK(cudaMalloc((void **)&h->d_comp[idx], want)); h->comp_cap[idx] = want;
+		}
+		if (nb > h->desc_cap[idx]) {
+			CK(cudaStreamSynchronize(h->s_main)); CK(cudaStreamSynchronize(h->s_copy));
+			if (h->d_desc[idx]) cudaFree(h->d_desc[idx]);
+			h->d_desc[idx] = nullptr; h->desc_cap[idx] = 0;
+			const size_t want = nb + nb / 8 + 64;
+			CK(cudaMalloc((void **)&h->d_desc[idx], want * sizeof(ngs_bgzf_desc))); h->desc_cap[idx] = want;
+		}
+		CK(cudaStreamWaitEvent(h->s_copy, h->ev_finalized, 0));
+		CK(cudaEventRecord(next_event(h->ev_cp, h->n_cp), h->s_copy));
+		CK(cudaMemcpyAsync(h->d_comp[idx], src + c.c0, cb, cudaMemcpyHostToDevice, h->s_copy));
+		CK(cudaMemcpyAsync(h->d_desc[idx], desc.data() + c.b0, nb * sizeof(ngs_bgzf_desc), cudaMemcpyHostToDevice, h->s_copy));
+		CK(cudaEventRecord(next_event(h->ev_cp, h->n_cp), h->s_copy));
+		CK(cudaEventRecord(h->ev_h2d[idx], h->s_copy));
+		return 0;
+	};
+	int idx = 0;
+	if ((r = stage_in(0, idx))) return r;
+	int sm = 148;
+	cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->device);
+	for (size_t k = 0; k < chunks.size(); ++k, idx ^= 1) {
+		const Chunk &c = chunks[k];
+		if ((r = resolve_pending(h, true))) return r;                /* chunk k-1 verified, its buffers are free */
+		if (k + 1 < chunks.size() && (r = stage_in(k + 1, idx ^ 1))) return r;
+		uint8_t *data = h->d_chunk[idx] + NGS_HEADROOM;
+		CK(cudaStreamWaitEvent(h->s_main, h->ev_h2d[idx], 0));
+		const uint32_t nb = (uint32_t)(c.b1 - c.b0);
+		const unsigned grid = (unsigned)std::min<size_t>((nb + NGS_INF_WARPS - 1) / NGS_INF_WARPS, (size_t)sm * 6);
+		CK(cudaEventRecord(next_event(h->ev_inf, h->n_inf), h->s_main));
+		k_bgzf_inflate<<<grid, NGS_INF_WARPS * 32, 0, h->s_main>>>(h->d_comp[idx], h->d_desc[idx], nb, data, h->d_st);
+		CK(cudaEventRecord(next_event(h->ev_inf, h->n_inf), h->s_main));
+		h->stats.launches += 1;
+		CK(cudaGetLastError());
+		const size_t sk = std::min(skip, c.ulen);
+		skip -= sk;
+		if (c.ulen == sk) continue;                                  /* header-only chunk */
+		if (!h->shift) {
+			int32_t bs = 0;
+			CK(cudaMemcpyAsync(&bs, data + sk, 4, cudaMemcpyDeviceToHost, h->s_main));
+			CK(cudaStreamSynchronize(h->s_main));
+			pick_shift(h, bs);
+		}
+		k_place_carry<<<1, 256, 0, h->s_main>>>(data + sk, h->d_st, h->d_carry);
+		h->stats.launches += 1;
+		if ((r = submit_chunk(h, data + sk, (int64_t)(c.ulen - sk), true, 0))) return r;
+	}
+	return 0;
+}
+
 extern "C" int ngscov_push_device(ngscov_t *h, const void *dev_records, size_t nbytes, int flags)
 {
 	if (!h || (!dev_records && nbytes)) return NGSCOV_EINVAL;
@@ -773,6 +873,7 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 	}
 	h->stats.ms_ingest += sum_events(h->ev_ing, h->n_ing);
 	h->stats.ms_h2d += sum_events(h->ev_cp, h->n_cp);
+	h->stats.ms_inflate += sum_events(h->ev_inf, h->n_inf);
 	const ngs_dev_state st = *h->h_st;
 	h->stats.records = st.records; h->stats.kept = st.kept; h->stats.m_ops = st.m_ops; h->stats.cigar_words = st.cigar_words;
 	h->stats.spec_subchunks = st.spec_walks; h->stats.spec_repaired = st.spec_repaired;

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "ngscov_hd.h"
+#include "ngscov_inflate.h"
 
 #ifndef NGS_SCAN_THREADS
 #define NGS_SCAN_THREADS 256
@@ -1635,6 +1636,47 @@ __global__ void __launch_bounds__(NGS_FMT_THREADS, MINB) k_format_bed(const __gr
 	}
 	const uint32_t tb = hb + (nv << 4);
 	if (tb + (uint32_t)t < total) g[tb + t] = s_stage[tb + t];
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* K0: BGZF inflate (replaces samtools-0.1.19 bgzf.c:214-238 inflate_block on the host).
+ * One warp per BGZF block.  The 32 lanes run the sequential DEFLATE decoder of ngscov_inflate.h in lock step on
+ * identical values (Huffman tables in the warp's slice of shared memory, table loads are broadcasts), so there is
+ * no divergence and nothing to exchange; only the bytes of a match or of a stored block are spread over the
+ * lanes.  A match of length len at distance dist copies byte i from pos - dist + (i mod dist): every source byte
+ * lies before pos, so the lanes need no ordering among themselves within one copy; __syncwarp() orders a copy
+ * after the literals and copies that produced its source. */
+struct ngs_bgzf_desc { unsigned long long src, dst; uint32_t clen, ulen; };
+
+struct WarpInflateOut {
+	uint8_t *o; int lane;
+	__device__ __forceinline__ void literal(uint32_t pos, uint32_t b) { if (lane == 0) o[pos] = (uint8_t)b; }
+	__device__ __forceinline__ void match(uint32_t pos, uint32_t len, uint32_t dist)
+	{
+		__syncwarp();
+		const uint8_t *src = o + pos - dist;
+		if (dist >= len) { for (uint32_t i = lane; i < len; i += 32) o[pos + i] = src[i]; }
+		else if (dist == 1u) { const uint8_t v = src[0]; for (uint32_t i = lane; i < len; i += 32) o[pos + i] = v; }
+		else { for (uint32_t i = lane; i < len; i += 32) o[pos + i] = src[i % dist]; }
+	}
+	__device__ __forceinline__ void stored(uint32_t pos, const uint8_t *src, uint32_t len)
+	{
+		for (uint32_t i = lane; i < len; i += 32) o[pos + i] = src[i];
+	}
+};
+
+#define NGS_INF_WARPS 8
+__global__ void __launch_bounds__(NGS_INF_WARPS * 32) k_bgzf_inflate(const uint8_t *comp, const ngs_bgzf_desc *desc, uint32_t n_blk, uint8_t *out, ngs_dev_state *st)
+{
+	__shared__ ngs_inf_tables s_T[NGS_INF_WARPS];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (uint32_t b = blockIdx.x * NGS_INF_WARPS + warp; b < n_blk; b += gridDim.x * NGS_INF_WARPS) {
+		const ngs_bgzf_desc d = desc[b];
+		WarpInflateOut o = { out + d.dst, lane };
+		const long r = ngs_inflate_stream(comp + d.src, d.clen, d.ulen, s_T[warp], o);
+		if (r != (long)d.ulen && lane == 0) atomicOr(&st->flags, NGS_FLAG_EFORMAT);
+		__syncwarp();
+	}
 }
 
 /* reset of look-back status words and tickets before a scan / format launch */

@@ -223,6 +223,7 @@ static size_t block_of(const blk_t *blk, size_t nblk, uint64_t coff)
 typedef struct {
 	/* in */
 	ngscov_cfg cfg; blk_t *blk; size_t nblk; size_t b_first, b_bound; uint32_t uoff; int to_eof, empty; int nthreads; const char *fn;
+	int gpu_inflate; const uint8_t *file_end;
 	/* out */
 	ngscov_t *h; int rc; char err[256]; long long t_io;
 } shard_t;
@@ -237,6 +238,26 @@ static void *shard_worker(void *arg)
 	/* blocks are inflated by a private copy of the table entries (dst differs per shard; shards may overlap at their ends) */
 	size_t b = s->b_first, limit = s->to_eof ? s->nblk : (s->b_bound + 1 < s->nblk ? s->b_bound + 1 : s->nblk);
 	int idx = 0, first = 1, last = s->empty;
+	if (s->gpu_inflate && !s->empty) {
+		/* compressed blocks [b, limit) go to the device as they lie in the file; extend while the slice is not done */
+		size_t skip = s->uoff;
+		while (!last) {
+			const uint8_t *p0 = s->blk[b].src - 18;
+			const uint8_t *p1 = limit < s->nblk ? s->blk[limit].src - 18 : s->file_end;
+			const int eof = limit >= s->nblk;
+			if ((rc = ngscov_push_bgzf(s->h, p0, (size_t)(p1 - p0), skip, eof ? NGSCOV_PUSH_LAST : 0))) break;
+			skip = 0; b = limit;
+			if (eof) { last = 1; break; }
+			int done = 0;
+			if ((rc = ngscov_slice_done(s->h, &done))) break;
+			if (done) { rc = ngscov_push(s->h, 0, 0, NGSCOV_PUSH_LAST | NGSCOV_PUSH_TRUNCATED_OK); last = 1; }
+			else limit = limit + 64 < s->nblk ? limit + 64 : s->nblk;
+		}
+		if (!rc) rc = ngscov_finish_runs(s->h);
+		if (rc && !s->err[0]) snprintf(s->err, sizeof s->err, "%s: %s (%s)", s->fn, ngscov_strerror(rc), ngscov_last_cuda_error(s->h));
+		s->rc = rc;
+		return NULL;
+	}
 	if (s->empty) { rc = ngscov_push(s->h, 0, 0, NGSCOV_PUSH_LAST); if (rc) { snprintf(s->err, sizeof s->err, "%s", ngscov_strerror(rc)); s->rc = rc; return NULL; } }
 	uint8_t *tmp = (uint8_t *)malloc(65536);
 	blk_t *mine = (blk_t *)malloc(4096 * sizeof(blk_t));
@@ -430,7 +451,7 @@ int main(int argc, char *argv[])
 				if (sl[g].end <= sl[g].beg) continue;          /* more shards than 16 kb tiles */
 				shard_t *s = &sh[ns];
 				s->cfg = cfg; s->cfg.device = devs[g]; s->cfg.slice_beg = sl[g].beg; s->cfg.slice_end = sl[g].end;
-				s->blk = blk; s->nblk = nblk; s->fn = fn; s->nthreads = nthreads / n_shards > 0 ? nthreads / n_shards : 1;
+				s->blk = blk; s->nblk = nblk; s->fn = fn; s->gpu_inflate = getenv("NGSCOV_GPU_INFLATE") && atoi(getenv("NGSCOV_GPU_INFLATE")) != 0; s->file_end = file + off; s->nthreads = nthreads / n_shards > 0 ? nthreads / n_shards : 1;
 				int cb, ce; uint32_t pb, pe;
 				locate(ref_len, n_ref, sl[g].beg, &cb, &pb); locate(ref_len, n_ref, sl[g].end, &ce, &pe);
 				const uint64_t v0 = bai_seek(&bai, cb, pb);
@@ -503,11 +524,16 @@ int main(int argc, char *argv[])
 		void *stage[2]; size_t scap[2];
 		for (int i = 0; i < 2; ++i) if ((rc = ngscov_staging(h, i, &stage[i], &scap[i]))) DIE("bam2bed: %s\n", ngscov_strerror(rc));
 
-		/* stream: [tail of the header blocks] then the remaining blocks, inflated in parallel into staging */
+		const int gpu_inflate = getenv("NGSCOV_GPU_INFLATE") && atoi(getenv("NGSCOV_GPU_INFLATE")) != 0;
 		long long t_io = 0;
+		if (gpu_inflate) {
+			/* the whole file goes to the device compressed; the inflated BAM header (hdr_len bytes) is skipped there */
+			if ((rc = ngscov_push_bgzf(h, file, off, hdr_len, NGSCOV_PUSH_LAST))) DIE("bam2bed: %s: %s (%s)\n", fn, ngscov_strerror(rc), ngscov_last_cuda_error(h));
+		}
+		/* stream: [tail of the header blocks] then the remaining blocks, inflated in parallel into staging */
 		int idx = 0; size_t b = hb;
 		size_t pending_hdr_tail = hbytes - hdr_len;            /* record bytes that came with the header blocks */
-		int first = 1, pushed_last = 0;
+		int first = 1, pushed_last = gpu_inflate;
 		while (!pushed_last) {
 			const long long t0 = usec();
 			if ((rc = ngscov_staging_wait(h, idx))) DIE("bam2bed: %s\n", ngscov_strerror(rc));
@@ -540,8 +566,8 @@ int main(int argc, char *argv[])
 		if (verbose) {
 			ngscov_stats_t st; ngscov_stats(h, &st);
 			fprintf(stderr, "ngscov: %llu records (%llu kept), %llu runs; host read+inflate %.3f s (%d threads); device: h2d %.3f ms ingest %.3f ms "
-			        "scan %.3f ms format %.3f ms d2h %.3f ms, %u kernel launches\n", (unsigned long long)st.records, (unsigned long long)st.kept,
-			        (unsigned long long)st.runs, t_io / 1e6, nthreads, st.ms_h2d, st.ms_ingest, st.ms_scan, st.ms_format, st.ms_d2h, st.launches);
+			        "scan %.3f ms format %.3f ms d2h %.3f ms, device inflate %.3f ms, %u kernel launches\n", (unsigned long long)st.records, (unsigned long long)st.kept,
+			        (unsigned long long)st.runs, t_io / 1e6, nthreads, st.ms_h2d, st.ms_ingest, st.ms_scan, st.ms_format, st.ms_d2h, st.ms_inflate, st.launches);
 		}
 		ngscov_destroy(h);
 		for (int k = 0; k < 4; ++k) if (outs[k]) fclose(outs[k]);

@@ -114,7 +114,7 @@ typedef struct {
 	/* device time per stage, CUDA events on the engine stream, summed over launches of this input */
 	float ms_zero, ms_ingest, ms_scan, ms_format, ms_h2d, ms_d2h;
 	uint32_t launches;             /* kernels launched for this input */
-	uint32_t reserved;
+	float ms_inflate;              /* device BGZF inflate (ngscov_push_bgzf), same clock as the stage times above */
 } ngscov_stats_t;
 
 int  ngscov_abi_version(void);
@@ -137,6 +137,12 @@ int ngscov_staging_wait(ngscov_t *h, int idx);
  * Records may straddle chunks and calls.  Returns when every chunk has been queued. */
 int ngscov_push_host(ngscov_t *h, const void *host_records, size_t nbytes, int flags);
 
+/* BGZF blocks exactly as they lie in the BAM file (host memory, whole blocks): the library walks the block headers,
+ * copies the COMPRESSED bytes to the device and inflates them there (one warp per block) into the chunk buffers the
+ * ingest kernels read -- the device-side replacement of samtools-0.1.19 bgzf.c:214-238 (inflate_block) /
+ * bgzf_read_block (bgzf.c:307-368).  `skip` inflated bytes at the start are dropped (the BAM header, or the in-block
+ * part of a BAI virtual offset).  Records may straddle calls like with ngscov_push_host. */
+int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, size_t skip, int flags);
 /* Submit records that already live in device memory (whole records only: the range must start and
  * end on record boundaries).  Used when the inflated stream is resident in HBM. */
 int ngscov_push_device(ngscov_t *h, const void *dev_records, size_t nbytes, int flags);

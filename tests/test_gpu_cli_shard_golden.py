@@ -50,8 +50,9 @@ def test_c_driver_writes_reference_identical_files(tmp_path, case, tool, window)
 
 @pytest.mark.parametrize("case,tool,window", [("random1", "depth", 150), ("random1", "wig", 150), ("c2_s0.0005", "depth", 20000),
                                               ("c4_s0.01", "wig", 100), ("c4_s0.01", "wig", 20000)])
-@pytest.mark.parametrize("shards", [2, 3, 7])
-def test_c_driver_region_shards_from_bai(tmp_path, case, tool, window, shards):
+@pytest.mark.parametrize("gpu_inflate", [0, 1])
+@pytest.mark.parametrize("shards", [1, 2, 3, 7])
+def test_c_driver_region_shards_from_bai(tmp_path, case, tool, window, shards, gpu_inflate):
     """NGSCOV_GPUS=N: every shard reads the BAM from the BAI linear-index offset of its slice, stops once the engine has
     seen a record behind the slice, and the stitched files equal the reference's (all shards on device 0 here)"""
     exe = os.path.join(ROOT, "highperformancengs_b200", "host", "bam2depth" if tool == "depth" else "bam2wig")
@@ -63,10 +64,13 @@ def test_c_driver_region_shards_from_bai(tmp_path, case, tool, window, shards):
     else:
         bamutil.write_bam(bam, names, lens, recs)
     args = [exe, "-o", str(tmp_path / "o"), "-w", str(window)] + (["-W"] if tool == "depth" else []) + [bam]
-    env = dict(os.environ, NGSCOV_STAGING_MB="1", NGSCOV_GPUS=str(shards), NGSCOV_DEVICES=",".join(["0"] * shards), NGSCOV_VERBOSE="1")
+    env = dict(os.environ, NGSCOV_STAGING_MB="1", NGSCOV_GPUS=str(shards), NGSCOV_DEVICES=",".join(["0"] * shards), NGSCOV_VERBOSE="1",
+               NGSCOV_GPU_INFLATE=str(gpu_inflate))
     r = subprocess.run(args, cwd=str(tmp_path), capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
-    assert r.stderr.count("ngscov: shard ") >= 2, r.stderr
+    assert shards == 1 or r.stderr.count("ngscov: shard ") >= 2, r.stderr
+    if gpu_inflate and shards == 1:
+        assert "device inflate 0.000 ms" not in r.stderr, r.stderr
     files = {"wig": "o.1.wig", "chromsize": "o.1.chromSize.txt"}
     if tool == "depth":
         files.update(bedgraph=os.path.basename(bam) + ".1.bedGraph", depth="o.1.depth")

@@ -193,3 +193,64 @@ def test_nine_digit_positions_and_name_lengths(oracle, monkeypatch, fmt):
     got = run_engine(names, lens, recs, 0, 20000)
     check(got, exp, 0, f"nine digits fmt={fmt}")
     assert b"\t100000" in got["bedgraph"] and b"\t99999" in got["bedgraph"]
+
+
+@pytest.mark.parametrize("staging", [0, 300000])
+@pytest.mark.parametrize("case", ["random", "c2", "c4", "c5", "stored"])
+def test_device_bgzf_inflate(oracle, tmp_path, case, staging):
+    """ngscov_push_bgzf: the BAM file's compressed blocks are inflated on the device (one warp per block) and feed the
+    same pipeline; outputs must equal the oracle's on the host-inflated stream.  `stored` = level-0 BGZF (stored
+    deflate blocks), `random` = zlib level 6 from Python (dynamic blocks), generator files = level 1."""
+    from highperformancengs_b200 import CoverageEngine, bamio
+    from highperformancengs_b200.gen import Generator
+    bam = str(tmp_path / "x.bam")
+    mode, window = 0, 500
+    if case in ("random", "stored"):
+        names, lens, reads = bamutil.random_case(31, n_reads=6000)
+        recs = bamutil.records(reads)
+        if case == "stored":
+            import zlib, struct
+            raw = bamutil.header_bytes(names, lens) + bytes(recs)
+            out = b""
+            for o in range(0, len(raw), 60000):
+                d = raw[o:o + 60000]
+                c = zlib.compressobj(0, zlib.DEFLATED, -15)
+                cd = c.compress(d) + c.flush()
+                out += struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, len(cd) + 25) + cd + struct.pack("<II", zlib.crc32(d), len(d))
+            open(bam, "wb").write(out)
+        else:
+            bamutil.write_bam(bam, names, lens, recs, index=False)
+    else:
+        cfgn, scale = {"c2": (2, 0.004), "c4": (4, 0.02), "c5": (5, 0.004)}[case]
+        g = Generator(cfgn, scale=scale)
+        g.write_bam(bam)
+        names, lens, recs = g.names, g.lens, g.records()
+        mode, window = (1, 100) if cfgn == 4 else (0, 20000)
+    data = open(bam, "rb").read()
+    inf = bamio.bgzf_inflate(data)
+    _, _, hdr_len = bamio.parse_header(inf)
+    assert bytes(inf[hdr_len:]) == bytes(recs)
+    exp = oracle.run(recs, names, lens, mode, window)
+    with CoverageEngine(names, lens, mode=mode, window=window, emit_wig=True, staging_bytes=staging) as eng:
+        eng.push_bgzf(data, skip=hdr_len, last=True)
+        eng.finish()
+        got = {"bedgraph": eng.output(0) if mode == 0 else b"", "depth": eng.output(1) if mode == 0 else b"", "wig": eng.output(2), "chromsize": eng.output(3)}
+        got["stats"] = eng.stats()
+    check(got, exp, mode, f"device inflate {case} staging={staging}")
+    assert got["stats"]["ms_inflate"] > 0
+
+
+def test_device_bgzf_inflate_rejects_corrupt_block(tmp_path):
+    from highperformancengs_b200 import CoverageEngine, NgscovError, bamio
+    names, lens, reads = bamutil.random_case(32, n_reads=3000)
+    bam = str(tmp_path / "x.bam")
+    bamutil.write_bam(bam, names, lens, bamutil.records(reads), index=False)
+    data = bytearray(open(bam, "rb").read())
+    _, _, hdr_len = bamio.parse_header(bamio.bgzf_inflate(bytes(data)))
+    for k in range(40, 60):
+        data[len(data) // 2 + k] ^= 0x5A          # damage the deflate stream of a block in the middle
+    with pytest.raises(NgscovError) as e:
+        with CoverageEngine(names, lens, mode=0, window=500) as eng:
+            eng.push_bgzf(bytes(data), skip=hdr_len, last=True)
+            eng.finish()
+    assert e.value.code == -4
