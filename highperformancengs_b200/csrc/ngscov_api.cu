@@ -64,7 +64,7 @@ struct ngscov {
 	/* runs */
 	uint32_t *d_run_start, *d_run_end; int *d_run_depth; size_t run_cap;
 	unsigned long long *d_rec_base, *d_stA, *d_stB, *d_fmt_status; size_t fmt_status_cap;
-	std::vector<unsigned long long> h_rec_base;
+	std::vector<unsigned long long> h_rec_base; unsigned long long *h_recb;   /* pinned landing area of the per-segment record offsets */
 	bool runs_done, formatted;
 	unsigned long long drop_idx, mod_idx; uint32_t mod_end;
 	ngscov_halo halo;
@@ -110,6 +110,7 @@ static float sum_events(std::vector<cudaEvent_t> &pool, size_t &used)
 	snprintf(h->cuda_err, sizeof h->cuda_err, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
 	return e__ == cudaErrorMemoryAllocation ? NGSCOV_ENOMEM : NGSCOV_ECUDA; } } while (0)
 
+static int small_d2h(ngscov *h, void *pinned, const void *dev, size_t nbytes);
 static void tic(ngscov *h) { cudaEventRecord(h->ev_t0, h->s_main); }
 static float toc(ngscov *h)
 {
@@ -282,6 +283,7 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	memset(h->h_tmpl, 0, sizeof(ngs_dev_state)); h->h_tmpl->first_run = ~0ull;
 	CK(cudaMalloc((void **)&h->d_ctr, NGS_CTR_STRIPES * 16 * 8));
 	CK(cudaHostAlloc((void **)&h->h_ctr, NGS_CTR_STRIPES * 16 * 8, cudaHostAllocDefault));
+	CK(cudaHostAlloc((void **)&h->h_recb, ((size_t)cfg->n_ref + 4) * 8, cudaHostAllocDefault));
 	h->stage_cap = cfg->staging_bytes ? (size_t)cfg->staging_bytes : (size_t)256 << 20;
 	/* Two ingest organisations are kept, both parity-tested: K1 record framing + K2 per-record decode (default:
 	 * 22.7 ms on config 2) and the single fused walk+decode kernel (NGSCOV_FUSED=1: 27.1 ms), DESIGN.md section 4. */
@@ -323,6 +325,7 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	for (int i = 0; i < 4; ++i) if (h->h_text[i]) cudaFreeHost(h->h_text[i]);
 	if (h->h_st) cudaFreeHost(h->h_st);
 	if (h->h_ctr) cudaFreeHost(h->h_ctr);
+	if (h->h_recb) cudaFreeHost(h->h_recb);
 	if (h->h_st2) cudaFreeHost(h->h_st2);
 	if (h->h_tmpl) cudaFreeHost(h->h_tmpl);
 	if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -449,6 +452,13 @@ static IngestArgs make_ingest_args(ngscov *h, const uint8_t *base, int64_t n, in
 	return A;
 }
 
+static int small_d2h(ngscov *h, void *pinned, const void *dev, size_t nbytes)
+{
+	k_to_host<<<1, 256, 0, h->s_main>>>((uint32_t *)pinned, (const uint32_t *)dev, (unsigned int)(nbytes / 4));
+	CK(cudaGetLastError());
+	return 0;
+}
+
 static int launch_verify(ngscov *h)
 {
 	const int64_t n_sub = h->p_nsub;
@@ -457,7 +467,11 @@ static int launch_verify(ngscov *h)
 	k_verify_scan<<<1, 1024, 0, h->s_main>>>(h->d_bmax, nb, h->d_st, h->p_fixed0, h->p_from_state ? 1 : 0);
 	k_verify_check<<<nb, 256, 0, h->s_main>>>(h->d_entry, h->d_exit, n_sub, h->d_bmax, h->shift, h->p_n, h->d_st);
 	h->stats.launches += 3;
-	CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
+	{ int r_ = small_d2h(h, h->h_st, h->d_st, sizeof(ngs_dev_state)); if (r_) return r_; }
+	/* the striped K2 counters travel with the same snapshot: both describe the chunks BEFORE this one (this chunk's K2
+	 * runs behind the verification), which is all the streamed finalize needs -- and it spares a second host
+	 * synchronisation per chunk */
+	{ int r_ = small_d2h(h, h->h_ctr, h->d_ctr, NGS_CTR_STRIPES * 16 * 8); if (r_) return r_; }
 	CK(cudaEventRecord(h->ev_verified, h->s_main));
 	CK(cudaGetLastError());
 	return 0;
@@ -495,11 +509,8 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 	h->pending = false;
 	/* sorted input: every contig below the highest refID decoded so far is complete */
 	if (allow_stream && h->stream_fin && (h->ingest_mode == 0 || h->ingest_mode == 3)) {
-		/* these variants count in striped counters (and K2 runs after the verification's state snapshot): take a
-		 * fresh snapshot and fold the stripes */
-		CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
-		CK(cudaMemcpyAsync(h->h_ctr, h->d_ctr, NGS_CTR_STRIPES * 16 * 8, cudaMemcpyDeviceToHost, h->s_main));
-		CK(cudaStreamSynchronize(h->s_main));
+		/* these variants count in striped counters: fold the stripes of the verification-time snapshot (K2 of the
+		 * chunks before this one; the contigs it reports complete were decoded entirely by those) */
 		for (int i = 0; i < NGS_CTR_STRIPES; ++i) h->h_st->m_ops += h->h_ctr[i * 16 + 2];
 	}
 	if (allow_stream && h->stream_fin && !(h->h_st->flags & (NGS_FLAG_EFORMAT | NGS_FLAG_ERANGE)) && h->h_st->max_ref_p1 > 1) {
@@ -655,6 +666,9 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 	if ((r = ensure_chunk(h, 0)) || (r = ensure_chunk(h, 1))) return r;
 	/* block table and chunk plan: whole blocks, at most stage_cap inflated bytes per chunk */
 	const uint8_t *src = (const uint8_t *)blocks;
+	const bool dbg = getenv("NGSCOV_DEBUG") != nullptr;
+	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t_parse = now(), t_res = 0, t_stage = 0, t_launch = 0;
 	struct Chunk { size_t b0, b1, c0, c1; size_t ulen; };
 	std::vector<ngs_bgzf_desc> desc; std::vector<Chunk> chunks;
 	{
@@ -674,6 +688,7 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 		c.b1 = desc.size(); c.c1 = off;
 		if (c.b1 > c.b0) chunks.push_back(c);
 	}
+	t_parse = now() - t_parse;
 	size_t total_u = 0;
 	for (const Chunk &c : chunks) total_u += c.ulen;
 	if (skip > total_u) return NGSCOV_EINVAL;
@@ -698,7 +713,8 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 			const size_t want = nb + nb / 8 + 64;
 			CK(cudaMalloc((void **)&h->d_desc[idx], want * sizeof(ngs_bgzf_desc))); h->desc_cap[idx] = want;
 		}
-		CK(cudaStreamWaitEvent(h->s_copy, h->ev_finalized, 0));
+		/* no device-side wait: the inflate that last read these two buffers precedes a verification the host has
+		 * already waited for */
 		CK(cudaEventRecord(next_event(h->ev_cp, h->n_cp), h->s_copy));
 		CK(cudaMemcpyAsync(h->d_comp[idx], src + c.c0, cb, cudaMemcpyHostToDevice, h->s_copy));
 		CK(cudaMemcpyAsync(h->d_desc[idx], desc.data() + c.b0, nb * sizeof(ngs_bgzf_desc), cudaMemcpyHostToDevice, h->s_copy));
@@ -712,8 +728,10 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 	cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->device);
 	for (size_t k = 0; k < chunks.size(); ++k, idx ^= 1) {
 		const Chunk &c = chunks[k];
-		if ((r = resolve_pending(h, true))) return r;                /* chunk k-1 verified, its buffers are free */
-		if (k + 1 < chunks.size() && (r = stage_in(k + 1, idx ^ 1))) return r;
+		/* the inflate of chunk k is queued BEFORE the host waits for the verification of chunk k-1: it depends on
+		 * nothing of it (other chunk buffer, no engine state), and it keeps the GPU busy while the host round trip --
+		 * wait, finalize k-1, copy k+1, frame k -- happens (measured: 4.5 ms of idle GPU per chunk otherwise) */
+		double t0 = now();
 		uint8_t *data = h->d_chunk[idx] + NGS_HEADROOM;
 		CK(cudaStreamWaitEvent(h->s_main, h->ev_h2d[idx], 0));
 		const uint32_t nb = (uint32_t)(c.b1 - c.b0);
@@ -723,6 +741,11 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 		CK(cudaEventRecord(next_event(h->ev_inf, h->n_inf), h->s_main));
 		h->stats.launches += 1;
 		CK(cudaGetLastError());
+		t_launch += now() - t0; t0 = now();
+		if ((r = resolve_pending(h, true))) return r;                /* chunk k-1 verified, its buffers are free */
+		t_res += now() - t0; t0 = now();
+		if (k + 1 < chunks.size() && (r = stage_in(k + 1, idx ^ 1))) return r;
+		t_stage += now() - t0; t0 = now();
 		const size_t sk = std::min(skip, c.ulen);
 		skip -= sk;
 		if (c.ulen == sk) continue;                                  /* header-only chunk */
@@ -735,7 +758,10 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 		k_place_carry<<<1, 256, 0, h->s_main>>>(data + sk, h->d_st, h->d_carry);
 		h->stats.launches += 1;
 		if ((r = submit_chunk(h, data + sk, (int64_t)(c.ulen - sk), true, 0))) return r;
+		t_launch += now() - t0;
 	}
+	if (dbg) fprintf(stderr, "ngscov_push_bgzf: %zu blocks, %zu chunks; host seconds: parse %.4f resolve %.4f stage_in %.4f launch %.4f\n",
+	                 desc.size(), chunks.size(), t_parse, t_res, t_stage, t_launch);
 	return 0;
 }
 
@@ -817,10 +843,11 @@ static int scan_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_b
 		h->stats.launches += 1;
 		CK(cudaGetLastError());
 	}
-	CK(cudaMemcpyAsync(h->h_st2, h->d_st, sizeof(ngs_dev_state), cudaMemcpyDeviceToHost, h->s_main));
-	h->h_rec_base.assign(h->seg.size() + 1, 0);
-	if (t1 > t0) CK(cudaMemcpyAsync(h->h_rec_base.data(), h->d_rec_base, (s1 - s0 + 1) * 8, cudaMemcpyDeviceToHost, h->s_main));
+	if ((r = small_d2h(h, h->h_st2, h->d_st, sizeof(ngs_dev_state)))) return r;
+	if (t1 > t0 && (r = small_d2h(h, h->h_recb, h->d_rec_base, (s1 - s0 + 1) * 8))) return r;
 	h->stats.ms_scan += toc(h);
+	h->h_rec_base.assign(h->seg.size() + 1, 0);
+	if (t1 > t0) memcpy(h->h_rec_base.data(), h->h_recb, (s1 - s0 + 1) * 8);
 	const ngs_dev_state &s2 = *h->h_st2;
 	h->acc_boundaries += s2.n_boundaries; h->acc_runs += s2.n_runs;
 	h->acc_max = std::max(h->acc_max, s2.max_depth); h->acc_min = std::min(h->acc_min, s2.min_depth);
@@ -873,6 +900,15 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 	}
 	h->stats.ms_ingest += sum_events(h->ev_ing, h->n_ing);
 	h->stats.ms_h2d += sum_events(h->ev_cp, h->n_cp);
+	if (getenv("NGSCOV_DEBUG") && h->n_inf >= 4) {
+		/* device timeline of the BGZF path: inflate kernels and what lies between them */
+		cudaEventSynchronize(h->ev_inf[h->n_inf - 1]);
+		float inf = 0, gap = 0, span = 0, g;
+		for (size_t i = 0; i + 1 < h->n_inf; i += 2) { cudaEventElapsedTime(&g, h->ev_inf[i], h->ev_inf[i + 1]); inf += g; }
+		for (size_t i = 1; i + 1 < h->n_inf; i += 2) { cudaEventElapsedTime(&g, h->ev_inf[i], h->ev_inf[i + 1]); gap += g; }
+		cudaEventElapsedTime(&span, h->ev_inf[0], h->ev_inf[h->n_inf - 1]);
+		fprintf(stderr, "ngscov: bgzf timeline: %zu inflate launches %.2f ms, between them %.2f ms, first..last %.2f ms\n", h->n_inf / 2, inf, gap, span);
+	}
 	h->stats.ms_inflate += sum_events(h->ev_inf, h->n_inf);
 	const ngs_dev_state st = *h->h_st;
 	h->stats.records = st.records; h->stats.kept = st.kept; h->stats.m_ops = st.m_ops; h->stats.cigar_words = st.cigar_words;
@@ -923,7 +959,7 @@ extern "C" int ngscov_slice_done(ngscov_t *h, int *done)
 	int r = resolve_pending(h);
 	if (r) return r;
 	unsigned int mr = 0;
-	CK(cudaMemcpyAsync(&h->h_st->max_ref_p1, &h->d_st->max_ref_p1, sizeof mr, cudaMemcpyDeviceToHost, h->s_main));
+	if ((r = small_d2h(h, &h->h_st->max_ref_p1, &h->d_st->max_ref_p1, sizeof mr))) return r;
 	CK(cudaStreamSynchronize(h->s_main));
 	mr = h->h_st->max_ref_p1;
 	*done = mr >= (unsigned int)h->end_ctg + 2u ? 1 : 0;
@@ -1071,7 +1107,7 @@ static int run_format(ngscov *h, int which, unsigned long long n_items, const Pr
 	h->stats.launches += 1;
 	CK(cudaGetLastError());
 	unsigned long long *fb = &h->h_st2->fmt_bytes;
-	CK(cudaMemcpyAsync(fb, &h->d_st->fmt_bytes, 8, cudaMemcpyDeviceToHost, h->s_main));
+	if ((r = small_d2h(h, fb, &h->d_st->fmt_bytes, 8))) return r;
 	h->stats.ms_format += toc(h);
 	if (*fb > h->d_text_cap[which] - out_off) return NGSCOV_ENOMEM;
 	h->text_len[which] = out_off + (size_t)*fb;
