@@ -735,7 +735,7 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 		uint8_t *data = h->d_chunk[idx] + NGS_HEADROOM;
 		CK(cudaStreamWaitEvent(h->s_main, h->ev_h2d[idx], 0));
 		const uint32_t nb = (uint32_t)(c.b1 - c.b0);
-		const unsigned grid = (unsigned)std::min<size_t>((nb + NGS_INF_WARPS - 1) / NGS_INF_WARPS, (size_t)sm * 6);
+		const unsigned grid = (unsigned)std::min<size_t>((nb + NGS_INF_WARPS - 1) / NGS_INF_WARPS, (size_t)sm * 9);
 		CK(cudaEventRecord(next_event(h->ev_inf, h->n_inf), h->s_main));
 		k_bgzf_inflate<<<grid, NGS_INF_WARPS * 32, 0, h->s_main>>>(h->d_comp[idx], h->d_desc[idx], nb, data, h->d_st);
 		CK(cudaEventRecord(next_event(h->ev_inf, h->n_inf), h->s_main));

