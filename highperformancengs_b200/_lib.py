@@ -34,7 +34,8 @@ class Stats(C.Structure):
                 ("stream_bytes", C.c_uint64), ("boundaries", C.c_uint64), ("runs", C.c_uint64), ("positions", C.c_uint64),
                 ("out_bytes", C.c_uint64 * 4), ("spec_subchunks", C.c_uint64), ("spec_repaired", C.c_uint64),
                 ("ms_zero", C.c_float), ("ms_ingest", C.c_float), ("ms_scan", C.c_float), ("ms_format", C.c_float),
-                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("launches", C.c_uint32), ("ms_inflate", C.c_float)]
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("launches", C.c_uint32), ("ms_inflate", C.c_float),
+                ("ms_decode", C.c_float), ("reserved2", C.c_float)]
 
 
 # every symbol include/ngscov.h declares: (restype, argtypes)

@@ -89,7 +89,7 @@ struct ngscov {
 	ngscov_stats_t stats;
 	int sm_count;
 	/* per-push timing events (start/end pairs), reused across inputs */
-	std::vector<cudaEvent_t> ev_ing, ev_cp, ev_inf; size_t n_ing, n_cp, n_inf;
+	std::vector<cudaEvent_t> ev_ing, ev_cp, ev_inf, ev_k2; size_t n_ing, n_cp, n_inf, n_k2;
 	uint8_t *d_comp[2]; size_t comp_cap[2]; ngs_bgzf_desc *d_desc[2]; size_t desc_cap[2];   /* BGZF blocks awaiting the device inflate */
 };
 
@@ -339,6 +339,7 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
 	for (cudaEvent_t e : h->ev_ing) cudaEventDestroy(e);
 	for (cudaEvent_t e : h->ev_inf) cudaEventDestroy(e);
+	for (cudaEvent_t e : h->ev_k2) cudaEventDestroy(e);
 	for (int i = 0; i < 2; ++i) { if (h->d_comp[i]) cudaFree(h->d_comp[i]); if (h->d_desc[i]) cudaFree(h->d_desc[i]); }
 	for (cudaEvent_t e : h->ev_cp) cudaEventDestroy(e);
 	delete h;
@@ -367,7 +368,7 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	memset(&h->halo, 0, sizeof h->halo); h->halo.first.contig = h->halo.last.contig = -1;
 	for (int i = 0; i < 4; ++i) { h->text_len[i] = 0; h->text_ready[i] = false; h->h_text_valid[i] = false; }
 	h->stage_busy[0] = h->stage_busy[1] = false;
-	h->n_ing = 0; h->n_cp = 0; h->n_inf = 0;
+	h->n_ing = 0; h->n_cp = 0; h->n_inf = 0; h->n_k2 = 0;
 	CK(cudaStreamSynchronize(h->s_out));
 	h->next_fin_seg = 0; h->mops_fin = 0; h->bins_zeroed = false; h->bed_off = 0; h->bed_d2h = 0;
 	h->acc_boundaries = h->acc_runs = 0; h->acc_max = h->acc_min = 0;
@@ -570,7 +571,9 @@ static int submit_chunk(ngscov *h, const uint8_t *base, int64_t n, bool from_sta
 	if (!r && !h->fused) {
 		/* K2 queued optimistically behind the verification: it returns at once if a mismatch was found,
 		 * and is then launched again by resolve_pending after the repair */
+		CK(cudaEventRecord(next_event(h->ev_k2, h->n_k2), h->s_main));
 		k_decode_scatter<<<(unsigned)((((uint64_t)n_sub << A.slot_shift) + 255) / 256), 256, 0, h->s_main>>>(A);
+		CK(cudaEventRecord(next_event(h->ev_k2, h->n_k2), h->s_main));
 		h->stats.launches += 1;
 		h->p_k2_done = true;
 		CK(cudaGetLastError());
@@ -910,6 +913,7 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 		fprintf(stderr, "ngscov: bgzf timeline: %zu inflate launches %.2f ms, between them %.2f ms, first..last %.2f ms\n", h->n_inf / 2, inf, gap, span);
 	}
 	h->stats.ms_inflate += sum_events(h->ev_inf, h->n_inf);
+	h->stats.ms_decode += sum_events(h->ev_k2, h->n_k2);
 	const ngs_dev_state st = *h->h_st;
 	h->stats.records = st.records; h->stats.kept = st.kept; h->stats.m_ops = st.m_ops; h->stats.cigar_words = st.cigar_words;
 	h->stats.spec_subchunks = st.spec_walks; h->stats.spec_repaired = st.spec_repaired;

@@ -431,8 +431,10 @@ __global__ void __launch_bounds__(256, 8) k_decode_scatter(IngestArgs A)
 	}
 	/* warp-level reduction, then one atomic per counter per warp into a stripe picked by the warp index (no
 	 * block barrier: this kernel does so little per thread that the barrier was 19 % of its stall samples) */
-	unsigned long long v0 = warp_sum_u64(cnt.records), v1 = warp_sum_u64(cnt.kept),
-	                   v2 = warp_sum_u64(cnt.m_ops), v3 = warp_sum_u64(cnt.cigar_words);
+	/* (32-bit REDUX: a thread decodes at most a sub-chunk's worth of records, the warp total stays far below 2^32;
+	 * four 64-bit shuffle trees here were 23 % of the kernel's instructions) */
+	const unsigned long long v0 = __reduce_add_sync(full, (unsigned)cnt.records), v1 = __reduce_add_sync(full, (unsigned)cnt.kept),
+	                         v2 = __reduce_add_sync(full, (unsigned)cnt.m_ops), v3 = __reduce_add_sync(full, (unsigned)cnt.cigar_words);
 	if ((threadIdx.x & 31) == 0 && v0) {
 		unsigned long long *c4 = A.ctr + (size_t)((tid >> 5) % NGS_CTR_STRIPES) * 16;
 		atomicAdd(c4 + 0, v0);

@@ -192,6 +192,6 @@ class CoverageEngine:
     def stats(self):
         s = L.Stats()
         self._check(self.lib.ngscov_stats(self.h, C.byref(s)), "ngscov_stats")
-        d = {k: getattr(s, k) for k, _ in L.Stats._fields_ if k not in ("out_bytes", "reserved")}
+        d = {k: getattr(s, k) for k, _ in L.Stats._fields_ if k not in ("out_bytes", "reserved", "reserved2")}
         d["out_bytes"] = list(s.out_bytes)
         return d

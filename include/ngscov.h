@@ -115,6 +115,8 @@ typedef struct {
 	float ms_zero, ms_ingest, ms_scan, ms_format, ms_h2d, ms_d2h;
 	uint32_t launches;             /* kernels launched for this input */
 	float ms_inflate;              /* device BGZF inflate (ngscov_push_bgzf), same clock as the stage times above */
+	float ms_decode;               /* the K2 (record decode + delta scatter) part of ms_ingest; the rest is K1 framing + verification */
+	float reserved2;
 } ngscov_stats_t;
 
 int  ngscov_abi_version(void);
