@@ -85,11 +85,33 @@ def _run(argv, depth_mode):
         if bamio.find_bai(fn) is None:
             sys.stderr.write("bam2bed: BAM indexing file is not available.\n")
             raise SystemExit(1)
-        names, lens, records = bamio.load_bam(fn)
+        gpu_inflate = os.environ.get("NGSCOV_GPU_INFLATE", "0") not in ("", "0")
+        if gpu_inflate:
+            # like the C drivers with NGSCOV_GPU_INFLATE=1: only the header blocks are inflated on the host
+            import zlib
+            with open(fn, "rb") as f:
+                raw = f.read()
+            inf, hdr = b"", None
+            for off, bs in bamio.bgzf_blocks(raw):
+                inf += zlib.decompress(raw[off + 18:off + bs - 8], -15)
+                try:
+                    hdr = bamio.parse_header(inf)
+                    break
+                except Exception:
+                    continue
+            if hdr is None:
+                sys.stderr.write(f"bam2bed: {fn} has no BAM header\n")
+                raise SystemExit(1)
+            names, lens, hdr_len = hdr
+        else:
+            names, lens, records = bamio.load_bam(fn)
         eng = CoverageEngine(names, lens, mode=MODE_DEPTH if depth_mode else MODE_WIG, window=window,
                              emit_wig=bool(wig), device=int(os.environ.get("NGSCOV_DEVICE", "0")))
         try:
-            eng.push_host(records, last=True)
+            if gpu_inflate:
+                eng.push_bgzf(raw, skip=hdr_len, last=True)
+            else:
+                eng.push_host(records, last=True)
             eng.finish()
             for which, f in streams.items():
                 f.write(eng.output(which))

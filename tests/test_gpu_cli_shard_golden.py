@@ -78,6 +78,29 @@ def test_c_driver_region_shards_from_bai(tmp_path, case, tool, window, shards, g
     check_against_gold(got, f"{case}|{tool}|{window}")
 
 
+@pytest.mark.parametrize("gpu_inflate", ["0", "1"])
+@pytest.mark.parametrize("case,tool,window", [("random1", "depth", 150), ("c4_s0.01", "wig", 100)])
+def test_python_cli_mirror(tmp_path, monkeypatch, case, tool, window, gpu_inflate):
+    """highperformancengs_b200.cli (ctypes mirror of the C drivers): same files as the reference, host or device inflate"""
+    from highperformancengs_b200 import cli
+    spec = [c for c in cases.CASES if c[0] == case][0]
+    names, lens, recs, g = cases.case_input(spec[1], spec[2])
+    bam = str(tmp_path / (case + ".bam"))
+    if g is not None:
+        g.write_bam(bam)
+    else:
+        bamutil.write_bam(bam, names, lens, recs)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("NGSCOV_GPU_INFLATE", gpu_inflate)
+    argv = ["bam2depth" if tool == "depth" else "bam2wig", "-o", "o", "-w", str(window)] + (["-W"] if tool == "depth" else []) + [bam]
+    assert (cli.bam2depth if tool == "depth" else cli.bam2wig)(argv) in (0, None)
+    files = {"wig": "o.1.wig", "chromsize": "o.1.chromSize.txt"}
+    if tool == "depth":
+        files.update(bedgraph=os.path.basename(bam) + ".1.bedGraph", depth="o.1.depth")
+    got = {k: open(str(tmp_path / p), "rb").read() for k, p in files.items()}
+    check_against_gold(got, f"{case}|{tool}|{window}")
+
+
 def _sharded(names, lens, recs, mode, window, n):
     """n engines on one GPU, each owning a genome slice but fed the whole stream (deltas are clipped)."""
     from highperformancengs_b200 import CoverageEngine, shard
