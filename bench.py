@@ -351,7 +351,10 @@ def main():
             # (ngscov_push_bgzf).  This is what the reference arm does from its file, inflate included.
             from highperformancengs_b200 import bamio
             import zlib
-            tdir = tempfile.mkdtemp(prefix="ngscov_bgzf_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            import shutil
+            need = int(nbytes * 0.2) + (1 << 30)          # the BAM is ~1/8 of the stream at zlib level 1
+            shm_ok = os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need
+            tdir = tempfile.mkdtemp(prefix="ngscov_bgzf_", dir="/dev/shm" if shm_ok else None)
             try:
                 bam = os.path.join(tdir, "bench.bam")
                 t0 = time.time()
@@ -361,7 +364,6 @@ def main():
                 with open(bam, "rb") as f:
                     f.readinto(memoryview(comp.numpy()))
             finally:
-                import shutil
                 shutil.rmtree(tdir, ignore_errors=True)
             inf, hdr_len = b"", None
             for off, bs in bamio.bgzf_blocks(memoryview(comp.numpy()[:8 << 20])):
