@@ -456,6 +456,7 @@ static IngestArgs make_ingest_args(ngscov *h, const uint8_t *base, int64_t n, in
 static int small_d2h(ngscov *h, void *pinned, const void *dev, size_t nbytes)
 {
 	k_to_host<<<1, 256, 0, h->s_main>>>((uint32_t *)pinned, (const uint32_t *)dev, (unsigned int)(nbytes / 4));
+	h->stats.launches += 1;
 	CK(cudaGetLastError());
 	return 0;
 }
