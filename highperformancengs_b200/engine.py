@@ -159,6 +159,17 @@ class CoverageEngine:
         self._check(self.lib.ngscov_runs_get(self.h, arr, n.value, C.byref(n)), "ngscov_runs_get")
         return [(r.contig, r.start, r.end, r.depth) for r in arr[:n.value]]
 
+    RUN_DTYPE = np.dtype([("contig", "<i4"), ("start", "<u4"), ("end", "<u4"), ("depth", "<i4")])
+
+    def runs_array(self):
+        """the binary run records as a numpy structured array (contig, start, end, depth) -- ngscov_runs_get without
+        building Python objects (tens of millions of runs)"""
+        n = C.c_uint64()
+        self._check(self.lib.ngscov_runs_get(self.h, None, 0, C.byref(n)), "ngscov_runs_get")
+        out = np.zeros(max(1, n.value), dtype=self.RUN_DTYPE)
+        self._check(self.lib.ngscov_runs_get(self.h, C.cast(out.ctypes.data, C.POINTER(L.Run)), n.value, C.byref(n)), "ngscov_runs_get")
+        return out[:n.value]
+
     def slice_done(self):
         """region shard: True once a record at or beyond the end of the slice has been decoded (synchronises)"""
         d = C.c_int(0)

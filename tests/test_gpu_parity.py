@@ -254,3 +254,80 @@ def test_device_bgzf_inflate_rejects_corrupt_block(tmp_path):
             eng.push_bgzf(bytes(data), skip=hdr_len, last=True)
             eng.finish()
     assert e.value.code == -4
+
+
+def test_large_scale_properties(tmp_path):
+    """Size-independent properties at a size the oracle cannot reach (config 2, NGSCOV_TEST_SCALE of the 30x genome,
+    default 0.1 = 62 M reads; 1.0 = the full benchmark input): the runs are sorted, disjoint, maximal, non-zero and
+    inside their contigs; the two accumulators agree (sum of depth over runs == sum of the window bins, per window);
+    the bedGraph text has exactly one line per run and exactly the length the runs' digit counts predict; its first and
+    last lines are the first and last runs; and the same bytes come out when the input is the compressed BAM inflated
+    on the device."""
+    import zlib
+    import torch
+    from highperformancengs_b200 import CoverageEngine, bamio
+    from highperformancengs_b200.gen import Generator
+    scale = float(os.environ.get("NGSCOV_TEST_SCALE", "0.1"))
+    W = 20000
+    g = Generator(2, scale=scale, seq=False)
+    recs = g.records()
+    dev = torch.from_numpy(recs).cuda()
+    torch.cuda.synchronize()
+    lens = np.asarray(g.lens, dtype=np.int64)
+    with CoverageEngine(g.names, g.lens, mode=0, window=W) as eng:
+        eng.push_device(dev.data_ptr(), dev.numel(), last=True)
+        eng.finish()
+        runs = eng.runs_array()
+        bins = eng.bins().astype(np.int64)
+        bed = np.array(eng.output_view(0), copy=True)
+        st = eng.stats()
+    del dev
+    c, s, e, d = runs["contig"].astype(np.int64), runs["start"].astype(np.int64), runs["end"].astype(np.int64), runs["depth"].astype(np.int64)
+    assert st["records"] == g.n_reads and len(runs) == st["runs"] and len(runs) > 0
+    # structure of the run list
+    assert (e > s).all() and (d > 0).all() and (c >= 0).all() and (e <= lens[c]).all()
+    same = c[1:] == c[:-1]
+    assert (c[1:] >= c[:-1]).all() and (s[1:][same] >= e[:-1][same]).all()
+    abut = same & (s[1:] == e[:-1])
+    assert (d[1:][abut] != d[:-1][abut]).all(), "two abutting runs of equal depth: not maximal"
+    # the window bins, recomputed from the runs (variant A: exact sum of depth over the bases of each window)
+    n_win = lens // W + 1
+    win0 = np.concatenate([[0], np.cumsum(n_win)])[:-1]
+    k0, k1 = s // W, (e - 1) // W
+    exp_bins = np.zeros(int(n_win.sum()), dtype=np.int64)
+    one = k0 == k1
+    np.add.at(exp_bins, win0[c[one]] + k0[one], (e[one] - s[one]) * d[one])
+    for ci, si, ei, di, a, b in zip(c[~one], s[~one], e[~one], d[~one], k0[~one], k1[~one]):      # runs crossing a window edge: few
+        for k in range(a, b + 1):
+            lo, hi = max(si, k * W), min(ei, (k + 1) * W)
+            exp_bins[win0[ci] + k] += (hi - lo) * di
+    assert int(bins.sum()) == int(((e - s) * d).sum())
+    assert (bins == exp_bins).all()
+    # the text: one line per run, and exactly as long as the digit counts say
+    p10 = 10 ** np.arange(1, 11, dtype=np.int64)
+    dig = lambda v: np.searchsorted(p10, v, side="right") + 1
+    name_len = np.asarray([len(n) for n in g.names], dtype=np.int64)
+    assert int((name_len[c] + dig(s) + dig(e) + dig(d) + 4).sum()) == bed.size
+    assert int((bed == 10).sum()) == len(runs)
+    head = bytes(bed[:200000]).split(b"\n")[:1000]
+    tail = bytes(bed[-200000:]).split(b"\n")[-1001:-1]
+    fmt = lambda i: b"%s\t%d\t%d\t%d" % (g.names[c[i]], s[i], e[i], d[i])
+    assert head == [fmt(i) for i in range(1000)]
+    assert tail == [fmt(i) for i in range(len(runs) - 1000, len(runs))]
+    # the same bytes from the BAM file's compressed blocks (device inflate)
+    ref_sum = zlib.adler32(bed)
+    bam = str(tmp_path / "big.bam")
+    g.write_bam(bam)
+    raw = np.fromfile(bam, dtype=np.uint8)
+    inf, hdr_len = b"", None
+    for off, bs in bamio.bgzf_blocks(memoryview(raw[:8 << 20])):
+        inf += zlib.decompress(bytes(raw[off + 18:off + bs - 8]), -15)
+        try:
+            hdr_len = bamio.parse_header(inf)[2]
+            break
+        except Exception:
+            continue
+    with CoverageEngine(g.names, g.lens, mode=0, window=W) as eng:
+        eng.push_bgzf(raw, skip=hdr_len, last=True)
+        eng.finish()
+        assert zlib.adler32(np.array(eng.output_view(0), copy=False)) == ref_sum
