@@ -159,6 +159,7 @@ static void *shard_worker(void *arg)
 	/* blocks are inflated by a private copy of the table entries (dst differs per shard; shards may overlap at their ends) */
 	size_t b = s->b_first, limit = s->to_eof ? s->nblk : (s->b_bound + 1 < s->nblk ? s->b_bound + 1 : s->nblk);
 	int idx = 0, first = 1, last = s->empty;
+	if (limit < b) limit = b;            /* the first record at or behind the slice start already lies behind its end bound */
 	if (s->gpu_inflate && !s->empty) {
 		/* compressed blocks [b, limit) go to the device as they lie in the file; extend while the slice is not done */
 		size_t skip = s->uoff;
