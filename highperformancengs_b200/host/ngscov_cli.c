@@ -167,8 +167,10 @@ static void *shard_worker(void *arg)
 			const uint8_t *p0 = s->blk[b].src - 18;
 			const uint8_t *p1 = limit < s->nblk ? s->blk[limit].src - 18 : s->file_end;
 			const int eof = limit >= s->nblk;
-			if ((rc = ngscov_push_bgzf(s->h, p0, (size_t)(p1 - p0), skip, eof ? NGSCOV_PUSH_LAST : 0))) break;
-			skip = 0; b = limit;
+			const size_t nb = (size_t)(p1 - p0);
+			if ((rc = ngscov_push_bgzf(s->h, p0, nb, nb ? skip : 0, eof ? NGSCOV_PUSH_LAST : 0))) break;
+			if (nb) skip = 0;
+			b = limit;
 			if (eof) { last = 1; break; }
 			int done = 0;
 			if ((rc = ngscov_slice_done(s->h, &done))) break;
