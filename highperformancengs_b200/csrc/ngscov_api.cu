@@ -79,6 +79,7 @@ struct ngscov {
 	 * of the rest of the stream */
 	bool stream_fin; size_t next_fin_seg; unsigned long long mops_fin; bool bins_zeroed;
 	int32_t end_ctg; uint32_t end_pos;          /* first position behind the slice (end_ctg = -2: whole genome) */
+	double fin_wall; int fin_calls;             /* host time spent in streamed finalizes (NGSCOV_DEBUG) */
 	size_t bed_off;                          /* bedGraph bytes produced so far */
 	size_t bed_d2h;                          /* ... of which already queued for D2H */
 	ngs_dev_state *h_st2;                    /* pinned read-back of the state block after scan / format launches */
@@ -863,13 +864,12 @@ static int scan_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_b
 static int format_bed_range(ngscov *h, size_t s0, size_t s1);
 
 /* Finalize segments [next_fin_seg, seg_end) while the rest of the stream is still arriving. */
-static double g_fin_wall = 0; static int g_fin_calls = 0;
 static int stream_finalize_impl(ngscov *h, size_t seg_end);
 static int stream_finalize(ngscov *h, size_t seg_end)
 {
 	const auto t0 = std::chrono::steady_clock::now();
 	const int r = stream_finalize_impl(h, seg_end);
-	g_fin_wall += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++g_fin_calls;
+	h->fin_wall += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++h->fin_calls;
 	return r;
 }
 static int stream_finalize_impl(ngscov *h, size_t seg_end)
@@ -949,7 +949,7 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 			}
 		}
 	}
-	if (getenv("NGSCOV_DEBUG")) { fprintf(stderr, "ngscov: streamed finalize: %d calls, %.3f s host wall\n", g_fin_calls, g_fin_wall); g_fin_wall = 0; g_fin_calls = 0; }
+	if (getenv("NGSCOV_DEBUG")) { fprintf(stderr, "ngscov: streamed finalize: %d calls, %.3f s host wall\n", h->fin_calls, h->fin_wall); h->fin_wall = 0; h->fin_calls = 0; }
 	h->runs_done = true;
 	return 0;
 }
