@@ -446,6 +446,118 @@ typedef struct {
 	uint32_t end_pos;            /* (end_ctg = -2: no slice).  Such a record counts as "the next contig has begun" */
 } ngs_walk_cfg;
 
+/* ---- compact record table (K1 -> K2) --------------------------------------------------------------
+ * K1 (k_chain_walk) frames AND decodes: every record that contributes at least one M interval leaves one
+ * 8-byte entry in the row of the sub-chunk it starts in, so that K2 never reads the stream again for
+ * ordinary records:
+ *   x = pos (29 bits, the record's POS) | cdelta << 29   (contig = row_ctg[row] + cdelta, cdelta 0..6)
+ *   y = kind << 30 | payload
+ *       SIMPLE  payload = len               one interval [pos, pos+len)  (abutting M ops are merged: the
+ *                                           zero-net deltas between them are transparent to the sweep)
+ *       PAIR    payload = len1 | gap << 12 | len2 << 18   [pos, pos+len1) and [pos+len1+gap, .. +len2)
+ *       CHAIN   payload = byte offset of the record from the row's entry point: decode it from the stream
+ *                         (long CIGARs, leading D/N, 28-bit key aliasing, more than six contigs in a row)
+ * Deltas are applied by the OWNER of the tile they fall into (k_owner_tiles: plain stores, no atomics on
+ * HBM) when the record is "near": the owner of tile T sees every record of its contig with
+ * P0(T) - NGS_NEAR_H <= pos < P0(T) + tile size.  Every other delta is "far" and is added afterwards with
+ * a RED (k_far_reds).  Both kernels evaluate ngs_delta_is_near, so each delta is applied exactly once. */
+#define NGS_ENT_SIMPLE  0u
+#define NGS_ENT_PAIR    1u
+#define NGS_ENT_CHAIN   2u
+#define NGS_ENT_CDELTA_MAX 6u
+#define NGS_NEAR_H      512            /* positions before a tile from which records are visible to its owner */
+#define NGS_OWN_TILE    8192           /* positions per owner tile (k_owner_tiles); multiple of NGS_TILE */
+#define NGS_TILE        2048           /* positions per scan tile (k_scan_emit); per-tile aggregates have this grain */
+#define NGS_KEY_NONE    0xFFFFFFFFFFFFFFFFull
+
+/* sort key of a record: samtools sorts by (refID as unsigned, pos); unmapped (refID -1) sort last */
+NGS_HD uint64_t ngs_sort_key(int32_t ref_id, int32_t pos) { return ((uint64_t)(uint32_t)ref_id << 32) | (uint32_t)(pos + 1); }
+
+/* one M interval [a, b) in RAW contig coordinates -> clipped element range of the segment; returns 0 when it
+ * contributes nothing.  Exactly the arithmetic of ngs_decode_record (28-bit keys, clip to the shard, hard end). */
+NGS_HD int ngs_clip_interval(const ngs_seg &sg, uint32_t a_raw, uint32_t b_raw, uint32_t &a, uint32_t &b, int &range_error)
+{
+	a = a_raw & NGS_POS_MASK; b = b_raw & NGS_POS_MASK;
+	if (a == b) return 0;
+	if (b < a) { range_error = 1; return 0; }
+	if (b > sg.lim) {
+		if (sg.hard_end) { range_error = 1; return 0; }
+		b = sg.lim;
+	}
+	if (a < sg.clip_lo) a = sg.clip_lo;
+	return a < b;
+}
+/* Is the delta at (clipped) contig position q of a record starting at rec_pos applied by the owner of q's tile?
+ * `aliased`: the record touches positions >= 2^28 (its keys wrap, so its deltas are not where the sort order says). */
+NGS_HD int ngs_delta_is_near(const ngs_seg &sg, uint32_t rec_pos, uint32_t q, int aliased)
+{
+	if (aliased) return 0;
+	const int64_t p0 = (int64_t)sg.clip_lo + (int64_t)((q - sg.clip_lo) / NGS_OWN_TILE) * NGS_OWN_TILE;
+	return (int64_t)rec_pos >= p0 - NGS_NEAR_H;
+}
+
+/* Intervals of a SIMPLE / PAIR entry in raw coordinates: n = 1 or 2 */
+NGS_HD int ngs_entry_intervals(uint32_t pos, uint32_t y, uint32_t a[2], uint32_t b[2])
+{
+	const uint32_t kind = y >> 30, pl = y & 0x3FFFFFFFu;
+	a[0] = pos;
+	if (kind == NGS_ENT_SIMPLE) { b[0] = pos + pl; return 1; }
+	b[0] = pos + (pl & 0xFFFu);
+	a[1] = b[0] + ((pl >> 12) & 0x3Fu);
+	b[1] = a[1] + (pl >> 18);
+	return 2;
+}
+
+/* What K1 learns about one record (Cig(i) returns CIGAR word i).  ret: 0 = no entry (filtered / nothing to count);
+ * 1 = entry (x_pos, y) to store.  end_raw = reference end of the last M interval (for the tile plan), far = the
+ * record may own a far delta.  Counters as ngs_decode_record. */
+template <class Cig>
+NGS_HD int ngs_classify_record(const ngs_walk_cfg &cfg, const ngs_hdr &h, uint32_t slot_off, Cig &cig,
+                               uint32_t &y, uint32_t &end_raw, int &far, ngs_counts &cnt)
+{
+	cnt.records += 1; cnt.cigar_words += h.n_cigar;
+	{
+		uint32_t r1 = (uint32_t)(h.ref_id + 1);
+		if (h.ref_id == cfg.end_ctg && (uint32_t)h.pos >= cfg.end_pos) r1 += 1;
+		if (r1 > cnt.max_ref_p1) cnt.max_ref_p1 = r1;
+	}
+	if ((h.flag & cfg.flag_mask) || h.ref_id < 0 || (uint32_t)h.pos >= (1u << 29)) return 0;
+	cnt.kept += 1;
+	const int32_t si = cfg.ctg2seg[h.ref_id];
+	if (si < 0 || h.n_cigar == 0) return 0;
+	/* walk the CIGAR: intervals with abutting ones merged */
+	uint32_t p = (uint32_t)h.pos, na = 0, ia[2] = { 0, 0 }, ib[2] = { 0, 0 };
+	uint32_t ca = 0, cb = 0; int open = 0;
+	for (uint32_t i = 0; i < h.n_cigar; ++i) {
+		const uint32_t w = cig(i), op = w & 0xf, len = w >> 4;
+		if (op == 0) {
+			if (len == 0) continue;
+			if (open && cb == p) cb = p + len;
+			else {
+				if (open) { if (na < 2) { ia[na] = ca; ib[na] = cb; } ++na; }
+				ca = p; cb = p + len; open = 1;
+			}
+			p += len;
+		} else if (op == 2 || op == 3) p += len;
+	}
+	if (!open) return 0;                                 /* no M at all */
+	if (na < 2) { ia[na] = ca; ib[na] = cb; }
+	++na;
+	end_raw = cb;
+	const ngs_seg &sg = cfg.seg[si];
+	const int aliased = cb > NGS_POS_MASK || cb < (uint32_t)h.pos;     /* wraps the 28-bit keys (or 32 bits) */
+	far = aliased || (uint32_t)h.pos + NGS_NEAR_H < sg.clip_lo || cb - (uint32_t)h.pos > NGS_NEAR_H;
+	if (!aliased && ia[0] == (uint32_t)h.pos) {
+		if (na == 1 && ib[0] - ia[0] < (1u << 30)) { y = (NGS_ENT_SIMPLE << 30) | (ib[0] - ia[0]); return 1; }
+		if (na == 2 && ib[0] - ia[0] < 4096u && ia[1] - ib[0] < 64u && ib[1] - ia[1] < 4096u) {
+			y = (NGS_ENT_PAIR << 30) | (ib[0] - ia[0]) | ((ia[1] - ib[0]) << 12) | ((ib[1] - ia[1]) << 18);
+			return 1;
+		}
+	}
+	y = (NGS_ENT_CHAIN << 30) | slot_off;
+	return 1;
+}
+
 /* decode one (already validated) record at offset o and emit its deltas with weight `sign` */
 template <class Mem, class Sink>
 NGS_HD void ngs_decode_record(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o, const ngs_hdr &h,
@@ -458,7 +570,7 @@ NGS_HD void ngs_decode_record(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o
 		if (h.ref_id == cfg.end_ctg && (uint32_t)h.pos >= cfg.end_pos) r1 += 1;
 		if (r1 > cnt.max_ref_p1) cnt.max_ref_p1 = r1;
 	}
-	if ((h.flag & cfg.flag_mask) || h.ref_id < 0 || h.pos >= (1 << 29)) return;
+	if ((h.flag & cfg.flag_mask) || h.ref_id < 0 || (uint32_t)h.pos >= (1u << 29)) return;   /* bam_fetch's is_overlap compares as uint32 (samtools bam_index.c:571-576) */
 	cnt.kept += 1;
 	const int32_t si = cfg.ctg2seg[h.ref_id];
 	if (si < 0 || h.n_cigar == 0) return;
