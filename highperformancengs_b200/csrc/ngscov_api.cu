@@ -4,7 +4,7 @@
  * data runs in the kernels of ngscov_kernels.cuh.
  */
 #include "../../include/ngscov.h"
-#include "ngscov_kernels.cuh"
+#include "ngscov_cover.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -87,6 +87,20 @@ struct ngscov {
 	cudaStream_t s_out; cudaEvent_t ev_fmt;
 	unsigned long long acc_boundaries, acc_runs; int acc_max, acc_min;
 
+	/* cover pipeline (ngscov_cover.cuh): compact record table, rows appended chunk after chunk */
+	bool cover;                              /* default; false: the classic RED + scan + format kernels (NGSCOV_PIPELINE=classic or any NGSCOV_INGEST) */
+	bool red_mode;                           /* cover pipeline fell back to REDs + classic scan: the input is not coordinate sorted */
+	uint2 *d_ent; ngs_row *d_rows; unsigned long long *d_rkmax; size_t rows_cap, rows_used;
+	size_t p_row0;                           /* first global row of the pending chunk */
+	unsigned long long *d_kbmax;
+	uint32_t *d_far_flag, *d_row_a, *d_row_b;
+	unsigned long long *d_stF;
+	uint4 *d_tile_first, *d_tile_last;
+	bool halo_have; ngscov_run cov_first, cov_last;   /* first / last non-zero run over the cover launches so far */
+	size_t bed_begin;                        /* halo: bytes of the dropped first line */
+	std::string bed_tail; size_t bed_tail_old; /* halo: replacement of the last line, and how many bytes it replaces */
+	bool bed_patched;
+
 	ngscov_stats_t stats;
 	int sm_count;
 	/* per-push timing events (start/end pairs), reused across inputs */
@@ -135,6 +149,7 @@ extern "C" const char *ngscov_strerror(int code)
 	case NGSCOV_ERANGE: return "alignment reaches beyond contig end + overhang pad";
 	case NGSCOV_ESTATE: return "call sequence violated";
 	case NGSCOV_ETOOBIG: return "record header larger than the carry area";
+	case NGSCOV_EUNSORTED: return "input is not coordinate sorted";
 	default: return "unknown error";
 	}
 }
@@ -306,6 +321,15 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 		h->ingest_mode = !strcmp(m, "fused") ? 1 : !strcmp(m, "tiles") ? 2 : !strcmp(m, "tiles2") ? 3 : 0;
 	}
 	h->fused = h->ingest_mode != 0;
+	h->cover = !(getenv("NGSCOV_INGEST") || getenv("NGSCOV_FUSED") || (getenv("NGSCOV_PIPELINE") && !strcmp(getenv("NGSCOV_PIPELINE"), "classic")));
+	if (h->cover) {
+		const size_t nt = std::max<uint64_t>(1, h->n_tiles);
+		CK(cudaMalloc((void **)&h->d_far_flag, nt * 4)); CK(cudaMemset(h->d_far_flag, 0, nt * 4));
+		CK(cudaMalloc((void **)&h->d_row_a, nt * 4)); CK(cudaMalloc((void **)&h->d_row_b, nt * 4));
+		CK(cudaMalloc((void **)&h->d_stF, nt * 8));
+		CK(cudaMalloc((void **)&h->d_tile_first, nt * 16)); CK(cudaMalloc((void **)&h->d_tile_last, nt * 16));
+		h->h_tmpl->first_tile = ~0ull;
+	}
 	h->shift = 0;
 	const char *env = getenv("NGSCOV_SUBCHUNK");
 	if (env && atoi(env) >= 64) { int v = atoi(env), s = 6; while ((1 << (s + 1)) <= v) ++s; h->shift = s; }
@@ -320,7 +344,8 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	void *dev[] = { h->d_seg, h->d_ctg2seg, h->d_tile2seg, h->d_ref_len, h->d_win_base, h->d_diff, h->d_bins, h->d_names, h->d_name8,
 	                h->d_name_off, h->d_wighdr, h->d_wighdr_off, h->d_chunk[0], h->d_chunk[1], h->d_carry, h->d_entry, h->d_exit,
 	                h->d_bmax, h->d_count, h->d_slots, h->d_ctr, h->d_st, h->d_run_start, h->d_run_end, h->d_run_depth, h->d_rec_base, h->d_stA, h->d_stB,
-	                h->d_fmt_status, h->d_text[0], h->d_text[1], h->d_text[2], h->d_text[3] };
+	                h->d_fmt_status, h->d_text[0], h->d_text[1], h->d_text[2], h->d_text[3],
+	                h->d_ent, h->d_rows, h->d_rkmax, h->d_kbmax, h->d_far_flag, h->d_row_a, h->d_row_b, h->d_stF, h->d_tile_first, h->d_tile_last };
 	for (void *p : dev) if (p) cudaFree(p);
 	for (int i = 0; i < 2; ++i) if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
 	for (int i = 0; i < 4; ++i) if (h->h_text[i]) cudaFreeHost(h->h_text[i]);
@@ -353,6 +378,7 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	CK(cudaStreamSynchronize(h->s_main)); CK(cudaStreamSynchronize(h->s_copy));
 	if (h->diff_dirty) {            /* pushes were made but the scan (which re-zeroes) never ran */
 		tic(h);
+		if (h->d_far_flag) CK(cudaMemsetAsync(h->d_far_flag, 0, std::max<uint64_t>(1, h->n_tiles) * 4, h->s_main));
 		CK(cudaMemsetAsync(h->d_diff, 0, h->n_elems * sizeof(int), h->s_main));
 		h->stats.ms_zero = toc(h);
 		h->diff_dirty = false;
@@ -373,6 +399,8 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	CK(cudaStreamSynchronize(h->s_out));
 	h->next_fin_seg = 0; h->mops_fin = 0; h->bins_zeroed = false; h->bed_off = 0; h->bed_d2h = 0;
 	h->acc_boundaries = h->acc_runs = 0; h->acc_max = h->acc_min = 0;
+	h->rows_used = 0; h->red_mode = false; h->halo_have = false;
+	h->bed_begin = 0; h->bed_tail.clear(); h->bed_tail_old = 0; h->bed_patched = false;
 	return 0;
 }
 
@@ -420,7 +448,7 @@ static int ensure_sub(ngscov *h, int64_t n_sub)
 		CK(cudaMalloc((void **)&h->d_count, cap * 4));
 		h->sub_cap = cap;
 	}
-	if (h->ingest_mode == 0) {
+	if (h->ingest_mode == 0 && !h->cover) {
 		const size_t need = ((size_t)n_sub << (h->shift - 5)) + 64;
 		if (need > h->slots_cap) {
 			CK(cudaStreamSynchronize(h->s_main));
@@ -434,9 +462,31 @@ static int ensure_sub(ngscov *h, int64_t n_sub)
 	if (nb > h->bmax_cap) {
 		CK(cudaStreamSynchronize(h->s_main));
 		if (h->d_bmax) cudaFree(h->d_bmax);
-		h->d_bmax = nullptr; h->bmax_cap = 0;
+		if (h->d_kbmax) cudaFree(h->d_kbmax);
+		h->d_bmax = nullptr; h->d_kbmax = nullptr; h->bmax_cap = 0;
 		CK(cudaMalloc((void **)&h->d_bmax, (nb + 1024) * 8));
+		CK(cudaMalloc((void **)&h->d_kbmax, (nb + 1024) * 8));
 		h->bmax_cap = nb + 1024;
+	}
+	if (h->cover && h->rows_used + (size_t)n_sub > h->rows_cap) {
+		/* the table grows by doubling; what is there is copied device to device (a few GB at most, ~1 ms per GB) */
+		CK(cudaStreamSynchronize(h->s_main));
+		const size_t need = h->rows_used + (size_t)n_sub;
+		const size_t cap = std::max(need + need / 8 + 64, h->rows_cap * 2);
+		uint2 *ne = nullptr; ngs_row *nr = nullptr; unsigned long long *nk = nullptr;
+		CK(cudaMalloc((void **)&ne, cap * NGS_ROW_SLOTS * sizeof(uint2)));
+		CK(cudaMalloc((void **)&nr, cap * sizeof(ngs_row)));
+		CK(cudaMalloc((void **)&nk, cap * 8));
+		if (h->rows_used) {
+			CK(cudaMemcpyAsync(ne, h->d_ent, h->rows_used * NGS_ROW_SLOTS * sizeof(uint2), cudaMemcpyDeviceToDevice, h->s_main));
+			CK(cudaMemcpyAsync(nr, h->d_rows, h->rows_used * sizeof(ngs_row), cudaMemcpyDeviceToDevice, h->s_main));
+			CK(cudaMemcpyAsync(nk, h->d_rkmax, h->rows_used * 8, cudaMemcpyDeviceToDevice, h->s_main));
+			CK(cudaStreamSynchronize(h->s_main));
+		}
+		if (h->d_ent) cudaFree(h->d_ent);
+		if (h->d_rows) cudaFree(h->d_rows);
+		if (h->d_rkmax) cudaFree(h->d_rkmax);
+		h->d_ent = ne; h->d_rows = nr; h->d_rkmax = nk; h->rows_cap = cap;
 	}
 	return 0;
 }
@@ -451,6 +501,8 @@ static IngestArgs make_ingest_args(ngscov *h, const uint8_t *base, int64_t n, in
 	A.count = h->d_count; A.slots = h->d_slots; A.slot_shift = h->shift - 5; A.ctr = h->d_ctr;
 	A.fixed_entry0 = fixed0; A.entry0_from_state = from_state ? 1 : 0;
 	A.debug = getenv("NGSCOV_DEBUG_INGEST") ? atoi(getenv("NGSCOV_DEBUG_INGEST")) : 0;
+	A.rows = h->d_rows ? h->d_rows + h->p_row0 : nullptr; A.ent = h->d_ent ? h->d_ent + h->p_row0 * NGS_ROW_SLOTS : nullptr;
+	A.rkmax = h->d_rkmax ? h->d_rkmax + h->p_row0 : nullptr; A.far_flag = h->d_far_flag;
 	return A;
 }
 
@@ -466,9 +518,16 @@ static int launch_verify(ngscov *h)
 {
 	const int64_t n_sub = h->p_nsub;
 	const unsigned nb = (unsigned)((n_sub + NGS_VER_PER_BLOCK - 1) / NGS_VER_PER_BLOCK);
-	k_verify_blockmax<<<nb, 256, 0, h->s_main>>>(h->d_exit, n_sub, h->d_bmax);
-	k_verify_scan<<<1, 1024, 0, h->s_main>>>(h->d_bmax, nb, h->d_st, h->p_fixed0, h->p_from_state ? 1 : 0);
-	k_verify_check<<<nb, 256, 0, h->s_main>>>(h->d_entry, h->d_exit, n_sub, h->d_bmax, h->shift, h->p_n, h->d_st);
+	if (h->cover) {
+		k_verify_blockmax_k<<<nb, 256, 0, h->s_main>>>(h->d_exit, h->d_rows + h->p_row0, n_sub, h->d_bmax, h->d_kbmax);
+		k_verify_scan_k<<<1, 1024, 0, h->s_main>>>(h->d_bmax, h->d_kbmax, nb, h->d_st, h->p_fixed0, h->p_from_state ? 1 : 0);
+		k_verify_check_k<<<nb, 256, 0, h->s_main>>>(h->d_entry, h->d_exit, h->d_rows + h->p_row0, n_sub, h->d_bmax, h->d_kbmax, h->d_rkmax + h->p_row0,
+		                                           h->shift, h->p_n, h->d_st);
+	} else {
+		k_verify_blockmax<<<nb, 256, 0, h->s_main>>>(h->d_exit, n_sub, h->d_bmax);
+		k_verify_scan<<<1, 1024, 0, h->s_main>>>(h->d_bmax, nb, h->d_st, h->p_fixed0, h->p_from_state ? 1 : 0);
+		k_verify_check<<<nb, 256, 0, h->s_main>>>(h->d_entry, h->d_exit, n_sub, h->d_bmax, h->shift, h->p_n, h->d_st);
+	}
 	h->stats.launches += 3;
 	{ int r_ = small_d2h(h, h->h_st, h->d_st, sizeof(ngs_dev_state)); if (r_) return r_; }
 	/* the striped K2 counters travel with the same snapshot: both describe the chunks BEFORE this one (this chunk's K2
@@ -476,6 +535,16 @@ static int launch_verify(ngscov *h)
 	 * synchronisation per chunk */
 	{ int r_ = small_d2h(h, h->h_ctr, h->d_ctr, NGS_CTR_STRIPES * 16 * 8); if (r_) return r_; }
 	CK(cudaEventRecord(h->ev_verified, h->s_main));
+	CK(cudaGetLastError());
+	return 0;
+}
+
+static int launch_special(ngscov *h, const IngestArgs &A, int mode)
+{
+	/* a warp takes 32 rows per step */
+	const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((A.n_sub + 255) / 256, (int64_t)h->sm_count * 8));
+	k_special_reds<<<grid, 256, 0, h->s_main>>>(A, mode);
+	h->stats.launches += 1;
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -492,7 +561,8 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 		const unsigned long long key = h->h_st->first_bad_key;
 		if ((key & 1) || iter > 100000) { h->sticky_err = NGSCOV_EFORMAT; h->pending = false; return NGSCOV_EFORMAT; }
 		IngestArgs A = make_ingest_args(h, h->p_base, h->p_n, h->p_nsub, h->p_from_state, h->p_fixed0);
-		if (h->fused) k_repair<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
+		if (h->cover) k_repair_classify<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
+		else if (h->fused) k_repair<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
 		else k_repair_chain<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
 		h->stats.launches += 1;
 		h->p_k2_done = false;                    /* the optimistic K2 saw n_bad != 0 and did nothing */
@@ -501,9 +571,23 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 	}
 	if (!h->fused && !h->p_k2_done) {
 		IngestArgs A = make_ingest_args(h, h->p_base, h->p_n, h->p_nsub, h->p_from_state, h->p_fixed0);
-		k_decode_scatter<<<(unsigned)((((uint64_t)h->p_nsub << A.slot_shift) + 255) / 256), 256, 0, h->s_main>>>(A);
-		h->stats.launches += 1;
+		if (h->cover) { int r_ = launch_special(h, A, h->red_mode ? 1 : 0); if (r_) return r_; }
+		else {
+			k_decode_scatter<<<(unsigned)((((uint64_t)h->p_nsub << A.slot_shift) + 255) / 256), 256, 0, h->s_main>>>(A);
+			h->stats.launches += 1;
+		}
 		h->p_k2_done = true;
+	}
+	if (h->cover && h->h_st->unsorted && !h->red_mode) {
+		/* the input is not coordinate sorted: the owner tiles cannot find their records by key.  Everything pushed so far
+		 * already had its rare deltas added to the global array; add the ordinary ones too (needs only the table) and go
+		 * on with REDs + the classic scan.  Contigs that were already finalized cannot be taken back. */
+		if (h->next_fin_seg > 0) { h->sticky_err = NGSCOV_EUNSORTED; h->pending = false; return NGSCOV_EUNSORTED; }
+		h->red_mode = true; h->stream_fin = false;
+		IngestArgs A = make_ingest_args(h, h->p_base, h->p_n, h->p_nsub, h->p_from_state, h->p_fixed0);
+		A.rows = h->d_rows; A.ent = h->d_ent; A.rkmax = h->d_rkmax; A.n_sub = (int64_t)h->rows_used;
+		int r_ = launch_special(h, A, 2);
+		if (r_) return r_;
 	}
 	k_finalize_chunk<<<1, 256, 0, h->s_main>>>(h->p_base, h->p_n, h->d_st, h->d_carry);
 	h->stats.launches += 1;
@@ -542,9 +626,14 @@ static int submit_chunk(ngscov *h, const uint8_t *base, int64_t n, bool from_sta
 	const int64_t n_sub = (n + ((int64_t)1 << h->shift) - 1) >> h->shift;
 	int r = ensure_sub(h, n_sub);
 	if (r) return r;
+	h->p_row0 = h->rows_used;
 	IngestArgs A = make_ingest_args(h, base, n, n_sub, from_state, fixed0);
 	CK(cudaEventRecord(next_event(h->ev_ing, h->n_ing), h->s_main));
-	if (!h->fused) {
+	if (h->cover) {
+		/* K1: frame AND classify (speculative chain walk, one 8-byte table entry per contributing record) */
+		k_chain_classify<<<(unsigned)((n_sub + 255) / 256), 256, 0, h->s_main>>>(A);
+		h->rows_used += (size_t)n_sub;
+	} else if (!h->fused) {
 		/* K1: frame the records (speculative chain walk, no atomics, full occupancy) */
 		const unsigned nb = (unsigned)((n_sub + 255) / 256);
 		k_chain_walk<<<nb, 256, 0, h->s_main>>>(A);
@@ -574,9 +663,12 @@ static int submit_chunk(ngscov *h, const uint8_t *base, int64_t n, bool from_sta
 		/* K2 queued optimistically behind the verification: it returns at once if a mismatch was found,
 		 * and is then launched again by resolve_pending after the repair */
 		CK(cudaEventRecord(next_event(h->ev_k2, h->n_k2), h->s_main));
-		k_decode_scatter<<<(unsigned)((((uint64_t)n_sub << A.slot_shift) + 255) / 256), 256, 0, h->s_main>>>(A);
+		if (h->cover) { if ((r = launch_special(h, A, h->red_mode ? 1 : 0))) return r; }
+		else {
+			k_decode_scatter<<<(unsigned)((((uint64_t)n_sub << A.slot_shift) + 255) / 256), 256, 0, h->s_main>>>(A);
+			h->stats.launches += 1;
+		}
 		CK(cudaEventRecord(next_event(h->ev_k2, h->n_k2), h->s_main));
-		h->stats.launches += 1;
 		h->p_k2_done = true;
 		CK(cudaGetLastError());
 	}
@@ -862,6 +954,7 @@ static int scan_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_b
 }
 
 static int format_bed_range(ngscov *h, size_t s0, size_t s1);
+static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_bound);
 
 /* Finalize segments [next_fin_seg, seg_end) while the rest of the stream is still arriving. */
 static int stream_finalize_impl(ngscov *h, size_t seg_end);
@@ -877,6 +970,12 @@ static int stream_finalize_impl(ngscov *h, size_t seg_end)
 	int r;
 	const unsigned long long mops_now = h->h_st->m_ops;
 	const size_t s0 = h->next_fin_seg;
+	if (h->cover && !h->red_mode) {
+		if ((r = cover_range(h, s0, seg_end, mops_now - h->mops_fin))) return r;
+		h->mops_fin += h->h_st2->n_boundaries / 2;
+		h->next_fin_seg = seg_end;
+		return 0;
+	}
 	if ((r = scan_range(h, s0, seg_end, mops_now - h->mops_fin))) return r;
 	/* how many of the intervals seen so far belong to the finished contigs is not known exactly; every interval
 	 * makes at most two boundaries, so boundaries/2 is a safe lower bound of what they consumed */
@@ -922,6 +1021,19 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 	if ((st.entry_next != 0 || st.carry_len != 0) && !(h->last_flags & NGSCOV_PUSH_TRUNCATED_OK)) return h->sticky_err = NGSCOV_EFORMAT;
 	if (st.flags & NGS_FLAG_ERANGE) return h->sticky_err = NGSCOV_ERANGE;
 
+	if (h->cover && !h->red_mode) {
+		if (h->next_fin_seg < h->seg.size() && (r = cover_range(h, h->next_fin_seg, h->seg.size(), st.m_ops - h->mops_fin))) return r;
+		if (h->cfg.mode == NGSCOV_MODE_DEPTH) { h->text_ready[NGSCOV_OUT_BEDGRAPH] = true; h->text_len[NGSCOV_OUT_BEDGRAPH] = h->bed_off; }
+		h->next_fin_seg = h->seg.size();
+		h->diff_dirty = false;
+		memset(&h->halo, 0, sizeof h->halo); h->halo.first.contig = h->halo.last.contig = -1;
+		h->halo.n_runs = h->acc_runs;
+		if (h->halo_have) { h->halo.first = h->cov_first; h->halo.last = h->cov_last; }
+		h->stats.boundaries = h->acc_boundaries; h->stats.runs = h->acc_runs; h->stats.positions = h->n_elems;
+		if (getenv("NGSCOV_DEBUG")) { fprintf(stderr, "ngscov: streamed finalize: %d calls, %.3f s host wall\n", h->fin_calls, h->fin_wall); h->fin_wall = 0; h->fin_calls = 0; }
+		h->runs_done = true;
+		return 0;
+	}
 	const bool streamed = h->next_fin_seg > 0;
 	if (h->next_fin_seg < h->seg.size() || h->seg.empty()) {
 		if (h->seg.empty()) { h->h_rec_base.assign(1, 0); memset(h->h_st2, 0, sizeof *h->h_st2); }
@@ -984,6 +1096,20 @@ extern "C" int ngscov_halo_put(ngscov_t *h, int drop_first, uint32_t new_last_en
 	if (!h) return NGSCOV_EINVAL;
 	if (!h->runs_done || h->formatted) return NGSCOV_ESTATE;
 	if (h->halo.n_runs == 0) return drop_first || new_last_end ? NGSCOV_EINVAL : 0;
+	if (h->cover && !h->red_mode) {
+		/* the text exists already: dropping the first run skips its line, a new end of the last run rewrites the last line */
+		auto line = [&](const ngscov_run &rn) { char b[64]; snprintf(b, sizeof b, "\t%u\t%u\t%d\n", rn.start, rn.end, rn.depth); return h->ref_name[rn.contig] + b; };
+		h->bed_begin = 0; h->bed_tail.clear(); h->bed_tail_old = 0; h->bed_patched = false;
+		if (h->cfg.mode != NGSCOV_MODE_DEPTH) return 0;
+		if (drop_first) h->bed_begin = h->halo.n_runs == 1 ? h->bed_off : line(h->halo.first).size();
+		if (new_last_end && !(drop_first && h->halo.n_runs == 1)) {
+			ngscov_run l = h->halo.last;
+			h->bed_tail_old = line(l).size();
+			l.end = new_last_end;
+			h->bed_tail = line(l);
+		}
+		return 0;
+	}
 	if (h->next_fin_seg > 0) return NGSCOV_ESTATE;           /* streamed finalize: the text is already made */
 	h->drop_idx = drop_first ? h->h_st2->first_run : ~0ull;
 	if (new_last_end) { h->mod_idx = h->h_st2->last_run; h->mod_end = new_last_end; } else h->mod_idx = ~0ull;
@@ -1120,7 +1246,98 @@ static int run_format(ngscov *h, int which, unsigned long long n_items, const Pr
 	return 0;
 }
 
+
 static uint32_t dig(uint64_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n; } return n; }
+
+/* Cover pipeline: owner tiles over segments [s0, s1) -- accumulate, scan, window bins and (DEPTH mode) the bedGraph
+ * text appended at bed_off, one kernel.  h_st2 receives the counters. */
+static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_bound)
+{
+	int r;
+	const bool text = h->cfg.mode == NGSCOV_MODE_DEPTH;
+	const uint64_t t0 = h->seg[s0].tile0, t1 = s1 < h->seg.size() ? h->seg[s1].tile0 : h->n_tiles;
+	const uint64_t elems = (t1 - t0) * (uint64_t)NGS_TILE;
+	size_t bound = 0; uint32_t stage = 0;
+	if (text) {
+		/* boundaries: at most two per accumulated interval, never more than tracked positions; depth <= intervals */
+		const size_t nb = (size_t)std::min<unsigned long long>(2ull * mops_bound, elems);
+		const uint32_t dd = std::min<uint32_t>(11, dig(mops_bound) + 1);
+		size_t max_line = 8, typ_line = 8;
+		for (size_t sg = s0; sg < s1; ++sg) {
+			const uint32_t pd = dig(h->seg[sg].lim);
+			const size_t nm = h->ref_name[h->seg[sg].contig].size() + 1;
+			max_line = std::max(max_line, nm + 2 * pd + 2 + dd + 1);
+			typ_line = std::max(typ_line, nm + 2 * pd + 2 + std::min<uint32_t>(dd, 5) + 1);
+		}
+		bound = nb * max_line;
+		/* the staging area of a batch (1024 lines) is sized for depths below 10^5; a batch that needs more writes its
+		 * lines straight to global memory */
+		stage = (uint32_t)std::min<size_t>(1024 * typ_line + 32, 64 * 1024);
+		if (getenv("NGSCOV_COVER_STAGE")) stage = (uint32_t)atoi(getenv("NGSCOV_COVER_STAGE"));
+		if ((r = grow_text(h, NGSCOV_OUT_BEDGRAPH, h->bed_off + bound + 64, h->bed_off))) return r;
+		h->text_ready[NGSCOV_OUT_BEDGRAPH] = true; h->h_text_valid[NGSCOV_OUT_BEDGRAPH] = false;
+	}
+	tic(h);
+	if (!h->bins_zeroed) { CK(cudaMemsetAsync(h->d_bins, 0, h->n_bins * 8, h->s_main)); h->bins_zeroed = true; }
+	{	/* reset the per-launch fields of the device state block (the ingest fields stay live) */
+		const size_t o0 = offsetof(ngs_dev_state, scan_ticket), o1 = offsetof(ngs_dev_state, key_seed);
+		CK(cudaMemcpyAsync((char *)h->d_st + o0, (const char *)h->h_tmpl + o0, o1 - o0, cudaMemcpyHostToDevice, h->s_main));
+		const size_t o2 = offsetof(ngs_dev_state, first_tile), o3 = sizeof(ngs_dev_state);
+		CK(cudaMemcpyAsync((char *)h->d_st + o2, (const char *)h->h_tmpl + o2, o3 - o2, cudaMemcpyHostToDevice, h->s_main));
+	}
+	if (t1 > t0) {
+		CK(cudaMemsetAsync(h->d_stB + t0, 0, (t1 - t0) * 8, h->s_main));
+		if (text) CK(cudaMemsetAsync(h->d_stF + t0, 0, (t1 - t0) * 8, h->s_main));
+		k_tile_rows<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, h->s_main>>>(h->d_rkmax, (uint32_t)h->rows_used, h->d_tile2seg + t0, h->d_seg, t0, t1 - t0,
+		                                                                   h->d_row_a + t0, h->d_row_b + t0);
+		CoverArgs A;
+		A.n_tiles = t1 - t0; A.tile_off = t0; A.tile2seg = h->d_tile2seg + t0; A.seg = h->d_seg;
+		A.ent = h->d_ent; A.rows = h->d_rows; A.row_a = h->d_row_a + t0; A.row_b = h->d_row_b + t0;
+		A.diff = h->d_diff + t0 * (uint64_t)NGS_TILE; A.far_flag = h->d_far_flag + t0;
+		A.stB = h->d_stB + t0; A.stF = h->d_stF + t0;
+		A.bins = h->d_bins; A.window = h->cfg.window; A.variant = h->cfg.mode == NGSCOV_MODE_WIG ? 1 : 0;
+		A.tile_first = h->d_tile_first + t0; A.tile_last = h->d_tile_last + t0;
+		A.nt.names = h->d_names; A.nt.name_off = h->d_name_off; A.nt.name8 = h->d_name8;
+		A.out = text ? h->d_text[NGSCOV_OUT_BEDGRAPH] + h->bed_off : nullptr;
+		A.out_cap = text ? h->d_text_cap[NGSCOV_OUT_BEDGRAPH] - h->bed_off : 0;
+		A.stage_bytes = stage; A.st = h->d_st;
+		A.debug = getenv("NGSCOV_DEBUG_SCAN") ? atoi(getenv("NGSCOV_DEBUG_SCAN")) : 0;
+		if (text) {
+			CK(cudaFuncSetAttribute(k_cover<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+			k_cover<true><<<(unsigned)(t1 - t0), NGS_COVER_THREADS, stage, h->s_main>>>(A);
+		} else k_cover<false><<<(unsigned)(t1 - t0), NGS_COVER_THREADS, 0, h->s_main>>>(A);
+		k_halo_gather<<<1, 32, 0, h->s_main>>>(h->d_st, h->d_tile_first, h->d_tile_last);
+		h->stats.launches += 3;
+		CK(cudaGetLastError());
+	}
+	if ((r = small_d2h(h, h->h_st2, h->d_st, sizeof(ngs_dev_state)))) return r;
+	h->stats.ms_scan += toc(h);
+	const ngs_dev_state &s2 = *h->h_st2;
+	if (s2.flags & NGS_FLAG_STALL) { snprintf(h->cuda_err, sizeof h->cuda_err, "look-back watchdog: a predecessor tile never published"); return h->sticky_err = NGSCOV_ECUDA; }
+	h->acc_boundaries += s2.n_boundaries; h->acc_runs += s2.n_runs;
+	h->acc_max = std::max(h->acc_max, s2.max_depth); h->acc_min = std::min(h->acc_min, s2.min_depth);
+	h->stats.boundaries = h->acc_boundaries; h->stats.runs = h->acc_runs; h->stats.positions = h->n_elems;
+	if (s2.n_runs) {
+		ngscov_run f = { (int32_t)s2.halo_first[3], s2.halo_first[0], s2.halo_first[1], (int32_t)s2.halo_first[2] };
+		ngscov_run l = { (int32_t)s2.halo_last[3], s2.halo_last[0], s2.halo_last[1], (int32_t)s2.halo_last[2] };
+		if (!h->halo_have) { h->cov_first = f; h->halo_have = true; }
+		h->cov_last = l;
+	}
+	if (text) {
+		if (s2.fmt_bytes > h->d_text_cap[NGSCOV_OUT_BEDGRAPH] - h->bed_off) return h->sticky_err = NGSCOV_ENOMEM;
+		h->bed_off += (size_t)s2.fmt_bytes;
+		h->text_len[NGSCOV_OUT_BEDGRAPH] = h->bed_off;
+		h->stats.out_bytes[NGSCOV_OUT_BEDGRAPH] = h->bed_off;
+		const bool streamed = h->stream_fin && (h->next_fin_seg > 0 || s1 < h->seg.size() || s0 > 0);
+		if (streamed && h->bed_off > h->bed_d2h && !getenv("NGSCOV_DEBUG_NOD2H")) {
+			if ((r = grow_host_text(h, NGSCOV_OUT_BEDGRAPH, h->bed_off, h->bed_d2h))) return r;
+			CK(cudaMemcpyAsync(h->h_text[NGSCOV_OUT_BEDGRAPH] + h->bed_d2h, h->d_text[NGSCOV_OUT_BEDGRAPH] + h->bed_d2h, h->bed_off - h->bed_d2h,
+			                   cudaMemcpyDeviceToHost, h->s_out));
+			h->bed_d2h = h->bed_off;
+		}
+	}
+	return 0;
+}
 
 /* bedGraph text of segments [s0, s1) from the records of the scan_range that just ran over them; appended at
  * bed_off.  In streamed mode the new bytes are queued for D2H at once (stream s_out). */
@@ -1164,7 +1381,9 @@ extern "C" int ngscov_format(ngscov_t *h, uint32_t which_mask)
 	CK(cudaSetDevice(h->device));
 	int r = 0;
 	NameTable nt = { h->d_names, h->d_name_off, h->d_name8 };
-	if ((which_mask & (1u << NGSCOV_OUT_BEDGRAPH)) && h->next_fin_seg == 0) {      /* streamed inputs already have their text */
+	if ((which_mask & (1u << NGSCOV_OUT_BEDGRAPH)) && h->cover && !h->red_mode) {
+		h->stats.out_bytes[NGSCOV_OUT_BEDGRAPH] = h->bed_off - h->bed_begin - h->bed_tail_old + h->bed_tail.size();
+	} else if ((which_mask & (1u << NGSCOV_OUT_BEDGRAPH)) && h->next_fin_seg == 0) {      /* streamed inputs already have their text */
 		if ((r = format_bed_range(h, 0, h->seg.size()))) return r;
 	}
 	if (which_mask & (1u << NGSCOV_OUT_DEPTH)) {
@@ -1212,6 +1431,19 @@ extern "C" int ngscov_output_device(ngscov_t *h, int which, const void **dev_buf
 {
 	if (!h || which < 0 || which > 2 || !dev_buf || !len) return NGSCOV_EINVAL;
 	if (!h->text_ready[which]) return NGSCOV_ESTATE;
+	if (which == NGSCOV_OUT_BEDGRAPH && h->cover && !h->red_mode && (h->bed_begin || h->bed_tail_old)) {
+		/* halo decisions: skip the dropped first line, overwrite the last line in place (the buffer has slack) */
+		CK(cudaSetDevice(h->device));
+		const size_t body = h->bed_off - h->bed_tail_old;
+		if (h->bed_begin >= h->bed_off) { *dev_buf = h->d_text[which]; *len = 0; return 0; }
+		if (!h->bed_tail.empty() && !h->bed_patched) {
+			CK(cudaMemcpyAsync(h->d_text[which] + body, h->bed_tail.data(), h->bed_tail.size(), cudaMemcpyHostToDevice, h->s_main));
+			CK(cudaStreamSynchronize(h->s_main));
+			h->bed_patched = true;
+		}
+		*dev_buf = h->d_text[which] + h->bed_begin; *len = body + h->bed_tail.size() - h->bed_begin;
+		return 0;
+	}
 	*dev_buf = h->d_text[which]; *len = h->text_len[which];
 	return 0;
 }
@@ -1243,12 +1475,41 @@ extern "C" int ngscov_output(ngscov_t *h, int which, const char **buf, size_t *l
 		h->h_text_valid[which] = true;
 	}
 	*buf = h->h_text[which]; *len = h->text_len[which];
+	if (which == NGSCOV_OUT_BEDGRAPH && h->cover && !h->red_mode && (h->bed_begin || h->bed_tail_old)) {
+		if (h->bed_begin >= h->bed_off) { *len = 0; return 0; }
+		const size_t body = h->bed_off - h->bed_tail_old;
+		if (body + h->bed_tail.size() > h->h_text_cap[which]) return NGSCOV_ENOMEM;     /* cannot happen: the buffers keep slack */
+		if (!h->bed_tail.empty()) memcpy(h->h_text[which] + body, h->bed_tail.data(), h->bed_tail.size());
+		*buf = h->h_text[which] + h->bed_begin; *len = body + h->bed_tail.size() - h->bed_begin;
+	}
 	return 0;
 }
 
 extern "C" int ngscov_runs_get(ngscov_t *h, ngscov_run *runs, uint64_t cap, uint64_t *n)
 {
 	if (!h || !n) return NGSCOV_EINVAL;
+	if (h->runs_done && h->cover && !h->red_mode) {
+		/* the cover pipeline keeps no binary run records: they are read back from the bedGraph text (DEPTH mode only) */
+		if (h->cfg.mode != NGSCOV_MODE_DEPTH) return NGSCOV_ESTATE;
+		const char *buf; size_t len;
+		int r = ngscov_output(h, NGSCOV_OUT_BEDGRAPH, &buf, &len);
+		if (r) return r;
+		CK(cudaStreamSynchronize(h->s_main));
+		uint64_t k = 0; size_t i = 0; int ctg = 0;
+		while (i < len) {
+			size_t j = i; while (j < len && buf[j] != '\t') ++j;
+			if (ctg >= h->n_ref || h->ref_name[ctg].size() != j - i || memcmp(h->ref_name[ctg].data(), buf + i, j - i)) {
+				for (ctg = 0; ctg < h->n_ref; ++ctg) if (h->ref_name[ctg].size() == j - i && !memcmp(h->ref_name[ctg].data(), buf + i, j - i)) break;
+			}
+			uint64_t v[3] = { 0, 0, 0 };
+			i = j + 1;
+			for (int f = 0; f < 3; ++f) { while (i < len && buf[i] >= '0' && buf[i] <= '9') v[f] = v[f] * 10 + (uint64_t)(buf[i++] - '0'); ++i; }
+			if (runs && k < cap) { runs[k].contig = ctg < h->n_ref ? ctg : -1; runs[k].start = (uint32_t)v[0]; runs[k].end = (uint32_t)v[1]; runs[k].depth = (int32_t)v[2]; }
+			++k;
+		}
+		*n = k;
+		return 0;
+	}
 	if (!h->runs_done || h->next_fin_seg > 0) return NGSCOV_ESTATE;      /* streamed inputs keep only the last contig's records */
 	CK(cudaSetDevice(h->device));
 	const uint64_t nb = h->stats.boundaries;

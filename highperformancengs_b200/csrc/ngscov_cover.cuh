@@ -1,0 +1,862 @@
+/* csrc/ngscov_cover.cuh -- the "cover" pipeline of libngscov_cuda (round 2): the difference array is never
+ * materialised in HBM for ordinary records.
+ *
+ *   K1  k_chain_classify   speculative per-sub-chunk block_size chain walk (as k_chain_walk) that also decodes core
+ *                          fields + CIGAR of every record while its cache line is there, and leaves one 8-byte entry
+ *                          per contributing record in the row of its sub-chunk (ngs_row / entry format: ngscov_hd.h).
+ *                          Replaces bam_read1 framing (samtools bam.c:191-223) + fetch_func (bam2depth.c:86-110,
+ *                          bam2wig.c:84-109).
+ *       k_verify_*_k       the boundary check of k_verify_*, plus a running max of the record sort keys: gives every
+ *                          row the largest key seen up to it (rkmax, the search array of k_tile_rows) and detects
+ *                          input that is not coordinate sorted.
+ *       k_special_reds     the rare records: CHAIN entries (decoded from the stream while the chunk is resident) and
+ *                          deltas further than NGS_NEAR_H from their record's POS -> REDs into the global int32
+ *                          array + far flag of the tile; also folds the per-row counters.
+ *   K2-K5  k_cover         one CTA owns a tile of NGS_CT positions: gathers the entries of the rows that can reach it
+ *                          (k_tile_rows: two binary searches per tile), accumulates their +1/-1 in shared memory,
+ *                          merges the tile of the far array when flagged, scans (decoupled look-back over one 64-bit
+ *                          word: sum | last boundary), detects run boundaries, adds the window bins (both `overlap`
+ *                          variants, bam2depth.c:132-176 / bam2wig.c:131-175) and writes the bedGraph lines
+ *                          (bam2depth.c:208-234) straight into the output text (second look-back over byte counts).
+ *                          Replaces insertInt2Hash + hashtbl (bam2depth.c:72-84, hashtbl.c) + union_hashed_keys +
+ *                          the sweep of hash2BedGraph + its fprintf.
+ */
+#pragma once
+#include "ngscov_kernels.cuh"
+
+#define NGS_COVER_THREADS 256
+#ifndef NGS_COVER_MINB
+#define NGS_COVER_MINB 4
+#endif
+#define NGS_WATCHDOG_POLLS (1u << 26)      /* look-back polls of one entry before the wait is abandoned (seconds) */
+
+template <class Mem>
+struct CigReader {
+	const Mem &mem; int64_t co;
+	__device__ __forceinline__ uint32_t operator()(uint32_t i) const { return mem.u32(co + 4ll * i); }
+};
+
+/* walk + classify the records starting in [entry, hi): entries -> row[], metadata -> m */
+template <class Mem>
+__device__ __forceinline__ long long chain_classify(const ngs_walk_cfg &cfg, const Mem &mem, long long entry, int64_t hi,
+                                                    uint2 *row, ngs_row &m)
+{
+	const int64_t n = mem.size();
+	int64_t o = entry;
+	ngs_counts32 cnt = { 0, 0, 0, 0, 0 };
+	uint64_t fk = NGS_KEY_NONE, prev = 0;
+	uint32_t count = 0, special = 0; int32_t ctg0 = -1;
+	long long result;
+	if (o >= hi) result = o;
+	else if (o + 36 > n) result = NGS_EXIT_PARTIAL(o);
+	else {
+		ngs_hdr h;
+		mem.hdr_lite(o, h);
+		for (;;) {
+			if (!ngs_hdr_valid(h, cfg.n_ref)) { result = NGS_EXIT_INVALID; break; }
+			if (o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar > n) { result = NGS_EXIT_PARTIAL(o); break; }
+			/* the next header is requested before this record is classified: the chain of dependent loads stays as
+			 * short as in the framing-only walk, the CIGAR loads ride along */
+			const int64_t nx = o + 4 + (int64_t)h.block_size;
+			const bool more = nx < hi, have = more && nx + 36 <= n;
+			ngs_hdr hn;
+			if (have) mem.hdr_lite(nx, hn);
+			const uint64_t key = ngs_sort_key(h.ref_id, h.pos);
+			if (fk == NGS_KEY_NONE) fk = key;
+			if (key < prev) special |= NGS_ROW_UNSORTED;
+			prev = key;
+			uint32_t y; int sp = 0;
+			CigReader<Mem> cig = { mem, o + 36 + (int64_t)h.l_qname };
+			if (ngs_classify_record(cfg, h, (uint32_t)(o - entry), cig, y, sp, cnt)) {
+				if (ctg0 < 0) ctg0 = h.ref_id;
+				uint32_t cd = (uint32_t)(h.ref_id - ctg0);
+				if (cd > NGS_ENT_CDELTA_MAX) { cd = 7u; y = (NGS_ENT_CHAIN << 30) | (uint32_t)(o - entry); sp = 1; }
+				if (count < NGS_ROW_SLOTS) row[count] = make_uint2((uint32_t)h.pos | (cd << 29), y);
+				++count; special += (uint32_t)sp;
+			}
+			if (!more) { result = nx; break; }
+			if (!have) { result = NGS_EXIT_PARTIAL(nx); break; }
+			h = hn; o = nx;
+		}
+	}
+	if (count > NGS_ROW_SLOTS) { count = 0; special = (special & NGS_ROW_UNSORTED) | NGS_ROW_OVERFLOW; }
+	m.fk = fk; m.lk = prev; m.count = count; m.special = special; m.ctg = ctg0;
+	m.nrec = cnt.records; m.nkept = cnt.kept; m.nmops = cnt.m_ops; m.ncig = cnt.cigar_words; m.max_ref_p1 = cnt.max_ref_p1;
+	m.pad0 = 0; m.pad1 = 0;
+	return result;
+}
+
+__device__ __forceinline__ void store_row(ngs_row *dst, const ngs_row &m)
+{
+	const uint4 *s = reinterpret_cast<const uint4 *>(&m);
+	uint4 *d = reinterpret_cast<uint4 *>(dst);
+	d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+}
+
+#ifndef NGS_K1_MINB
+#define NGS_K1_MINB 4
+#endif
+__global__ void __launch_bounds__(256, NGS_K1_MINB) k_chain_classify(const __grid_constant__ IngestArgs A)
+{
+	const unsigned full = 0xffffffffu;
+	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = c < A.n_sub;
+	DevMem mem = { A.base, A.n };
+	const int64_t lo = live ? (c << A.shift) : 0;
+	int64_t hi = live ? lo + ((int64_t)1 << A.shift) : 0;
+	if (hi > A.n) hi = A.n;
+	long long entry = NGS_NONE;
+	bool searching = live && c != 0;
+	if (live && c == 0) {
+		const long long e0 = A.entry0_from_state ? A.st->entry_next : A.fixed_entry0;
+		entry = e0 < hi ? e0 : NGS_NONE;
+	}
+	{
+		const int64_t end = hi < A.n - 35 ? hi : A.n - 35;
+		int64_t o = lo;
+		while (__any_sync(full, searching)) {
+			if (searching) { o = mem.next_candidate(o, end, (uint32_t)A.cfg.n_ref); if (o == NGS_NONE) searching = false; }
+			__syncwarp();
+			if (searching) {
+				if (ngs_candidate_ok(A.cfg, mem, A.ref_len, o)) { entry = o; searching = false; } else ++o;
+			}
+		}
+	}
+	long long ex = 0;
+	ngs_row m;
+	m.fk = NGS_KEY_NONE; m.lk = 0; m.count = 0; m.special = 0; m.ctg = -1; m.nrec = m.nkept = m.nmops = m.ncig = m.max_ref_p1 = 0; m.pad0 = m.pad1 = 0;
+	if (entry != NGS_NONE) ex = chain_classify(A.cfg, mem, entry, hi, A.ent + (size_t)c * NGS_ROW_SLOTS, m);
+	if (live) { A.entry[c] = entry; A.exit[c] = ex; store_row(A.rows + c, m); }
+	const unsigned w = __reduce_add_sync(full, entry != NGS_NONE ? 1u : 0u);
+	if ((threadIdx.x & 31) == 0 && w) atomicAdd(&A.st->spec_walks, (unsigned long long)w);
+}
+
+/* Rare path, single thread: zip the true chain forward from the first mismatching sub-chunk until it meets an
+ * already-framed entry, rewriting entry / exit / row on the way (k_repair_chain for the table) */
+__global__ void k_repair_classify(IngestArgs A, long long first_bad, const long long *bexcl)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	DevMem mem = { A.base, A.n };
+	long long cur = bexcl[first_bad / NGS_VER_PER_BLOCK];
+	for (long long k = (first_bad / NGS_VER_PER_BLOCK) * NGS_VER_PER_BLOCK; k < first_bad; ++k) {
+		const long long x = exit_num(A.exit[k]);
+		cur = x > cur ? x : cur;
+	}
+	ngs_row empty;
+	empty.fk = NGS_KEY_NONE; empty.lk = 0; empty.count = 0; empty.special = 0; empty.ctg = -1;
+	empty.nrec = empty.nkept = empty.nmops = empty.ncig = empty.max_ref_p1 = 0; empty.pad0 = empty.pad1 = 0;
+	long long c = first_bad, repaired = 0;
+	for (;;) {
+		long long cc = cur >= A.n ? A.n_sub : (cur < 0 ? 0 : (cur >> A.shift));
+		if (cc > A.n_sub) cc = A.n_sub;
+		for (long long k = c; k < cc; ++k)              /* sub-chunks the true chain jumps over hold no record start */
+			if (A.entry[k] != NGS_NONE) { A.entry[k] = NGS_NONE; A.exit[k] = 0; A.rows[k] = empty; ++repaired; }
+		if (cc >= A.n_sub) break;
+		if (A.entry[cc] == cur) break;                  /* converged */
+		long long hi = (cc + 1) << A.shift; if (hi > A.n) hi = A.n;
+		ngs_row m;
+		const long long x = chain_classify(A.cfg, mem, cur, hi, A.ent + (size_t)cc * NGS_ROW_SLOTS, m);
+		A.entry[cc] = cur; A.exit[cc] = x; A.rows[cc] = m; ++repaired;
+		c = cc + 1;
+		cur = (x == NGS_EXIT_INVALID || x >= NGS_EXIT_INF) ? A.n : x;
+	}
+	atomicAdd(&A.st->spec_repaired, (unsigned long long)repaired);
+}
+
+/* ---- verification with keys: the three kernels of k_verify_* carrying a second running max ------------------- */
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long *sm)
+{
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+	const int w = threadIdx.x >> 5;
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) sm[w] = v;
+	__syncthreads();
+	unsigned long long r = sm[0];
+	for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = sm[i] > r ? sm[i] : r;
+	return r;
+}
+
+__global__ void __launch_bounds__(256) k_verify_blockmax_k(const long long *exit, const ngs_row *rows, int64_t n_sub, long long *bmax, unsigned long long *kbmax)
+{
+	__shared__ long long sm[8];
+	__shared__ unsigned long long smk[8];
+	const int64_t b0 = (int64_t)blockIdx.x * NGS_VER_PER_BLOCK;
+	long long m = 0; unsigned long long km = 0;
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const int64_t c = b0 + i * 256 + threadIdx.x;
+		if (c < n_sub) {
+			long long x = exit_num(exit[c]); m = x > m ? x : m;
+			const unsigned long long lk = rows[c].lk; km = lk > km ? lk : km;
+		}
+	}
+	m = block_max_ll(m, sm);
+	km = block_max_u64(km, smk);
+	if (threadIdx.x == 0) { bmax[blockIdx.x] = m; kbmax[blockIdx.x] = km; }
+}
+
+/* single block: exclusive running max over the block maxima (exits seeded with the chunk's first entry, keys with
+ * the committed key of the previous chunks) */
+__global__ void __launch_bounds__(1024) k_verify_scan_k(long long *bmax, unsigned long long *kbmax, int64_t n_blocks, ngs_dev_state *st,
+                                                        long long fixed_entry0, int entry0_from_state)
+{
+	__shared__ long long sm[32];
+	__shared__ unsigned long long smk[32];
+	__shared__ long long carry_s;
+	__shared__ unsigned long long kcarry_s;
+	if (threadIdx.x == 0) {
+		carry_s = entry0_from_state ? st->entry_next : fixed_entry0;
+		kcarry_s = st->key_seed;
+		st->n_bad = 0; st->first_bad_key = ~0ull; st->unsorted = 0;
+	}
+	__syncthreads();
+	for (int64_t b0 = 0; b0 < n_blocks; b0 += 1024) {
+		const int64_t b = b0 + threadIdx.x;
+		long long v = b < n_blocks ? bmax[b] : 0;
+		unsigned long long kv = b < n_blocks ? kbmax[b] : 0;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			long long t = __shfl_up_sync(0xffffffffu, v, o); unsigned long long kt = __shfl_up_sync(0xffffffffu, kv, o);
+			if ((threadIdx.x & 31) >= o) { if (t > v) v = t; if (kt > kv) kv = kt; }
+		}
+		if ((threadIdx.x & 31) == 31) { sm[threadIdx.x >> 5] = v; smk[threadIdx.x >> 5] = kv; }
+		__syncthreads();
+		long long pre = carry_s; unsigned long long kpre = kcarry_s;
+		for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) { pre = sm[w] > pre ? sm[w] : pre; kpre = smk[w] > kpre ? smk[w] : kpre; }
+		const long long incl = v > pre ? v : pre; const unsigned long long kincl = kv > kpre ? kv : kpre;
+		const long long prev = __shfl_up_sync(0xffffffffu, v, 1); const unsigned long long kprev = __shfl_up_sync(0xffffffffu, kv, 1);
+		const long long excl = (threadIdx.x & 31) ? (prev > pre ? prev : pre) : pre;
+		const unsigned long long kexcl = (threadIdx.x & 31) ? (kprev > kpre ? kprev : kpre) : kpre;
+		if (b < n_blocks) { bmax[b] = excl; kbmax[b] = kexcl; }
+		__syncthreads();
+		if (threadIdx.x == 1023) { carry_s = incl; kcarry_s = kincl; }
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) { st->chunk_exit = carry_s; st->key_chunk_max = kcarry_s; }
+}
+
+__global__ void __launch_bounds__(256) k_verify_check_k(const long long *entry, const long long *exit, const ngs_row *rows, int64_t n_sub,
+                                                        const long long *bexcl, const unsigned long long *kbexcl, unsigned long long *rkmax,
+                                                        int shift, int64_t n, ngs_dev_state *st)
+{
+	__shared__ long long sm[8];
+	__shared__ unsigned long long smk[8];
+	const int64_t c0 = (int64_t)blockIdx.x * NGS_VER_PER_BLOCK + (int64_t)threadIdx.x * 4;
+	long long ex[4], en[4]; unsigned long long fk[4], lk[4]; unsigned int sp[4];
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const int64_t c = c0 + i;
+		ex[i] = c < n_sub ? exit_num(exit[c]) : 0;
+		en[i] = c < n_sub ? entry[c] : NGS_NONE;
+		fk[i] = NGS_KEY_NONE; lk[i] = 0; sp[i] = 0;
+		if (c < n_sub) { const uint4 a = reinterpret_cast<const uint4 *>(rows + c)[0], b = reinterpret_cast<const uint4 *>(rows + c)[1];
+			fk[i] = (unsigned long long)a.x | ((unsigned long long)a.y << 32); lk[i] = (unsigned long long)a.z | ((unsigned long long)a.w << 32); sp[i] = b.y; }
+	}
+	long long tmax = ex[0];
+	tmax = ex[1] > tmax ? ex[1] : tmax; tmax = ex[2] > tmax ? ex[2] : tmax; tmax = ex[3] > tmax ? ex[3] : tmax;
+	unsigned long long ktmax = lk[0];
+	ktmax = lk[1] > ktmax ? lk[1] : ktmax; ktmax = lk[2] > ktmax ? lk[2] : ktmax; ktmax = lk[3] > ktmax ? lk[3] : ktmax;
+	long long v = tmax; unsigned long long kv = ktmax;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		long long t = __shfl_up_sync(0xffffffffu, v, o); unsigned long long kt = __shfl_up_sync(0xffffffffu, kv, o);
+		if ((threadIdx.x & 31) >= o) { if (t > v) v = t; if (kt > kv) kv = kt; }
+	}
+	if ((threadIdx.x & 31) == 31) { sm[threadIdx.x >> 5] = v; smk[threadIdx.x >> 5] = kv; }
+	__syncthreads();
+	long long pre = bexcl[blockIdx.x]; unsigned long long kpre = kbexcl[blockIdx.x];
+	for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) { pre = sm[w] > pre ? sm[w] : pre; kpre = smk[w] > kpre ? smk[w] : kpre; }
+	const long long prev = __shfl_up_sync(0xffffffffu, v, 1); const unsigned long long kprev = __shfl_up_sync(0xffffffffu, kv, 1);
+	long long run = (threadIdx.x & 31) ? (prev > pre ? prev : pre) : pre;
+	unsigned long long krun = (threadIdx.x & 31) ? (kprev > kpre ? kprev : kpre) : kpre;
+	unsigned int unsorted = 0;
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const int64_t c = c0 + i;
+		if (c < n_sub) {
+			const long long expected = run;
+			const int64_t lo = c << shift;
+			int64_t hi = lo + ((int64_t)1 << shift);
+			if (hi > n) hi = n;
+			const bool exp_in = expected < hi;
+			int kind = -1;
+			if (exp_in && c > 0 && expected < lo) kind = 1;                  /* a verified chain ended early */
+			else if (exp_in ? (en[i] != expected) : (en[i] != NGS_NONE)) kind = 0;
+			else if (en[i] != NGS_NONE && exit[c] == NGS_EXIT_INVALID) kind = 1;
+			if (kind >= 0) {
+				atomicAdd(&st->n_bad, 1ull);
+				atomicMin(&st->first_bad_key, (unsigned long long)c * 2 + (unsigned)kind);
+			}
+			run = ex[i] > run ? ex[i] : run;
+			if ((sp[i] & NGS_ROW_UNSORTED) || (fk[i] != NGS_KEY_NONE && fk[i] < krun)) unsorted = 1;
+			krun = lk[i] > krun ? lk[i] : krun;
+			rkmax[c] = krun;
+		}
+	}
+	if (__any_sync(0xffffffffu, unsorted) && (threadIdx.x & 31) == 0) st->unsorted = 1;
+}
+
+/* ---- the rare records ------------------------------------------------------------------------------------- */
+struct FarSink {                     /* RED into the global array + far flag of the element's tile */
+	int *diff; uint32_t *far_flag; unsigned int *flags; int mark;
+	__device__ __forceinline__ void one(uint64_t idx, int v) { atomicAdd(diff + idx, v); if (mark) far_flag[idx / NGS_TILE] = 1u; }
+	__device__ __forceinline__ void add2(uint64_t ia, uint64_t ib, int sign) { one(ia, sign); one(ib, -sign); }
+	__device__ __forceinline__ void flag_range_error() { atomicOr(flags, NGS_FLAG_ERANGE); }
+};
+
+/* mode 0: CHAIN entries (all their deltas) and the far deltas of SIMPLE / PAIR entries, rows that overflowed; folds
+ *         the per-row counters into the striped counters (cover pipeline, once per verified chunk)
+ * mode 1: every delta of every entry (input that is not coordinate sorted: the classic scan follows) + counters
+ * mode 2: only the near deltas of SIMPLE / PAIR entries (catch-up for rows that already had a mode-0 pass when the
+ *         input turned out to be unsorted; needs no stream) */
+__global__ void __launch_bounds__(256) k_special_reds(const __grid_constant__ IngestArgs A, int mode)
+{
+	const unsigned full = 0xffffffffu;
+	if (mode != 2) {
+		const ngs_dev_state *st = A.st;
+		if (st->n_bad != 0 || (st->flags & NGS_FLAG_EFORMAT)) return;      /* launched optimistically behind the verification */
+	}
+	const int lane = threadIdx.x & 31;
+	const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5, wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	DevMem mem = { A.base, A.n };
+	FarSink sink = { A.diff, A.far_flag, &A.st->flags, mode == 0 ? 1 : 0 };
+	unsigned int s_rec = 0, s_kept = 0, s_mops = 0, s_cig = 0, s_max = 0, s_sp = 0;
+	for (int64_t r0 = wid * 32; r0 < A.n_sub; r0 += n_warps * 32) {
+		const int64_t c = r0 + lane;
+		uint4 b = make_uint4(0, 0, 0xffffffffu, 0), d = make_uint4(0, 0, 0, 0);
+		if (c < A.n_sub) { b = reinterpret_cast<const uint4 *>(A.rows + c)[1]; d = reinterpret_cast<const uint4 *>(A.rows + c)[2]; }
+		/* b = count, special, ctg, nrec ; d = nkept, nmops, ncig, max_ref_p1 */
+		s_rec += b.w; s_kept += d.x; s_mops += d.y; s_cig += d.z; s_max = d.w > s_max ? d.w : s_max; s_sp += b.y & 0xffffu;
+		const bool need = mode == 0 ? (b.y & ~NGS_ROW_UNSORTED) != 0 : (mode == 1 ? (b.x != 0 || (b.y & NGS_ROW_OVERFLOW)) : b.x != 0);
+		unsigned todo = __ballot_sync(full, need);
+		while (todo) {
+			const int src = __ffs(todo) - 1; todo &= todo - 1;
+			const unsigned int count = __shfl_sync(full, b.x, src), special = __shfl_sync(full, b.y, src);
+			const int ctg0 = (int)__shfl_sync(full, b.z, src);
+			const int64_t row = r0 + src;
+			if (special & NGS_ROW_OVERFLOW) {
+				if (mode != 2 && lane == 0) {         /* the whole row goes the classic way: sequential walk, run-length combined REDs */
+					long long hi = (row + 1) << A.shift; if (hi > A.n) hi = A.n;
+					ngs_counts dummy = { 0, 0, 0, 0, 0 };
+					ngs_walk(A.cfg, mem, A.entry[row], hi, sink, +1, dummy);
+				}
+				continue;
+			}
+			const long long ent0 = mode != 2 ? A.entry[row] : 0;
+			for (unsigned int k = lane; k < count; k += 32) {
+				const uint2 e = A.ent[(size_t)row * NGS_ROW_SLOTS + k];
+				const uint32_t kind = e.y >> 30;
+				if (kind == NGS_ENT_CHAIN) {
+					if (mode == 2) continue;
+					const int64_t o = ent0 + (int64_t)(e.y & 0x3FFFFFFFu);
+					ngs_hdr h; mem.hdr_lite(o, h);
+					ngs_counts dummy = { 0, 0, 0, 0, 0 };
+					ngs_decode_record(A.cfg, mem, o, h, sink, +1, dummy);
+					continue;
+				}
+				const uint32_t pos = e.x & 0x1FFFFFFFu;
+				uint32_t ia[2], ib[2];
+				const int ni = ngs_entry_intervals(pos, e.y, ia, ib);
+				if (mode == 0 && ib[ni - 1] - pos <= NGS_NEAR_H) continue;       /* nothing of it can be far */
+				const ngs_seg &sg = A.cfg.seg[A.cfg.ctg2seg[ctg0 + (int)(e.x >> 29)]];
+				for (int j = 0; j < ni; ++j) {
+					const int na = ngs_delta_is_near(sg.clip_lo, pos, ia[j]), nb = ngs_delta_is_near(sg.clip_lo, pos, ib[j]);
+					if (mode == 1 || (mode == 0 ? !na : na)) sink.one(sg.base + (ia[j] - sg.clip_lo), +1);
+					if (mode == 1 || (mode == 0 ? !nb : nb)) sink.one(sg.base + (ib[j] - sg.clip_lo), -1);
+				}
+			}
+		}
+	}
+	if (mode == 2) return;
+	const unsigned v0 = __reduce_add_sync(full, s_rec), v1 = __reduce_add_sync(full, s_kept), v2 = __reduce_add_sync(full, s_mops),
+	               v3 = __reduce_add_sync(full, s_cig), v4 = __reduce_max_sync(full, s_max), v5 = __reduce_add_sync(full, s_sp);
+	if (lane == 0 && v0) {
+		unsigned long long *c4 = A.ctr + (size_t)(wid % NGS_CTR_STRIPES) * 16;
+		atomicAdd(c4 + 0, (unsigned long long)v0);
+		if (v1) atomicAdd(c4 + 1, (unsigned long long)v1);
+		if (v2) atomicAdd(c4 + 2, (unsigned long long)v2);
+		if (v3) atomicAdd(c4 + 3, (unsigned long long)v3);
+		if (v4 > A.st->max_ref_p1) atomicMax(&A.st->max_ref_p1, v4);
+		if (v5) atomicAdd(&A.st->n_special, v5);
+	}
+}
+
+/* ---- tile -> rows ------------------------------------------------------------------------------------------ */
+/* For every tile of the launch: the rows whose records can reach it.  rkmax is non-decreasing by construction, so
+ *   row_a = first row with rkmax >= key(contig, P0 - H)   (every earlier row only holds smaller keys)
+ *   row_b = 1 + first row with rkmax >= key(contig, P0 + CT)  (sorted input: every later row starts at or behind it) */
+__global__ void __launch_bounds__(256) k_tile_rows(const unsigned long long *rkmax, uint32_t n_rows, const uint32_t *tile2seg, const ngs_seg *seg,
+                                                   uint64_t tile_off, uint64_t n_tiles, uint32_t *row_a, uint32_t *row_b)
+{
+	const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tile >= n_tiles) return;
+	const ngs_seg &sg = seg[tile2seg[tile]];
+	const uint64_t p0 = (uint64_t)sg.clip_lo + (tile + tile_off - sg.tile0) * NGS_CT;
+	const uint64_t lo_pos = p0 > NGS_NEAR_H ? p0 - NGS_NEAR_H : 0;
+	const unsigned long long ka = ((unsigned long long)sg.contig << 32) | (lo_pos + 1), kb = ((unsigned long long)sg.contig << 32) | (p0 + NGS_CT + 1);
+	uint32_t lo = 0, hi = n_rows;                       /* first row with rkmax >= ka */
+	while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (rkmax[mid] < ka) lo = mid + 1; else hi = mid; }
+	const uint32_t a = lo;
+	hi = n_rows;
+	while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (rkmax[mid] < kb) lo = mid + 1; else hi = mid; }
+	row_a[tile] = a;
+	row_b[tile] = lo < n_rows ? lo + 1 : n_rows;
+}
+
+/* ---- K2..K5 fused: the tile owner -------------------------------------------------------------------------- */
+struct CoverArgs {
+	uint64_t n_tiles, tile_off;          /* tiles of this launch / global index of the first one; per-tile pointers are pre-offset */
+	const uint32_t *tile2seg; const ngs_seg *seg;
+	const uint2 *ent; const ngs_row *rows;              /* the whole table */
+	const uint32_t *row_a, *row_b;
+	int *diff; uint32_t *far_flag;       /* far array */
+	unsigned long long *stB, *stF;       /* look-back words: status:2 | lastb:30 | sum:32  and  status:2 | bytes:62 */
+	unsigned long long *bins; uint32_t window; int variant;
+	uint4 *tile_first, *tile_last;       /* first / last non-zero run of each tile (halo candidates) */
+	NameTable nt;
+	char *out; unsigned long long out_cap;
+	uint32_t stage_bytes;
+	int debug;                           /* bit 0: skip the look-back waits (timing experiments only, wrong output) */
+	ngs_dev_state *st;
+};
+
+/* padded accumulator index: 16 consecutive elements per thread, 4 ints of padding -> conflict-free 128-bit reads */
+__device__ __forceinline__ int acc_idx(int i) { return i + ((i >> 4) << 2); }
+
+/* generic bedGraph line, byte by byte (long contig names, depths outside [0, 10^9), staging overflow) */
+__device__ __noinline__ uint32_t bed_line_bytes(char *dst, const NameTable nt, uint32_t ctg, uint32_t s, uint32_t e, int d)
+{
+	const uint32_t a = nt.name_off[ctg], nl = nt.name_off[ctg + 1] - a;
+	if (!dst) return nl + ngs_ndigits(s) + ngs_ndigits(e) + ngs_len_i32(d) + 3u;
+	char *p = dst;
+	for (uint32_t i = 0; i < nl; ++i) p[i] = nt.names[a + i];
+	p += nl;
+	p += ngs_put_u32(p, s); *p++ = '\t';
+	p += ngs_put_u32(p, e); *p++ = '\t';
+	p += ngs_put_i32(p, d); *p++ = '\n';
+	return (uint32_t)(p - dst);
+}
+
+/* block-wide look-back over one status word per tile (status:2 | payload:62, payload added up), thread i inspects
+ * predecessor tile-1-i.  Returns the exclusive prefix; publishes the inclusive one. */
+__device__ __forceinline__ unsigned long long lookback_bytes(unsigned long long *status, unsigned long long tile, unsigned long long total,
+                                                             unsigned int *s_li, unsigned long long *s_lb, ngs_dev_state *st)
+{
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	unsigned long long run = 0;
+	long long base = (long long)tile - 1;
+	for (;;) {
+		const long long idx = base - t;
+		unsigned long long a = NGS_ST_INC << 62;
+		if (idx >= 0) {
+			unsigned int polls = 0;
+			do { a = ld_relaxed_u64(&status[idx]); } while ((a >> 62) == NGS_ST_EMPTY && ++polls < NGS_WATCHDOG_POLLS);
+			if ((a >> 62) == NGS_ST_EMPTY) { atomicOr(&st->flags, NGS_FLAG_STALL); a = NGS_ST_INC << 62; }
+		}
+		const unsigned int im = __ballot_sync(0xffffffffu, (a >> 62) == NGS_ST_INC);
+		if (lane == 0) s_li[warp] = im ? (unsigned)(warp * 32 + __ffs(im) - 1) : 0xffffffffu;
+		__syncthreads();
+		unsigned int first_inc = 0xffffffffu;
+		#pragma unroll
+		for (int w = 0; w < 8; ++w) first_inc = s_li[w] < first_inc ? s_li[w] : first_inc;
+		unsigned long long v = (unsigned)t <= first_inc ? (a & 0x3FFFFFFFFFFFFFFFull) : 0;
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		if (lane == 0) s_lb[warp] = v;
+		__syncthreads();
+		#pragma unroll
+		for (int w = 0; w < 8; ++w) run += s_lb[w];
+		if (first_inc != 0xffffffffu) break;
+		base -= NGS_COVER_THREADS;
+		__syncthreads();
+	}
+	if (t == 0) st_relaxed_u64(&status[tile], (NGS_ST_INC << 62) | (run + total));
+	return run;
+}
+
+template <bool TEXT>
+__global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(const __grid_constant__ CoverArgs A)
+{
+	extern __shared__ __align__(16) char s_stage[];
+	__shared__ __align__(16) int s_tile[NGS_SCAN_SMEM / 4];   /* phase 1: padded accumulators (20 KB); phase 2: compact boundary list
+	                                                             (u16 position [NGS_CT] + i32 local depth [NGS_CT]) */
+	__shared__ long long s_wsum[8]; __shared__ unsigned int s_wcnt[8], s_wlast[8];
+	__shared__ unsigned int s_lb_inc[8], s_lb_last[8]; __shared__ long long s_lb_sum[8];
+	__shared__ long long s_bk[8], s_bv[8];
+	__shared__ unsigned int s_wr[8]; __shared__ int s_wmax[8], s_wmin[8];
+	__shared__ unsigned int s_rfirst[8], s_rlast[8], s_wlen[8];
+	__shared__ unsigned int s_w[8], s_li[8];
+	__shared__ unsigned long long s_lb[8];
+
+	const unsigned full = 0xffffffffu;
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const uint64_t tile = blockIdx.x;                    /* launch-local; dispatch order = tile order (see k_scan_runs) */
+	if (tile >= A.n_tiles) return;
+	const uint32_t si = A.tile2seg[tile];
+	const uint32_t ra = A.row_a[tile], rb = A.row_b[tile], far = A.far_flag[tile];
+	#pragma unroll
+	for (int j = 0; j < (NGS_CT * 20 / 16) / 4 / NGS_COVER_THREADS; ++j) reinterpret_cast<int4 *>(s_tile)[j * NGS_COVER_THREADS + t] = make_int4(0, 0, 0, 0);
+	const ngs_seg sg = A.seg[si];
+	const uint64_t tile_g = tile + A.tile_off;
+	const uint32_t pos0 = sg.clip_lo + (uint32_t)((tile_g - sg.tile0) * NGS_CT);
+	__syncthreads();
+
+	/* ---- gather: +1/-1 of every visible record into the shared accumulators (four rows in flight per thread) */
+	{
+		const int64_t vis_lo = (int64_t)pos0 - NGS_NEAR_H;
+		for (uint32_t r0 = ra; r0 < rb; r0 += 4) {
+			uint32_t cnt[4]; int ctg[4]; uint2 e[4];
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				cnt[j] = 0; ctg[j] = 0;
+				if (r0 + j < rb) { const uint4 m = __ldg(reinterpret_cast<const uint4 *>(A.rows + r0 + j) + 1); cnt[j] = m.x; ctg[j] = (int)m.z; }
+			}
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) { e[j] = make_uint2(0, NGS_ENT_CHAIN << 30); if ((uint32_t)t < cnt[j]) e[j] = __ldg(A.ent + (size_t)(r0 + j) * NGS_ROW_SLOTS + t); }
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const uint32_t kind = e[j].y >> 30, pos = e[j].x & 0x1FFFFFFFu;
+				if (kind == NGS_ENT_CHAIN || ctg[j] + (int)(e[j].x >> 29) != (int)sg.contig || (int64_t)pos < vis_lo) continue;
+				const uint32_t pl = e[j].y & 0x3FFFFFFFu;
+				const uint32_t a0 = pos - pos0;                         /* wraps to a huge value for pos < pos0: fails the < NGS_CT test */
+				uint32_t b0;
+				if (kind == NGS_ENT_SIMPLE) b0 = a0 + pl;
+				else {
+					b0 = a0 + (pl & 0xFFFu);
+					const uint32_t a1 = b0 + ((pl >> 12) & 0x3Fu), b1 = a1 + (pl >> 18);
+					if (a1 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)a1)], 1);
+					if (b1 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)b1)], -1);
+				}
+				if (a0 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)a0)], 1);
+				if (b0 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)b0)], -1);
+			}
+		}
+	}
+	__syncthreads();
+	if (far) {                                           /* merge (and re-zero) this tile of the far array */
+		int *g = A.diff + tile * (uint64_t)NGS_CT;
+		#pragma unroll 4
+		for (int j = 0; j < NGS_CT / NGS_COVER_THREADS; ++j) {
+			const int i = j * NGS_COVER_THREADS + t;
+			const int v = g[i];
+			if (v) { s_tile[acc_idx(i)] += v; g[i] = 0; }
+		}
+		if (t == 0) A.far_flag[tile] = 0;
+		__syncthreads();
+	}
+
+	/* ---- scan (as k_scan_runs): 16 consecutive elements per thread */
+	int d[16];
+	#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int4 v = *reinterpret_cast<const int4 *>(&s_tile[t * 20 + j * 4]);
+		d[4 * j] = v.x; d[4 * j + 1] = v.y; d[4 * j + 2] = v.z; d[4 * j + 3] = v.w;
+	}
+	int tsum = 0; unsigned int tcnt = 0, tlast = 0;
+	#pragma unroll
+	for (int i = 0; i < 16; ++i) { tsum += d[i]; if (d[i] != 0) { ++tcnt; tlast = (unsigned)(t * 16 + i + 1); } }
+	int isum = tsum; unsigned int icnt = tcnt, ilast = tlast;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const int a = __shfl_up_sync(full, isum, o);
+		const unsigned int b = __shfl_up_sync(full, icnt, o);
+		const unsigned int c = __shfl_up_sync(full, ilast, o);
+		if (lane >= o) { isum += a; icnt += b; ilast = ilast > c ? ilast : c; }
+	}
+	if (lane == 31) { s_wsum[warp] = isum; s_wcnt[warp] = icnt; s_wlast[warp] = ilast; }
+	__syncthreads();                                     /* also: every thread has its 16 elements, s_tile may be reused */
+	long long wpre_sum = 0; unsigned int wpre_cnt = 0;
+	long long tot_sum = 0; unsigned int tot_cnt = 0, tot_last = 0;
+	#pragma unroll
+	for (int w = 0; w < 8; ++w) {
+		if (w < warp) { wpre_sum += s_wsum[w]; wpre_cnt += s_wcnt[w]; }
+		tot_sum += s_wsum[w]; tot_cnt += s_wcnt[w]; tot_last = s_wlast[w] > tot_last ? s_wlast[w] : tot_last;
+	}
+	const int psum = __shfl_up_sync(full, isum, 1);
+	const unsigned int pcnt = __shfl_up_sync(full, icnt, 1);
+	const long long ex_sum = wpre_sum + (lane ? psum : 0);
+	const unsigned int ex_cnt = wpre_cnt + (lane ? pcnt : 0);
+	const uint32_t agg_lastb = tot_last ? pos0 + tot_last : 0;     /* 1 + contig position, 0 = none */
+	if (t == 0) st_relaxed_u64(&A.stB[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
+
+	/* ---- compact the boundaries (tile-relative position, depth before it WITHOUT the carry) while the predecessors
+	 * publish their aggregates */
+	unsigned short *c_pos = reinterpret_cast<unsigned short *>(s_tile);
+	int *c_dep = s_tile + NGS_CT / 2;
+	if (tcnt) {
+		int depth = (int)ex_sum;
+		unsigned int r = ex_cnt;
+		#pragma unroll
+		for (int i = 0; i < 16; ++i) {
+			if (d[i] != 0) { c_pos[r] = (unsigned short)(t * 16 + i); c_dep[r] = depth; depth += d[i]; ++r; }
+		}
+	}
+
+	/* ---- decoupled look-back over (sum, last boundary) */
+	long long carry = 0; unsigned int tile_last = 0;
+	if (tile > 0 && !(A.debug & 1)) {
+		long long base = (long long)tile - 1;
+		for (;;) {
+			const long long idx = base - t;
+			unsigned long long b = NGS_ST_INC << 62;
+			if (idx >= 0) {
+				unsigned int polls = 0;
+				do { b = ld_relaxed_u64(&A.stB[idx]); } while ((b >> 62) == NGS_ST_EMPTY && ++polls < NGS_WATCHDOG_POLLS);
+				if ((b >> 62) == NGS_ST_EMPTY) { atomicOr(&A.st->flags, NGS_FLAG_STALL); b = NGS_ST_INC << 62; }
+			}
+			const unsigned int im = __ballot_sync(full, (b >> 62) == NGS_ST_INC);
+			if (lane == 0) s_lb_inc[warp] = im ? (unsigned)(warp * 32 + __ffs(im) - 1) : 0xffffffffu;
+			__syncthreads();
+			unsigned int first_inc = 0xffffffffu;
+			#pragma unroll
+			for (int w = 0; w < 8; ++w) first_inc = s_lb_inc[w] < first_inc ? s_lb_inc[w] : first_inc;
+			long long vs = 0; unsigned int vl = 0;
+			if ((unsigned)t <= first_inc) { vs = (long long)(int)(uint32_t)b; vl = (unsigned int)((b >> 32) & 0x3FFFFFFFu); }
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) vs += __shfl_xor_sync(full, vs, o);
+			const unsigned int has = __ballot_sync(full, vl != 0);
+			unsigned int near_l = 0;
+			if (has) near_l = __shfl_sync(full, vl, __ffs(has) - 1);      /* lowest lane = nearest tile */
+			if (lane == 0) { s_lb_sum[warp] = vs; s_lb_last[warp] = near_l; }
+			__syncthreads();
+			unsigned int rl = 0;
+			#pragma unroll
+			for (int w = 0; w < 8; ++w) { carry += s_lb_sum[w]; if (rl == 0) rl = s_lb_last[w]; }
+			if (tile_last == 0) tile_last = rl;
+			if (first_inc != 0xffffffffu) break;
+			base -= NGS_COVER_THREADS;
+			__syncthreads();
+		}
+		if (t == 0) {
+			const unsigned int inc_last = agg_lastb ? agg_lastb : tile_last;
+			st_relaxed_u64(&A.stB[tile], (NGS_ST_INC << 62) | ((unsigned long long)inc_last << 32) | (uint32_t)(int)(carry + tot_sum));
+		}
+	} else __syncthreads();                              /* c_pos / c_dep complete */
+	if (tot_cnt == 0) {
+		/* an empty tile still resolves and publishes its inclusive byte count: a successor must never have to look back
+		 * through a long stretch of aggregate-only words (sparse coverage: most tiles of the genome are empty) */
+		if (TEXT) {
+			if (t == 0) st_relaxed_u64(&A.stF[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62));
+			const unsigned long long run = (tile > 0 && !(A.debug & 1)) ? lookback_bytes(A.stF, tile, 0, s_li, s_lb, A.st) : 0;
+			if (t == 0 && tile == A.n_tiles - 1) A.st->fmt_bytes = run;
+		}
+		return;
+	}
+	const int icarry = (int)carry;
+	const uint32_t first_start = tile_last ? tile_last - 1 : 0;       /* start of the run that ends at the tile's first boundary */
+	const uint32_t ctg = sg.contig;
+	const uint32_t nl = A.nt.name_off[ctg + 1] - A.nt.name_off[ctg];
+
+	/* ---- window bins, statistics, text length: record r, r+256, .. per thread */
+	BinAcc bacc; bacc.bins = A.bins + sg.bins0; bacc.k = -1; bacc.acc = 0;
+	unsigned int my_runs = 0, my_first = 0xffffffffu, my_last = 0, my_len = 0; int my_max = 0, my_min = 0;
+	{
+		const uint32_t W = A.window;
+		const uint32_t kt = pos0 / W;
+		const uint64_t wlo = (uint64_t)kt * W, whi = wlo + W - 1;
+		for (unsigned int r = t; r < tot_cnt; r += NGS_COVER_THREADS) {
+			const uint32_t pos = pos0 + c_pos[r];
+			const int depth = c_dep[r] + icarry;
+			const uint32_t start = r ? pos0 + c_pos[r - 1] : first_start;
+			if (depth != 0) {
+				if (start >= wlo && pos <= whi && pos <= sg.ref_len) bacc(kt, (int64_t)(pos - start) * depth);
+				else ngs_bin_run(A.variant, start, pos, (int64_t)depth, W, sg.ref_len, sg.n_win, bacc);
+				++my_runs; my_max = depth > my_max ? depth : my_max; my_min = depth < my_min ? depth : my_min;
+				my_first = r < my_first ? r : my_first; my_last = r;
+				if (TEXT) my_len += nl + ngs_ndigits(start) + ngs_ndigits(pos) + ngs_len_i32(depth) + 3u;
+			}
+		}
+	}
+	{
+		const bool has = bacc.k >= 0 && bacc.acc != 0;
+		const unsigned hm = __ballot_sync(full, has);
+		long long wk = -1, wv = 0;
+		if (hm) {
+			const int leader = __ffs(hm) - 1;
+			const long long k0 = __shfl_sync(full, bacc.k, leader);
+			if (__all_sync(full, !has || bacc.k == k0)) {
+				long long v = has ? bacc.acc : 0;
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+				wk = k0; wv = v;
+			} else if (has) atomicAdd(bacc.bins + bacc.k, (unsigned long long)bacc.acc);
+		}
+		const unsigned wr = __reduce_add_sync(full, my_runs), wl = __reduce_add_sync(full, my_len);
+		const int wmax = __reduce_max_sync(full, my_max), wmin = __reduce_min_sync(full, my_min);
+		const unsigned wfirst = __reduce_min_sync(full, my_first), wlast = __reduce_max_sync(full, my_last);
+		if (lane == 0) {
+			s_bk[warp] = wk; s_bv[warp] = wv;
+			s_wr[warp] = wr; s_wmax[warp] = wmax; s_wmin[warp] = wmin; s_rfirst[warp] = wfirst; s_rlast[warp] = wlast; s_wlen[warp] = wl;
+		}
+	}
+	__syncthreads();
+	unsigned int total = 0;                              /* text bytes of the tile */
+	#pragma unroll
+	for (int w = 0; w < 8; ++w) total += s_wlen[w];
+	if (t == 0) {
+		if (TEXT) st_relaxed_u64(&A.stF[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | total);
+		long long ck = -1, cv = 0;
+		unsigned long long nr = 0; unsigned int fr = 0xffffffffu, lr = 0; int mx = 0, mn = 0;
+		for (int w = 0; w < 8; ++w) {
+			if (s_bk[w] >= 0) {
+				if (s_bk[w] == ck) cv += s_bv[w];
+				else { if (ck >= 0 && cv) atomicAdd(bacc.bins + ck, (unsigned long long)cv); ck = s_bk[w]; cv = s_bv[w]; }
+			}
+			nr += s_wr[w]; mx = s_wmax[w] > mx ? s_wmax[w] : mx; mn = s_wmin[w] < mn ? s_wmin[w] : mn;
+			fr = s_rfirst[w] < fr ? s_rfirst[w] : fr; lr = s_rlast[w] > lr ? s_rlast[w] : lr;
+		}
+		if (ck >= 0 && cv) atomicAdd(bacc.bins + ck, (unsigned long long)cv);
+		atomicAdd(&A.st->n_boundaries, (unsigned long long)tot_cnt);
+		if (nr) {
+			atomicAdd(&A.st->n_runs, nr);
+			atomicMax(&A.st->max_depth, mx); atomicMin(&A.st->min_depth, mn);
+			A.tile_first[tile] = make_uint4(fr ? pos0 + c_pos[fr - 1] : first_start, pos0 + c_pos[fr], (uint32_t)(c_dep[fr] + icarry), ctg);
+			A.tile_last[tile] = make_uint4(lr ? pos0 + c_pos[lr - 1] : first_start, pos0 + c_pos[lr], (uint32_t)(c_dep[lr] + icarry), ctg);
+			atomicMin(&A.st->first_tile, (unsigned long long)tile_g); atomicMax(&A.st->last_tile_p1, (unsigned long long)tile_g + 1);
+		}
+	}
+	if (!TEXT) return;
+
+	/* ---- text: batches of 1024 boundaries (four consecutive ones per thread), lines assembled in registers and
+	 * staged in shared memory as in k_format_bed; the byte-offset look-back runs after the first batch is assembled */
+	const unsigned long long name8 = A.nt.name8[ctg];
+	const uint32_t n_lo = (uint32_t)name8, n_hi = (uint32_t)(name8 >> 32);
+	uint32_t *sw = reinterpret_cast<uint32_t *>(s_stage);
+	unsigned long long goff = 0; uint32_t done_bytes = 0;
+	const unsigned int n_batches = (tot_cnt + 1023u) >> 10;
+	for (unsigned int bt = 0; bt < n_batches; ++bt) {
+		const unsigned int r0 = (bt << 10) + 4u * (unsigned)t;
+		uint32_t S0 = 0, E[4]; int D[4];
+		#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const bool in = r0 + i < tot_cnt;
+			E[i] = in ? pos0 + c_pos[r0 + i] : 0; D[i] = in ? c_dep[r0 + i] + icarry : 0;
+		}
+		if (r0 < tot_cnt) S0 = r0 ? pos0 + c_pos[r0 - 1] : first_start;
+		ngs_hcache hc; hc.H = 0xffffffffu; hc.hlo = hc.sh = hc.nH = hc.selA = hc.selB = hc.selC = 0;
+		hc.nh0 = hc.nh1 = hc.nh2 = hc.nh3 = hc.th0 = hc.th1 = 0;
+		uint32_t L4e[4], L4s0 = 0, len[4], tlen = 0;
+		int bad = nl > 8u;
+		auto pos_digits = [&](uint32_t p, uint32_t &L4) -> uint32_t {
+			const uint32_t H = p / 10000u, raw = ngs_digits4_raw(p - H * 10000u);
+			L4 = raw + 0x30303030u;
+			if (H == 0) return raw ? 4u - ngs_low_byte_index(raw) : 1u;
+			if (H >= 100000u) { bad = 1; return 10u; }
+			if (H != hc.H) ngs_hcache_fill(hc, H, n_lo, n_hi, nl);
+			return hc.nH + 4u;
+		};
+		{
+			bool any = false;
+			#pragma unroll
+			for (int i = 0; i < 4; ++i) { any |= D[i] != 0; len[i] = 0; L4e[i] = 0; }
+			if (any && nl <= 8u) {
+				uint32_t n_prev = pos_digits(S0, L4s0);
+				#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const uint32_t ns = n_prev;
+					const uint32_t ne = pos_digits(E[i], L4e[i]);
+					n_prev = ne;
+					if (D[i] != 0) {
+						uint32_t nd;
+						if ((uint32_t)D[i] < 10000u) nd = 1u + ((uint32_t)D[i] >= 10u) + ((uint32_t)D[i] >= 100u) + ((uint32_t)D[i] >= 1000u);
+						else if ((uint32_t)D[i] < 1000000000u) nd = ngs_ndigits((uint32_t)D[i]);
+						else { bad = 1; nd = ngs_len_i32(D[i]); }
+						len[i] = nl + ns + ne + nd + 3u;
+					}
+					tlen += len[i];
+				}
+			} else if (any) {
+				#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					if (D[i] != 0) len[i] = nl + ngs_ndigits(i ? E[i - 1] : S0) + ngs_ndigits(E[i]) + ngs_len_i32(D[i]) + 3u;
+					tlen += len[i];
+				}
+			}
+		}
+		uint32_t inc = tlen;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(full, inc, o); if (lane >= o) inc += v; }
+		if (lane == 31) s_w[warp] = inc;
+		const bool slow = __syncthreads_or(bad) != 0;
+		uint32_t wpre = 0, btotal = 0;
+		#pragma unroll
+		for (int w = 0; w < 8; ++w) { if (w < warp) wpre += s_w[w]; btotal += s_w[w]; }
+		const uint32_t off = wpre + inc - tlen;
+		const bool staged = btotal + 32u <= A.stage_bytes;
+		if (t == 0 && staged && !slow) sw[btotal >> 2] = 0;         /* the batch's last, partial word is only ever OR-ed into */
+		ngs_lw<uint32_t *> L;
+		L.begin(sw, off);
+		if (staged && btotal) {
+			if (slow) {
+				char *p = s_stage + off;
+				#pragma unroll
+				for (int i = 0; i < 4; ++i) if (len[i]) p += bed_line_bytes(p, A.nt, ctg, i ? E[i - 1] : S0, E[i], D[i]);
+			} else if (tlen) {
+				#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					if (len[i]) {
+						if (i == 0) L.bed_line_cached(hc, n_lo, n_hi, nl, S0, L4s0, E[0], L4e[0], (uint32_t)D[0]);
+						else L.bed_line_cached(hc, n_lo, n_hi, nl, E[i - 1], L4e[i - 1], E[i], L4e[i], (uint32_t)D[i]);
+					}
+				}
+			}
+		}
+		__syncthreads();                                        /* every head word stored */
+		if (staged && !slow && tlen && L.k) atomicOr(L.w, L.carry);
+		if (bt == 0) {
+			if (tile > 0 && !(A.debug & 1)) goff = lookback_bytes(A.stF, tile, total, s_li, s_lb, A.st);
+			else __syncthreads();
+			if (A.debug & 1) goff = tile * 24000ull;
+			if (t == 0 && tile == A.n_tiles - 1) A.st->fmt_bytes = goff + total;
+		} else __syncthreads();
+		if (goff + total > A.out_cap) return;                   /* block-uniform; the host sees fmt_bytes > capacity */
+		char *g = A.out + goff + done_bytes;
+		if (!staged) {                                          /* lines too long for the staging area: straight to global */
+			char *p = g + off;
+			#pragma unroll
+			for (int i = 0; i < 4; ++i) if (len[i]) p += bed_line_bytes(p, A.nt, ctg, i ? E[i - 1] : S0, E[i], D[i]);
+		} else if (btotal) {
+			/* copy-out: head bytes up to the first 16-byte boundary of the output, aligned 128-bit stores whose source
+			 * starts (16 - mis) bytes into the staging area, tail bytes */
+			const uint32_t mis = (uint32_t)((uintptr_t)g & 15);
+			uint32_t hb = (16u - mis) & 15u;
+			if (hb > btotal) hb = btotal;
+			if ((uint32_t)t < hb) g[t] = s_stage[t];
+			const uint32_t nv = (btotal - hb) >> 4;
+			int4 *dst = reinterpret_cast<int4 *>(g + hb);
+			const int4 *src = reinterpret_cast<const int4 *>(s_stage);
+			if (hb == 0) {
+				for (uint32_t c = t; c < nv; c += NGS_COVER_THREADS) dst[c] = src[c];
+			} else {
+				const uint32_t wsh = hb >> 2, sel = 0x3210u + 0x1111u * (hb & 3u);
+				for (uint32_t c = t; c < nv; c += NGS_COVER_THREADS) {
+					const int4 a = src[c], b = src[c + 1];
+					uint32_t v0, v1, v2, v3, v4;
+					if (wsh == 0) { v0 = a.x; v1 = a.y; v2 = a.z; v3 = a.w; v4 = b.x; }
+					else if (wsh == 1) { v0 = a.y; v1 = a.z; v2 = a.w; v3 = b.x; v4 = b.y; }
+					else if (wsh == 2) { v0 = a.z; v1 = a.w; v2 = b.x; v3 = b.y; v4 = b.z; }
+					else { v0 = a.w; v1 = b.x; v2 = b.y; v3 = b.z; v4 = b.w; }
+					int4 o;
+					o.x = (int)__byte_perm(v0, v1, sel); o.y = (int)__byte_perm(v1, v2, sel);
+					o.z = (int)__byte_perm(v2, v3, sel); o.w = (int)__byte_perm(v3, v4, sel);
+					dst[c] = o;
+				}
+			}
+			const uint32_t tb = hb + (nv << 4);
+			if (tb + (uint32_t)t < btotal) g[tb + t] = s_stage[tb + t];
+		}
+		done_bytes += btotal;
+		__syncthreads();                                        /* staging area free for the next batch */
+	}
+}
+
+/* after a cover launch: the halo candidates of the first / last tile that produced a run -> the state block */
+__global__ void k_halo_gather(ngs_dev_state *st, const uint4 *tile_first, const uint4 *tile_last)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	if (st->last_tile_p1 == 0) return;
+	const uint4 a = tile_first[st->first_tile], b = tile_last[st->last_tile_p1 - 1];
+	st->halo_first[0] = a.x; st->halo_first[1] = a.y; st->halo_first[2] = a.z; st->halo_first[3] = a.w;
+	st->halo_last[0] = b.x; st->halo_last[1] = b.y; st->halo_last[2] = b.z; st->halo_last[3] = b.w;
+}

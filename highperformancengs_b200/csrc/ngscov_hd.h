@@ -436,6 +436,7 @@ typedef struct {
 	uint64_t records, kept, m_ops, cigar_words;
 	uint32_t max_ref_p1;         /* 1 + highest refID seen (0: none): sorted input => every lower contig is complete */
 } ngs_counts;
+typedef struct { uint32_t records, kept, m_ops, cigar_words, max_ref_p1; } ngs_counts32;   /* one row's worth */
 
 typedef struct {
 	int32_t  n_ref;
@@ -446,74 +447,78 @@ typedef struct {
 	uint32_t end_pos;            /* (end_ctg = -2: no slice).  Such a record counts as "the next contig has begun" */
 } ngs_walk_cfg;
 
-/* ---- compact record table (K1 -> K2) --------------------------------------------------------------
- * K1 (k_chain_walk) frames AND decodes: every record that contributes at least one M interval leaves one
- * 8-byte entry in the row of the sub-chunk it starts in, so that K2 never reads the stream again for
- * ordinary records:
- *   x = pos (29 bits, the record's POS) | cdelta << 29   (contig = row_ctg[row] + cdelta, cdelta 0..6)
+/* ---- compact record table (K1 -> owner tiles) ---------------------------------------------------
+ * K1 (k_chain_classify) frames AND decodes: every record that contributes at least one M interval leaves one
+ * 8-byte entry in the ROW of the sub-chunk it starts in (at most NGS_ROW_SLOTS entries per row), so that the
+ * stream is never read a second time for ordinary records:
+ *   x = pos (29 bits, the record's POS) | cdelta << 29   (contig = row.ctg + cdelta, cdelta 0..6)
  *   y = kind << 30 | payload
  *       SIMPLE  payload = len               one interval [pos, pos+len)  (abutting M ops are merged: the
  *                                           zero-net deltas between them are transparent to the sweep)
  *       PAIR    payload = len1 | gap << 12 | len2 << 18   [pos, pos+len1) and [pos+len1+gap, .. +len2)
- *       CHAIN   payload = byte offset of the record from the row's entry point: decode it from the stream
- *                         (long CIGARs, leading D/N, 28-bit key aliasing, more than six contigs in a row)
- * Deltas are applied by the OWNER of the tile they fall into (k_owner_tiles: plain stores, no atomics on
- * HBM) when the record is "near": the owner of tile T sees every record of its contig with
- * P0(T) - NGS_NEAR_H <= pos < P0(T) + tile size.  Every other delta is "far" and is added afterwards with
- * a RED (k_far_reds).  Both kernels evaluate ngs_delta_is_near, so each delta is applied exactly once. */
+ *       CHAIN   payload = byte offset of the record from the row's entry point: decoded from the stream by
+ *                         k_special_reds while the chunk is still resident (long CIGARs, leading D/N, 28-bit
+ *                         key aliasing, records reaching outside the shard's clip range, more than seven
+ *                         contigs in one row)
+ * SIMPLE and PAIR records lie entirely inside [clip_lo, lim] of their segment and below 2^28, so the owner of a
+ * tile applies them without any clipping.
+ * A delta at position q of a record starting at pos is applied by the OWNER of q's tile (k_cover: shared-memory
+ * accumulation, never materialised in HBM) when the record is visible to it: P0(tile(q)) - NGS_NEAR_H <= pos.
+ * Every other delta is "far" and is added to the global difference array with a RED by k_special_reds, which
+ * also raises the tile's far flag so that the owner merges that tile of the array.  Both kernels evaluate
+ * ngs_delta_is_near, so each delta is applied exactly once. */
 #define NGS_ENT_SIMPLE  0u
 #define NGS_ENT_PAIR    1u
 #define NGS_ENT_CHAIN   2u
 #define NGS_ENT_CDELTA_MAX 6u
+#define NGS_ROW_SLOTS   256            /* entries per row = threads of an owner CTA */
 #define NGS_NEAR_H      512            /* positions before a tile from which records are visible to its owner */
-#define NGS_OWN_TILE    8192           /* positions per owner tile (k_owner_tiles); multiple of NGS_TILE */
-#define NGS_TILE        2048           /* positions per scan tile (k_scan_emit); per-tile aggregates have this grain */
+#define NGS_CT          4096           /* positions per owner tile (k_cover) = elements per difference-array tile */
 #define NGS_KEY_NONE    0xFFFFFFFFFFFFFFFFull
+#define NGS_ROW_UNSORTED 0x80000000u   /* row.special: record keys decrease inside the row */
+#define NGS_ROW_OVERFLOW 0x40000000u   /* row.special: more entries than slots -- the whole row goes the RED way */
+
+/* per-row (= per sub-chunk) metadata written by K1 together with the entries */
+typedef struct {
+	uint64_t fk, lk;             /* sort key of the first / last record starting in the row (fk = NGS_KEY_NONE: none) */
+	uint32_t count;              /* entries stored (0 when the row overflowed) */
+	uint32_t special;            /* CHAIN + possibly-far entries | NGS_ROW_* flags */
+	int32_t  ctg;                /* contig of cdelta 0 (-1: no entry) */
+	uint32_t nrec;               /* records starting in the row */
+	uint32_t nkept, nmops, ncig; /* as ngs_counts, for this row */
+	uint32_t max_ref_p1;
+	uint64_t pad0, pad1;
+} ngs_row;
 
 /* sort key of a record: samtools sorts by (refID as unsigned, pos); unmapped (refID -1) sort last */
 NGS_HD uint64_t ngs_sort_key(int32_t ref_id, int32_t pos) { return ((uint64_t)(uint32_t)ref_id << 32) | (uint32_t)(pos + 1); }
 
-/* one M interval [a, b) in RAW contig coordinates -> clipped element range of the segment; returns 0 when it
- * contributes nothing.  Exactly the arithmetic of ngs_decode_record (28-bit keys, clip to the shard, hard end). */
-NGS_HD int ngs_clip_interval(const ngs_seg &sg, uint32_t a_raw, uint32_t b_raw, uint32_t &a, uint32_t &b, int &range_error)
+/* Is the delta at contig position q (inside its segment) of a record starting at rec_pos applied by the owner of
+ * q's tile?  The tile grid of a segment starts at clip_lo. */
+NGS_HD int ngs_delta_is_near(uint32_t clip_lo, uint32_t rec_pos, uint32_t q)
 {
-	a = a_raw & NGS_POS_MASK; b = b_raw & NGS_POS_MASK;
-	if (a == b) return 0;
-	if (b < a) { range_error = 1; return 0; }
-	if (b > sg.lim) {
-		if (sg.hard_end) { range_error = 1; return 0; }
-		b = sg.lim;
-	}
-	if (a < sg.clip_lo) a = sg.clip_lo;
-	return a < b;
-}
-/* Is the delta at (clipped) contig position q of a record starting at rec_pos applied by the owner of q's tile?
- * `aliased`: the record touches positions >= 2^28 (its keys wrap, so its deltas are not where the sort order says). */
-NGS_HD int ngs_delta_is_near(const ngs_seg &sg, uint32_t rec_pos, uint32_t q, int aliased)
-{
-	if (aliased) return 0;
-	const int64_t p0 = (int64_t)sg.clip_lo + (int64_t)((q - sg.clip_lo) / NGS_OWN_TILE) * NGS_OWN_TILE;
+	const int64_t p0 = (int64_t)clip_lo + (int64_t)((q - clip_lo) / NGS_CT) * NGS_CT;
 	return (int64_t)rec_pos >= p0 - NGS_NEAR_H;
 }
 
-/* Intervals of a SIMPLE / PAIR entry in raw coordinates: n = 1 or 2 */
+/* Intervals of a SIMPLE / PAIR entry in contig coordinates: n = 1 or 2 */
 NGS_HD int ngs_entry_intervals(uint32_t pos, uint32_t y, uint32_t a[2], uint32_t b[2])
 {
 	const uint32_t kind = y >> 30, pl = y & 0x3FFFFFFFu;
 	a[0] = pos;
-	if (kind == NGS_ENT_SIMPLE) { b[0] = pos + pl; return 1; }
+	if (kind == NGS_ENT_SIMPLE) { b[0] = pos + pl; a[1] = b[1] = 0; return 1; }
 	b[0] = pos + (pl & 0xFFFu);
 	a[1] = b[0] + ((pl >> 12) & 0x3Fu);
 	b[1] = a[1] + (pl >> 18);
 	return 2;
 }
 
-/* What K1 learns about one record (Cig(i) returns CIGAR word i).  ret: 0 = no entry (filtered / nothing to count);
- * 1 = entry (x_pos, y) to store.  end_raw = reference end of the last M interval (for the tile plan), far = the
- * record may own a far delta.  Counters as ngs_decode_record. */
-template <class Cig>
+/* What K1 learns about one record (cig(i) returns CIGAR word i).  Returns 0 = no entry (filtered / nothing to count);
+ * 1 = entry word y to store (its x is pos | cdelta << 29, made by the caller); special = 1 when the entry is CHAIN or
+ * may own a far delta.  Counters as ngs_decode_record except m_ops, which counts MERGED intervals here. */
+template <class Cig, class Cnt>
 NGS_HD int ngs_classify_record(const ngs_walk_cfg &cfg, const ngs_hdr &h, uint32_t slot_off, Cig &cig,
-                               uint32_t &y, uint32_t &end_raw, int &far, ngs_counts &cnt)
+                               uint32_t &y, int &special, Cnt &cnt)
 {
 	cnt.records += 1; cnt.cigar_words += h.n_cigar;
 	{
@@ -525,33 +530,37 @@ NGS_HD int ngs_classify_record(const ngs_walk_cfg &cfg, const ngs_hdr &h, uint32
 	cnt.kept += 1;
 	const int32_t si = cfg.ctg2seg[h.ref_id];
 	if (si < 0 || h.n_cigar == 0) return 0;
-	/* walk the CIGAR: intervals with abutting ones merged */
-	uint32_t p = (uint32_t)h.pos, na = 0, ia[2] = { 0, 0 }, ib[2] = { 0, 0 };
-	uint32_t ca = 0, cb = 0; int open = 0;
+	/* walk the CIGAR: M intervals with abutting ones merged */
+	const uint32_t pos = (uint32_t)h.pos;
+	uint32_t p = pos, na = 0, a0 = 0, b0 = 0, a1 = 0, b1 = 0, ca = 0, cb = 0;
+	int open = 0, wrapped = 0;
 	for (uint32_t i = 0; i < h.n_cigar; ++i) {
 		const uint32_t w = cig(i), op = w & 0xf, len = w >> 4;
 		if (op == 0) {
 			if (len == 0) continue;
 			if (open && cb == p) cb = p + len;
 			else {
-				if (open) { if (na < 2) { ia[na] = ca; ib[na] = cb; } ++na; }
+				if (open) { if (na == 0) { a0 = ca; b0 = cb; } else if (na == 1) { a1 = ca; b1 = cb; } ++na; }
 				ca = p; cb = p + len; open = 1;
 			}
+			if (p + len < p) wrapped = 1;
 			p += len;
-		} else if (op == 2 || op == 3) p += len;
+		} else if (op == 2 || op == 3) { if (p + len < p) wrapped = 1; p += len; }
 	}
 	if (!open) return 0;                                 /* no M at all */
-	if (na < 2) { ia[na] = ca; ib[na] = cb; }
+	if (na == 0) { a0 = ca; b0 = cb; } else if (na == 1) { a1 = ca; b1 = cb; }
 	++na;
-	end_raw = cb;
+	cnt.m_ops += na;
 	const ngs_seg &sg = cfg.seg[si];
-	const int aliased = cb > NGS_POS_MASK || cb < (uint32_t)h.pos;     /* wraps the 28-bit keys (or 32 bits) */
-	far = aliased || (uint32_t)h.pos + NGS_NEAR_H < sg.clip_lo || cb - (uint32_t)h.pos > NGS_NEAR_H;
-	if (!aliased && ia[0] == (uint32_t)h.pos) {
-		if (na == 1 && ib[0] - ia[0] < (1u << 30)) { y = (NGS_ENT_SIMPLE << 30) | (ib[0] - ia[0]); return 1; }
-		if (na == 2 && ib[0] - ia[0] < 4096u && ia[1] - ib[0] < 64u && ib[1] - ia[1] < 4096u) {
-			y = (NGS_ENT_PAIR << 30) | (ib[0] - ia[0]) | ((ia[1] - ib[0]) << 12) | ((ib[1] - ia[1]) << 18);
-			return 1;
+	/* entirely inside the tracked range of the segment and below the 28-bit key wrap? */
+	const int inside = !wrapped && cb <= NGS_POS_MASK && pos >= sg.clip_lo && cb <= sg.lim;
+	special = 1;
+	if (inside && a0 == pos) {
+		const int far = cb - pos > NGS_NEAR_H;            /* a delta further than H from POS may fall outside its owner's view */
+		if (na == 1 && b0 - a0 < (1u << 30)) { y = (NGS_ENT_SIMPLE << 30) | (b0 - a0); special = far; return 1; }
+		if (na == 2 && b0 - a0 < 4096u && a1 - b0 < 64u && b1 - a1 < 4096u) {
+			y = (NGS_ENT_PAIR << 30) | (b0 - a0) | ((a1 - b0) << 12) | ((b1 - a1) << 18);
+			special = far; return 1;
 		}
 	}
 	y = (NGS_ENT_CHAIN << 30) | slot_off;

@@ -75,7 +75,15 @@ struct ngs_dev_state {
 	/* format */
 	unsigned long long fmt_ticket;
 	unsigned long long fmt_bytes;
+	/* cover pipeline */
+	unsigned long long key_seed;       /* running max of the record sort keys over the chunks already committed */
+	unsigned long long key_chunk_max;  /* ... including the chunk being verified (committed by k_finalize_chunk) */
+	unsigned int unsorted;             /* verify pass: a record key decreases (only meaningful in a clean pass) */
+	unsigned int n_special;            /* CHAIN / possibly-far entries seen */
+	unsigned long long first_tile, last_tile_p1;   /* cover: first / 1 + last tile holding a non-zero run */
+	unsigned int halo_first[4], halo_last[4];      /* start, end, depth, contig of the first / last non-zero run */
 };
+#define NGS_FLAG_STALL   4u           /* a look-back wait hit its watchdog bound (predecessor tile never published) */
 
 /* numeric value of an exit slot for the running max */
 __device__ __forceinline__ long long exit_num(long long x) { return x == NGS_EXIT_INVALID ? 0 : x; }
@@ -207,6 +215,9 @@ struct IngestArgs {
 	unsigned long long *ctr;               /* [NGS_CTR_STRIPES][16] striped counters: records, kept, m_ops, cigar_words */
 	long long fixed_entry0;                /* used when entry0_from_state == 0 */
 	int entry0_from_state;                 /* 1: first entry = st->entry_next (streamed pushes) */
+	/* compact record table (cover pipeline, ngscov_cover.cuh): this chunk's rows, one per sub-chunk */
+	ngs_row *rows; uint2 *ent; unsigned long long *rkmax;
+	uint32_t *far_flag;                    /* [n_tiles] raised when a far delta was added to a tile of the difference array */
 };
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
@@ -894,6 +905,7 @@ __global__ void __launch_bounds__(256) k_finalize_chunk(const uint8_t *base, int
 	if (threadIdx.x == 0) {
 		st->carry_len = len;
 		st->entry_next = len ? -(long long)len : (ce >= NGS_EXIT_INF ? 0 : ce - n);
+		if (st->key_chunk_max > st->key_seed) st->key_seed = st->key_chunk_max;
 	}
 }
 

@@ -64,7 +64,9 @@ enum {                       /* error codes */
 	NGSCOV_ERANGE    = -5,   /* an alignment reaches beyond contig end + NGSCOV_OVERHANG_PAD (the
 	                            reference's own behaviour is undefined there) */
 	NGSCOV_ESTATE    = -6,   /* call sequence violated */
-	NGSCOV_ETOOBIG   = -7    /* record header+CIGAR larger than the carry area */
+	NGSCOV_ETOOBIG   = -7,   /* record header+CIGAR larger than the carry area */
+	NGSCOV_EUNSORTED = -8    /* the input is not coordinate sorted and contigs had already been finalized while streaming
+	                            (unsorted input that is detected earlier is still processed, on a slower path) */
 };
 
 #define NGSCOV_OVERHANG_PAD 65536u   /* positions past a contig's end that are still tracked */
