@@ -94,7 +94,7 @@ struct ngscov {
 	size_t p_row0;                           /* first global row of the pending chunk */
 	unsigned long long *d_kbmax;
 	uint32_t *d_far_flag, *d_row_a, *d_row_b;
-	unsigned long long *d_stF;
+	unsigned long long *d_stF, *d_stC;       /* look-back words of the owner tiles: bytes / (sum, last boundary) */
 	uint4 *d_tile_first, *d_tile_last;
 	bool halo_have; ngscov_run cov_first, cov_last;   /* first / last non-zero run over the cover launches so far */
 	size_t bed_begin;                        /* halo: bytes of the dropped first line */
@@ -323,8 +323,9 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	h->fused = h->ingest_mode != 0;
 	h->cover = !(getenv("NGSCOV_INGEST") || getenv("NGSCOV_FUSED") || (getenv("NGSCOV_PIPELINE") && !strcmp(getenv("NGSCOV_PIPELINE"), "classic")));
 	if (h->cover) {
-		const size_t nt = std::max<uint64_t>(1, h->n_tiles);
+		const size_t nt = std::max<uint64_t>(1, h->n_tiles) * NGS_CPT;      /* owner tiles */
 		CK(cudaMalloc((void **)&h->d_far_flag, nt * 4)); CK(cudaMemset(h->d_far_flag, 0, nt * 4));
+		CK(cudaMalloc((void **)&h->d_stC, nt * 8));
 		CK(cudaMalloc((void **)&h->d_row_a, nt * 4)); CK(cudaMalloc((void **)&h->d_row_b, nt * 4));
 		CK(cudaMalloc((void **)&h->d_stF, nt * 8));
 		CK(cudaMalloc((void **)&h->d_tile_first, nt * 16)); CK(cudaMalloc((void **)&h->d_tile_last, nt * 16));
@@ -345,7 +346,7 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	                h->d_name_off, h->d_wighdr, h->d_wighdr_off, h->d_chunk[0], h->d_chunk[1], h->d_carry, h->d_entry, h->d_exit,
 	                h->d_bmax, h->d_count, h->d_slots, h->d_ctr, h->d_st, h->d_run_start, h->d_run_end, h->d_run_depth, h->d_rec_base, h->d_stA, h->d_stB,
 	                h->d_fmt_status, h->d_text[0], h->d_text[1], h->d_text[2], h->d_text[3],
-	                h->d_ent, h->d_rows, h->d_rkmax, h->d_kbmax, h->d_far_flag, h->d_row_a, h->d_row_b, h->d_stF, h->d_tile_first, h->d_tile_last };
+	                h->d_ent, h->d_rows, h->d_rkmax, h->d_kbmax, h->d_far_flag, h->d_row_a, h->d_row_b, h->d_stF, h->d_stC, h->d_tile_first, h->d_tile_last };
 	for (void *p : dev) if (p) cudaFree(p);
 	for (int i = 0; i < 2; ++i) if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
 	for (int i = 0; i < 4; ++i) if (h->h_text[i]) cudaFreeHost(h->h_text[i]);
@@ -378,7 +379,7 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	CK(cudaStreamSynchronize(h->s_main)); CK(cudaStreamSynchronize(h->s_copy));
 	if (h->diff_dirty) {            /* pushes were made but the scan (which re-zeroes) never ran */
 		tic(h);
-		if (h->d_far_flag) CK(cudaMemsetAsync(h->d_far_flag, 0, std::max<uint64_t>(1, h->n_tiles) * 4, h->s_main));
+		if (h->d_far_flag) CK(cudaMemsetAsync(h->d_far_flag, 0, std::max<uint64_t>(1, h->n_tiles) * NGS_CPT * 4, h->s_main));
 		CK(cudaMemsetAsync(h->d_diff, 0, h->n_elems * sizeof(int), h->s_main));
 		h->stats.ms_zero = toc(h);
 		h->diff_dirty = false;
@@ -1255,8 +1256,8 @@ static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_
 {
 	int r;
 	const bool text = h->cfg.mode == NGSCOV_MODE_DEPTH;
-	const uint64_t t0 = h->seg[s0].tile0, t1 = s1 < h->seg.size() ? h->seg[s1].tile0 : h->n_tiles;
-	const uint64_t elems = (t1 - t0) * (uint64_t)NGS_TILE;
+	const uint64_t t0 = h->seg[s0].tile0 * NGS_CPT, t1 = (s1 < h->seg.size() ? h->seg[s1].tile0 : h->n_tiles) * NGS_CPT;   /* owner tiles */
+	const uint64_t elems = (t1 - t0) * (uint64_t)NGS_CT;
 	size_t bound = 0; uint32_t stage = 0;
 	if (text) {
 		/* boundaries: at most two per accumulated interval, never more than tracked positions; depth <= intervals */
@@ -1272,7 +1273,7 @@ static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_
 		bound = nb * max_line;
 		/* the staging area of a batch (1024 lines) is sized for depths below 10^5; a batch that needs more writes its
 		 * lines straight to global memory */
-		stage = (uint32_t)std::min<size_t>(1024 * typ_line + 32, 64 * 1024);
+		stage = (uint32_t)std::min<size_t>(NGS_CBATCH * typ_line + 32, 64 * 1024);
 		if (getenv("NGSCOV_COVER_STAGE")) stage = (uint32_t)atoi(getenv("NGSCOV_COVER_STAGE"));
 		if ((r = grow_text(h, NGSCOV_OUT_BEDGRAPH, h->bed_off + bound + 64, h->bed_off))) return r;
 		h->text_ready[NGSCOV_OUT_BEDGRAPH] = true; h->h_text_valid[NGSCOV_OUT_BEDGRAPH] = false;
@@ -1286,15 +1287,15 @@ static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_
 		CK(cudaMemcpyAsync((char *)h->d_st + o2, (const char *)h->h_tmpl + o2, o3 - o2, cudaMemcpyHostToDevice, h->s_main));
 	}
 	if (t1 > t0) {
-		CK(cudaMemsetAsync(h->d_stB + t0, 0, (t1 - t0) * 8, h->s_main));
+		CK(cudaMemsetAsync(h->d_stC + t0, 0, (t1 - t0) * 8, h->s_main));
 		if (text) CK(cudaMemsetAsync(h->d_stF + t0, 0, (t1 - t0) * 8, h->s_main));
-		k_tile_rows<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, h->s_main>>>(h->d_rkmax, (uint32_t)h->rows_used, h->d_tile2seg + t0, h->d_seg, t0, t1 - t0,
+		k_tile_rows<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, h->s_main>>>(h->d_rkmax, (uint32_t)h->rows_used, h->d_tile2seg, h->d_seg, t0, t1 - t0,
 		                                                                   h->d_row_a + t0, h->d_row_b + t0);
 		CoverArgs A;
-		A.n_tiles = t1 - t0; A.tile_off = t0; A.tile2seg = h->d_tile2seg + t0; A.seg = h->d_seg;
+		A.n_tiles = t1 - t0; A.tile_off = t0; A.tile2seg = h->d_tile2seg; A.seg = h->d_seg;
 		A.ent = h->d_ent; A.rows = h->d_rows; A.row_a = h->d_row_a + t0; A.row_b = h->d_row_b + t0;
-		A.diff = h->d_diff + t0 * (uint64_t)NGS_TILE; A.far_flag = h->d_far_flag + t0;
-		A.stB = h->d_stB + t0; A.stF = h->d_stF + t0;
+		A.diff = h->d_diff + t0 * (uint64_t)NGS_CT; A.far_flag = h->d_far_flag + t0;
+		A.stB = h->d_stC + t0; A.stF = h->d_stF + t0;
 		A.bins = h->d_bins; A.window = h->cfg.window; A.variant = h->cfg.mode == NGSCOV_MODE_WIG ? 1 : 0;
 		A.tile_first = h->d_tile_first + t0; A.tile_last = h->d_tile_last + t0;
 		A.nt.names = h->d_names; A.nt.name_off = h->d_name_off; A.nt.name8 = h->d_name8;

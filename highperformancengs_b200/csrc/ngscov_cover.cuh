@@ -24,9 +24,11 @@
 #pragma once
 #include "ngscov_kernels.cuh"
 
+#ifndef NGS_COVER_THREADS
 #define NGS_COVER_THREADS 256
+#endif
 #ifndef NGS_COVER_MINB
-#define NGS_COVER_MINB 4
+#define NGS_COVER_MINB 3
 #endif
 #define NGS_WATCHDOG_POLLS (1u << 26)      /* look-back polls of one entry before the wait is abandoned (seconds) */
 
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(256) k_verify_check_k(const long long *entry, 
 /* ---- the rare records ------------------------------------------------------------------------------------- */
 struct FarSink {                     /* RED into the global array + far flag of the element's tile */
 	int *diff; uint32_t *far_flag; unsigned int *flags; int mark;
-	__device__ __forceinline__ void one(uint64_t idx, int v) { atomicAdd(diff + idx, v); if (mark) far_flag[idx / NGS_TILE] = 1u; }
+	__device__ __forceinline__ void one(uint64_t idx, int v) { atomicAdd(diff + idx, v); if (mark) far_flag[idx / NGS_CT] = 1u; }
 	__device__ __forceinline__ void add2(uint64_t ia, uint64_t ib, int sign) { one(ia, sign); one(ib, -sign); }
 	__device__ __forceinline__ void flag_range_error() { atomicOr(flags, NGS_FLAG_ERANGE); }
 };
@@ -391,8 +393,8 @@ __global__ void __launch_bounds__(256) k_tile_rows(const unsigned long long *rkm
 {
 	const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (tile >= n_tiles) return;
-	const ngs_seg &sg = seg[tile2seg[tile]];
-	const uint64_t p0 = (uint64_t)sg.clip_lo + (tile + tile_off - sg.tile0) * NGS_CT;
+	const ngs_seg &sg = seg[tile2seg[(tile + tile_off) / NGS_CPT]];       /* tile2seg: one entry per difference-array tile, not pre-offset */
+	const uint64_t p0 = (uint64_t)sg.clip_lo + (tile + tile_off - sg.tile0 * NGS_CPT) * NGS_CT;
 	const uint64_t lo_pos = p0 > NGS_NEAR_H ? p0 - NGS_NEAR_H : 0;
 	const unsigned long long ka = ((unsigned long long)sg.contig << 32) | (lo_pos + 1), kb = ((unsigned long long)sg.contig << 32) | (p0 + NGS_CT + 1);
 	uint32_t lo = 0, hi = n_rows;                       /* first row with rkmax >= ka */
@@ -421,14 +423,22 @@ struct CoverArgs {
 	ngs_dev_state *st;
 };
 
-/* padded accumulator index: 16 consecutive elements per thread, 4 ints of padding -> conflict-free 128-bit reads */
-__device__ __forceinline__ int acc_idx(int i) { return i + ((i >> 4) << 2); }
+/* padded accumulator index: NGS_CITEMS consecutive elements per thread + 4 ints of padding -> conflict-free 128-bit reads */
+#define NGS_CITEMS (NGS_CT / NGS_COVER_THREADS)          /* elements per thread: 8 or 16 */
+__device__ __forceinline__ int acc_idx(int i) { return i + (i / NGS_CITEMS) * 4; }
+#define NGS_ACC_INTS (NGS_CT * 3 / 2)                    /* >= padded accumulators; = u16 [NGS_CT] + i32 [NGS_CT] of the boundary list */
+#define NGS_ACC_USED (NGS_CT / NGS_CITEMS * (NGS_CITEMS + 4))
+#ifndef NGS_CIPT
+#define NGS_CIPT 5                                       /* consecutive boundaries per thread per text batch */
+#endif
+#define NGS_CBATCH (NGS_COVER_THREADS * NGS_CIPT)
+#define NGS_CNW (NGS_COVER_THREADS / 32)                 /* warps per owner CTA */
+#define NGS_ROW_PASSES (NGS_ROW_SLOTS / NGS_COVER_THREADS)
 
-/* generic bedGraph line, byte by byte (long contig names, depths outside [0, 10^9), staging overflow) */
+/* generic bedGraph line, byte by byte (tiles with a long contig name or positions below 10^4, staging overflow) */
 __device__ __noinline__ uint32_t bed_line_bytes(char *dst, const NameTable nt, uint32_t ctg, uint32_t s, uint32_t e, int d)
 {
 	const uint32_t a = nt.name_off[ctg], nl = nt.name_off[ctg + 1] - a;
-	if (!dst) return nl + ngs_ndigits(s) + ngs_ndigits(e) + ngs_len_i32(d) + 3u;
 	char *p = dst;
 	for (uint32_t i = 0; i < nl; ++i) p[i] = nt.names[a + i];
 	p += nl;
@@ -436,6 +446,23 @@ __device__ __noinline__ uint32_t bed_line_bytes(char *dst, const NameTable nt, u
 	p += ngs_put_u32(p, e); *p++ = '\t';
 	p += ngs_put_i32(p, d); *p++ = '\n';
 	return (uint32_t)(p - dst);
+}
+/* one line through the register writer with full conversions (a start before the tile, depth of five digits or more) */
+/* (the writer state travels by value: a reference would pin it in local memory for the whole text loop) */
+__device__ __noinline__ uint4 lw_generic_line(uint32_t *w, uint32_t carry, uint32_t k, uint32_t n_lo, uint32_t n_hi, uint32_t nl, uint32_t s, uint32_t e, uint32_t d)
+{
+	ngs_lw<uint32_t *> L; L.w = w; L.carry = carry; L.k = k;
+	ngs_num xs, xe, xd;
+	ngs_num_conv(s, xs); ngs_num_conv(e, xe); ngs_num_conv(d, xd);
+	L.bed_line(n_lo, n_hi, nl, xs, xe, xd);
+	return make_uint4((uint32_t)(L.w - w), L.carry, L.k, 0u);
+}
+/* thread 0 / 1: the cached prefixes "name\tH" and "\tH" for H0 and H0 + 1 (positions of a tile span at most two H) */
+__device__ __noinline__ void fill_tile_hcache(ngs_hcache *dst, uint32_t H, uint32_t n_lo, uint32_t n_hi, uint32_t nl)
+{
+	ngs_hcache c;
+	ngs_hcache_fill(c, H, n_lo, n_hi, nl);
+	*dst = c;
 }
 
 /* block-wide look-back over one status word per tile (status:2 | payload:62, payload added up), thread i inspects
@@ -459,14 +486,14 @@ __device__ __forceinline__ unsigned long long lookback_bytes(unsigned long long 
 		__syncthreads();
 		unsigned int first_inc = 0xffffffffu;
 		#pragma unroll
-		for (int w = 0; w < 8; ++w) first_inc = s_li[w] < first_inc ? s_li[w] : first_inc;
+		for (int w = 0; w < NGS_CNW; ++w) first_inc = s_li[w] < first_inc ? s_li[w] : first_inc;
 		unsigned long long v = (unsigned)t <= first_inc ? (a & 0x3FFFFFFFFFFFFFFFull) : 0;
 		#pragma unroll
 		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 		if (lane == 0) s_lb[warp] = v;
 		__syncthreads();
 		#pragma unroll
-		for (int w = 0; w < 8; ++w) run += s_lb[w];
+		for (int w = 0; w < NGS_CNW; ++w) run += s_lb[w];
 		if (first_inc != 0xffffffffu) break;
 		base -= NGS_COVER_THREADS;
 		__syncthreads();
@@ -475,87 +502,104 @@ __device__ __forceinline__ unsigned long long lookback_bytes(unsigned long long 
 	return run;
 }
 
+/* rare: the tile's share of the far array */
+__device__ __noinline__ void merge_far_tile(int *g, int *s_tile, uint32_t *flag)
+{
+	const int t = threadIdx.x;
+	for (int j = 0; j < NGS_CITEMS; ++j) {
+		const int i = j * NGS_COVER_THREADS + t;
+		const int v = g[i];
+		if (v) { s_tile[acc_idx(i)] += v; g[i] = 0; }
+	}
+	if (t == 0) *flag = 0;
+}
+
 template <bool TEXT>
 __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(const __grid_constant__ CoverArgs A)
 {
 	extern __shared__ __align__(16) char s_stage[];
-	__shared__ __align__(16) int s_tile[NGS_SCAN_SMEM / 4];   /* phase 1: padded accumulators (20 KB); phase 2: compact boundary list
+	__shared__ __align__(16) int s_tile[NGS_ACC_INTS];        /* phase 1: padded accumulators; phase 2: compact boundary list
 	                                                             (u16 position [NGS_CT] + i32 local depth [NGS_CT]) */
-	__shared__ long long s_wsum[8]; __shared__ unsigned int s_wcnt[8], s_wlast[8];
-	__shared__ unsigned int s_lb_inc[8], s_lb_last[8]; __shared__ long long s_lb_sum[8];
-	__shared__ long long s_bk[8], s_bv[8];
-	__shared__ unsigned int s_wr[8]; __shared__ int s_wmax[8], s_wmin[8];
-	__shared__ unsigned int s_rfirst[8], s_rlast[8], s_wlen[8];
-	__shared__ unsigned int s_w[8], s_li[8];
-	__shared__ unsigned long long s_lb[8];
+	__shared__ ngs_hcache s_hc[2];
+	__shared__ unsigned int s_rcnt[32]; __shared__ int s_rctg[32];
+	__shared__ long long s_wsum[NGS_CNW]; __shared__ unsigned int s_wcnt[NGS_CNW], s_wlast[NGS_CNW];
+	__shared__ unsigned int s_lb_inc[NGS_CNW], s_lb_last[NGS_CNW]; __shared__ long long s_lb_sum[NGS_CNW];
+	__shared__ long long s_bk[NGS_CNW], s_bv[NGS_CNW];
+	__shared__ unsigned int s_wr[NGS_CNW]; __shared__ int s_wmax[NGS_CNW], s_wmin[NGS_CNW];
+	__shared__ unsigned int s_rfirst[NGS_CNW], s_rlast[NGS_CNW];
+	__shared__ unsigned int s_w[NGS_CNW], s_li[NGS_CNW];
+	__shared__ unsigned long long s_lb[NGS_CNW];
 
 	const unsigned full = 0xffffffffu;
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	const uint64_t tile = blockIdx.x;                    /* launch-local; dispatch order = tile order (see k_scan_runs) */
+	const uint64_t tile = blockIdx.x;                    /* launch-local cover tile; dispatch order = tile order (see k_scan_runs) */
 	if (tile >= A.n_tiles) return;
-	const uint32_t si = A.tile2seg[tile];
+	const uint64_t tile_g = tile + A.tile_off;
+	const uint32_t si = A.tile2seg[tile_g / NGS_CPT];    /* tile2seg is NOT pre-offset: one entry per difference-array tile */
 	const uint32_t ra = A.row_a[tile], rb = A.row_b[tile], far = A.far_flag[tile];
 	#pragma unroll
-	for (int j = 0; j < (NGS_CT * 20 / 16) / 4 / NGS_COVER_THREADS; ++j) reinterpret_cast<int4 *>(s_tile)[j * NGS_COVER_THREADS + t] = make_int4(0, 0, 0, 0);
+	for (int j = 0; j < NGS_ACC_USED / 4 / NGS_COVER_THREADS; ++j) reinterpret_cast<int4 *>(s_tile)[j * NGS_COVER_THREADS + t] = make_int4(0, 0, 0, 0);
 	const ngs_seg sg = A.seg[si];
-	const uint64_t tile_g = tile + A.tile_off;
-	const uint32_t pos0 = sg.clip_lo + (uint32_t)((tile_g - sg.tile0) * NGS_CT);
-	__syncthreads();
+	const uint32_t pos0 = sg.clip_lo + (uint32_t)((tile_g - sg.tile0 * NGS_CPT) * NGS_CT);
+	const uint32_t ctg = sg.contig;
+	const uint32_t nl = A.nt.name_off[ctg + 1] - A.nt.name_off[ctg];
+	const unsigned long long name8 = A.nt.name8[ctg];
+	const uint32_t n_lo = (uint32_t)name8, n_hi = (uint32_t)(name8 >> 32);
+	const uint32_t H0 = pos0 / 10000u;
+	if (TEXT && t < 2 && H0 != 0 && nl <= 8u) fill_tile_hcache(&s_hc[t], H0 + (uint32_t)t, n_lo, n_hi, nl);
 
-	/* ---- gather: +1/-1 of every visible record into the shared accumulators (four rows in flight per thread) */
+	/* ---- gather: +1/-1 of every visible record into the shared accumulators.  The row headers of up to 32 rows go
+	 * through shared memory first, so the entry loads of all rows are independent of each other */
 	{
 		const int64_t vis_lo = (int64_t)pos0 - NGS_NEAR_H;
-		for (uint32_t r0 = ra; r0 < rb; r0 += 4) {
-			uint32_t cnt[4]; int ctg[4]; uint2 e[4];
-			#pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				cnt[j] = 0; ctg[j] = 0;
-				if (r0 + j < rb) { const uint4 m = __ldg(reinterpret_cast<const uint4 *>(A.rows + r0 + j) + 1); cnt[j] = m.x; ctg[j] = (int)m.z; }
-			}
-			#pragma unroll
-			for (int j = 0; j < 4; ++j) { e[j] = make_uint2(0, NGS_ENT_CHAIN << 30); if ((uint32_t)t < cnt[j]) e[j] = __ldg(A.ent + (size_t)(r0 + j) * NGS_ROW_SLOTS + t); }
-			#pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				const uint32_t kind = e[j].y >> 30, pos = e[j].x & 0x1FFFFFFFu;
-				if (kind == NGS_ENT_CHAIN || ctg[j] + (int)(e[j].x >> 29) != (int)sg.contig || (int64_t)pos < vis_lo) continue;
-				const uint32_t pl = e[j].y & 0x3FFFFFFFu;
-				const uint32_t a0 = pos - pos0;                         /* wraps to a huge value for pos < pos0: fails the < NGS_CT test */
-				uint32_t b0;
-				if (kind == NGS_ENT_SIMPLE) b0 = a0 + pl;
-				else {
-					b0 = a0 + (pl & 0xFFFu);
-					const uint32_t a1 = b0 + ((pl >> 12) & 0x3Fu), b1 = a1 + (pl >> 18);
-					if (a1 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)a1)], 1);
-					if (b1 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)b1)], -1);
+		for (uint32_t rbase = ra; rbase < rb; rbase += 32) {
+			const uint32_t nr = rb - rbase < 32u ? rb - rbase : 32u;
+			__syncthreads();                                 /* accumulators zeroed / previous row headers consumed */
+			if ((uint32_t)t < nr) { const uint4 m = __ldg(reinterpret_cast<const uint4 *>(A.rows + rbase + t) + 1); s_rcnt[t] = m.x; s_rctg[t] = (int)m.z; }
+			__syncthreads();
+			/* a row has NGS_ROW_SLOTS slots: NGS_ROW_PASSES blocks of one slot per thread; four blocks in flight */
+			for (uint32_t b0 = 0; b0 < nr * NGS_ROW_PASSES; b0 += 4) {
+				uint2 e[4];
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const uint32_t bk = b0 + j, rw = bk / NGS_ROW_PASSES, slot = (bk % NGS_ROW_PASSES) * NGS_COVER_THREADS + (uint32_t)t;
+					e[j] = make_uint2(0, NGS_ENT_CHAIN << 30);
+					if (rw < nr && slot < s_rcnt[rw]) e[j] = __ldg(A.ent + (size_t)(rbase + rw) * NGS_ROW_SLOTS + slot);
 				}
-				if (a0 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)a0)], 1);
-				if (b0 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)b0)], -1);
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const uint32_t kind = e[j].y >> 30, pos = e[j].x & 0x1FFFFFFFu;
+					if (kind == NGS_ENT_CHAIN) continue;
+					if (s_rctg[((b0 + j) / NGS_ROW_PASSES) & 31] + (int)(e[j].x >> 29) != (int)ctg || (int64_t)pos < vis_lo) continue;
+					const uint32_t pl = e[j].y & 0x3FFFFFFFu;
+					const uint32_t a0 = pos - pos0;                     /* wraps to a huge value for pos < pos0: fails the < NGS_CT test */
+					uint32_t b0e;
+					if (kind == NGS_ENT_SIMPLE) b0e = a0 + pl;
+					else {
+						b0e = a0 + (pl & 0xFFFu);
+						const uint32_t a1 = b0e + ((pl >> 12) & 0x3Fu), b1 = a1 + (pl >> 18);
+						if (a1 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)a1)], 1);
+						if (b1 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)b1)], -1);
+					}
+					if (a0 < NGS_CT) atomicAdd(&s_tile[acc_idx((int)a0)], 1);
+					if (b0e < NGS_CT) atomicAdd(&s_tile[acc_idx((int)b0e)], -1);
+				}
 			}
 		}
 	}
 	__syncthreads();
-	if (far) {                                           /* merge (and re-zero) this tile of the far array */
-		int *g = A.diff + tile * (uint64_t)NGS_CT;
-		#pragma unroll 4
-		for (int j = 0; j < NGS_CT / NGS_COVER_THREADS; ++j) {
-			const int i = j * NGS_COVER_THREADS + t;
-			const int v = g[i];
-			if (v) { s_tile[acc_idx(i)] += v; g[i] = 0; }
-		}
-		if (t == 0) A.far_flag[tile] = 0;
-		__syncthreads();
-	}
+	if (far) { merge_far_tile(A.diff + tile * (uint64_t)NGS_CT, s_tile, &A.far_flag[tile]); __syncthreads(); }
 
-	/* ---- scan (as k_scan_runs): 16 consecutive elements per thread */
-	int d[16];
+	/* ---- scan: NGS_CITEMS consecutive elements per thread */
+	int d[NGS_CITEMS];
 	#pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		const int4 v = *reinterpret_cast<const int4 *>(&s_tile[t * 20 + j * 4]);
+	for (int j = 0; j < NGS_CITEMS / 4; ++j) {
+		const int4 v = *reinterpret_cast<const int4 *>(&s_tile[t * (NGS_CITEMS + 4) + j * 4]);
 		d[4 * j] = v.x; d[4 * j + 1] = v.y; d[4 * j + 2] = v.z; d[4 * j + 3] = v.w;
 	}
 	int tsum = 0; unsigned int tcnt = 0, tlast = 0;
 	#pragma unroll
-	for (int i = 0; i < 16; ++i) { tsum += d[i]; if (d[i] != 0) { ++tcnt; tlast = (unsigned)(t * 16 + i + 1); } }
+	for (int i = 0; i < NGS_CITEMS; ++i) { tsum += d[i]; if (d[i] != 0) { ++tcnt; tlast = (unsigned)(t * NGS_CITEMS + i + 1); } }
 	int isum = tsum; unsigned int icnt = tcnt, ilast = tlast;
 	#pragma unroll
 	for (int o = 1; o < 32; o <<= 1) {
@@ -565,18 +609,16 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 		if (lane >= o) { isum += a; icnt += b; ilast = ilast > c ? ilast : c; }
 	}
 	if (lane == 31) { s_wsum[warp] = isum; s_wcnt[warp] = icnt; s_wlast[warp] = ilast; }
-	__syncthreads();                                     /* also: every thread has its 16 elements, s_tile may be reused */
+	__syncthreads();                                     /* also: every thread has its elements, s_tile may be reused */
 	long long wpre_sum = 0; unsigned int wpre_cnt = 0;
 	long long tot_sum = 0; unsigned int tot_cnt = 0, tot_last = 0;
 	#pragma unroll
-	for (int w = 0; w < 8; ++w) {
+	for (int w = 0; w < NGS_CNW; ++w) {
 		if (w < warp) { wpre_sum += s_wsum[w]; wpre_cnt += s_wcnt[w]; }
 		tot_sum += s_wsum[w]; tot_cnt += s_wcnt[w]; tot_last = s_wlast[w] > tot_last ? s_wlast[w] : tot_last;
 	}
 	const int psum = __shfl_up_sync(full, isum, 1);
 	const unsigned int pcnt = __shfl_up_sync(full, icnt, 1);
-	const long long ex_sum = wpre_sum + (lane ? psum : 0);
-	const unsigned int ex_cnt = wpre_cnt + (lane ? pcnt : 0);
 	const uint32_t agg_lastb = tot_last ? pos0 + tot_last : 0;     /* 1 + contig position, 0 = none */
 	if (t == 0) st_relaxed_u64(&A.stB[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
 
@@ -585,11 +627,11 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 	unsigned short *c_pos = reinterpret_cast<unsigned short *>(s_tile);
 	int *c_dep = s_tile + NGS_CT / 2;
 	if (tcnt) {
-		int depth = (int)ex_sum;
-		unsigned int r = ex_cnt;
+		int depth = (int)wpre_sum + (lane ? psum : 0);
+		unsigned int r = wpre_cnt + (lane ? pcnt : 0);
 		#pragma unroll
-		for (int i = 0; i < 16; ++i) {
-			if (d[i] != 0) { c_pos[r] = (unsigned short)(t * 16 + i); c_dep[r] = depth; depth += d[i]; ++r; }
+		for (int i = 0; i < NGS_CITEMS; ++i) {
+			if (d[i] != 0) { c_pos[r] = (unsigned short)(t * NGS_CITEMS + i); c_dep[r] = depth; depth += d[i]; ++r; }
 		}
 	}
 
@@ -610,11 +652,10 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 			__syncthreads();
 			unsigned int first_inc = 0xffffffffu;
 			#pragma unroll
-			for (int w = 0; w < 8; ++w) first_inc = s_lb_inc[w] < first_inc ? s_lb_inc[w] : first_inc;
-			long long vs = 0; unsigned int vl = 0;
-			if ((unsigned)t <= first_inc) { vs = (long long)(int)(uint32_t)b; vl = (unsigned int)((b >> 32) & 0x3FFFFFFFu); }
-			#pragma unroll
-			for (int o = 16; o > 0; o >>= 1) vs += __shfl_xor_sync(full, vs, o);
+			for (int w = 0; w < NGS_CNW; ++w) first_inc = s_lb_inc[w] < first_inc ? s_lb_inc[w] : first_inc;
+			int vs = 0; unsigned int vl = 0;
+			if ((unsigned)t <= first_inc) { vs = (int)(uint32_t)b; vl = (unsigned int)((b >> 32) & 0x3FFFFFFFu); }
+			vs = __reduce_add_sync(full, vs);
 			const unsigned int has = __ballot_sync(full, vl != 0);
 			unsigned int near_l = 0;
 			if (has) near_l = __shfl_sync(full, vl, __ffs(has) - 1);      /* lowest lane = nearest tile */
@@ -622,7 +663,7 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 			__syncthreads();
 			unsigned int rl = 0;
 			#pragma unroll
-			for (int w = 0; w < 8; ++w) { carry += s_lb_sum[w]; if (rl == 0) rl = s_lb_last[w]; }
+			for (int w = 0; w < NGS_CNW; ++w) { carry += s_lb_sum[w]; if (rl == 0) rl = s_lb_last[w]; }
 			if (tile_last == 0) tile_last = rl;
 			if (first_inc != 0xffffffffu) break;
 			base -= NGS_COVER_THREADS;
@@ -645,60 +686,190 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 	}
 	const int icarry = (int)carry;
 	const uint32_t first_start = tile_last ? tile_last - 1 : 0;       /* start of the run that ends at the tile's first boundary */
-	const uint32_t ctg = sg.contig;
-	const uint32_t nl = A.nt.name_off[ctg + 1] - A.nt.name_off[ctg];
+	const bool tile_slow = TEXT && (H0 == 0 || nl > 8u);               /* byte-wise lines for the whole tile */
+	const bool multi = tot_cnt > NGS_CBATCH;
 
-	/* ---- window bins, statistics, text length: record r, r+256, .. per thread */
-	BinAcc bacc; bacc.bins = A.bins + sg.bins0; bacc.k = -1; bacc.acc = 0;
-	unsigned int my_runs = 0, my_first = 0xffffffffu, my_last = 0, my_len = 0; int my_max = 0, my_min = 0;
-	{
-		const uint32_t W = A.window;
-		const uint32_t kt = pos0 / W;
-		const uint64_t wlo = (uint64_t)kt * W, whi = wlo + W - 1;
+	/* ---- more boundaries than one batch holds (coverage above ~45x): the tile's text length is needed before the first
+	 * batch is assembled, so the lengths get a pass of their own */
+	unsigned int total = 0;
+	if (TEXT && multi) {
+		unsigned int my_len = 0;
 		for (unsigned int r = t; r < tot_cnt; r += NGS_COVER_THREADS) {
-			const uint32_t pos = pos0 + c_pos[r];
 			const int depth = c_dep[r] + icarry;
-			const uint32_t start = r ? pos0 + c_pos[r - 1] : first_start;
-			if (depth != 0) {
-				if (start >= wlo && pos <= whi && pos <= sg.ref_len) bacc(kt, (int64_t)(pos - start) * depth);
-				else ngs_bin_run(A.variant, start, pos, (int64_t)depth, W, sg.ref_len, sg.n_win, bacc);
-				++my_runs; my_max = depth > my_max ? depth : my_max; my_min = depth < my_min ? depth : my_min;
-				my_first = r < my_first ? r : my_first; my_last = r;
-				if (TEXT) my_len += nl + ngs_ndigits(start) + ngs_ndigits(pos) + ngs_len_i32(depth) + 3u;
+			if (depth != 0) my_len += nl + ngs_ndigits(r ? pos0 + c_pos[r - 1] : first_start) + ngs_ndigits(pos0 + c_pos[r]) + ngs_len_i32(depth) + 3u;
+		}
+		my_len = __reduce_add_sync(full, my_len);
+		if (lane == 0) s_w[warp] = my_len;
+		__syncthreads();
+		#pragma unroll
+		for (int w = 0; w < NGS_CNW; ++w) total += s_w[w];
+		if (t == 0) st_relaxed_u64(&A.stF[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | total);
+		__syncthreads();
+	}
+
+	/* ---- batches of NGS_CBATCH boundaries, NGS_CIPT consecutive ones per thread: window bins, statistics and the
+	 * bedGraph lines (assembled in registers, staged in shared memory as in k_format_bed; the byte-offset look-back runs
+	 * after the first batch is assembled) */
+	BinAcc bacc; bacc.bins = A.bins + sg.bins0; bacc.k = -1; bacc.acc = 0;
+	unsigned int my_runs = 0, my_first = 0xffffffffu, my_last = 0; int my_max = 0, my_min = 0;
+	const uint32_t W = A.window;
+	const uint32_t kt = pos0 / W;
+	/* fast path of the bins: run inside the window of the tile's first position and inside the contig (positions and
+	 * windows are below 2^30, so the bounds fit 32 bits) */
+	const uint32_t wlo = kt * W, whi = min(wlo + W - 1u, sg.ref_len);
+	long long facc = 0;                                              /* contribution to window kt */
+	const uint32_t Hb = (H0 + 1u) * 10000u;                          /* positions >= Hb have H = H0 + 1 */
+	const uint32_t nH0 = (TEXT && !tile_slow) ? s_hc[0].nH : 0u, nH1 = (TEXT && !tile_slow) ? s_hc[1].nH : 0u;
+	uint32_t *sw = reinterpret_cast<uint32_t *>(s_stage);
+	unsigned long long goff = 0; uint32_t done_bytes = 0;
+	const unsigned int n_batches = (tot_cnt + NGS_CBATCH - 1) / NGS_CBATCH;
+	for (unsigned int bt = 0; bt < n_batches; ++bt) {
+		const unsigned int r0 = bt * NGS_CBATCH + NGS_CIPT * (unsigned)t;
+		uint32_t S0 = 0, E[NGS_CIPT]; int D[NGS_CIPT];
+		#pragma unroll
+		for (int i = 0; i < NGS_CIPT; ++i) {
+			const bool in = r0 + i < tot_cnt;
+			E[i] = in ? pos0 + c_pos[r0 + i] : 0; D[i] = in ? c_dep[r0 + i] + icarry : 0;
+		}
+		if (r0 < tot_cnt) S0 = r0 ? pos0 + c_pos[r0 - 1] : first_start;
+		uint32_t len[NGS_CIPT], tlen = 0;
+		#pragma unroll
+		for (int i = 0; i < NGS_CIPT; ++i) {
+			len[i] = 0;
+			if (D[i] != 0) {
+				const uint32_t start = i ? E[i - 1] : S0, pos = E[i];
+				if (start >= wlo && pos <= whi) facc += (long long)(pos - start) * D[i];
+				else ngs_bin_run(A.variant, start, pos, (int64_t)D[i], W, sg.ref_len, sg.n_win, bacc);
+				++my_runs; my_max = D[i] > my_max ? D[i] : my_max; my_min = D[i] < my_min ? D[i] : my_min;
+				my_first = r0 + i < my_first ? r0 + i : my_first; my_last = r0 + i;
+				if (TEXT) {
+					/* positions inside the tile have the digits of H0 or H0 + 1 in front of four more */
+					if (tile_slow || start < pos0 || (uint32_t)D[i] >= 10000u) len[i] = nl + ngs_ndigits(start) + ngs_ndigits(pos) + ngs_len_i32(D[i]) + 3u;
+					else {
+						const uint32_t nd = 1u + ((uint32_t)D[i] >= 10u) + ((uint32_t)D[i] >= 100u) + ((uint32_t)D[i] >= 1000u);
+						len[i] = nl + (start >= Hb ? nH1 : nH0) + (pos >= Hb ? nH1 : nH0) + 11u + nd;
+					}
+					tlen += len[i];
+				}
 			}
 		}
-	}
-	{
-		const bool has = bacc.k >= 0 && bacc.acc != 0;
-		const unsigned hm = __ballot_sync(full, has);
-		long long wk = -1, wv = 0;
-		if (hm) {
-			const int leader = __ffs(hm) - 1;
-			const long long k0 = __shfl_sync(full, bacc.k, leader);
-			if (__all_sync(full, !has || bacc.k == k0)) {
-				long long v = has ? bacc.acc : 0;
+		if (!TEXT) continue;
+		uint32_t inc = tlen;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(full, inc, o); if (lane >= o) inc += v; }
+		if (lane == 31) s_w[warp] = inc;
+		__syncthreads();
+		uint32_t wpre = 0, btotal = 0;
+		#pragma unroll
+		for (int w = 0; w < NGS_CNW; ++w) { if (w < warp) wpre += s_w[w]; btotal += s_w[w]; }
+		const uint32_t off = wpre + inc - tlen;
+		if (!multi) { total = btotal; if (t == 0) st_relaxed_u64(&A.stF[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | total); }
+		const bool staged = btotal + 32u <= A.stage_bytes;
+		if (t == 0 && staged && !tile_slow) sw[btotal >> 2] = 0;    /* the batch's last, partial word is only ever OR-ed into */
+		ngs_lw<uint32_t *> L;
+		L.begin(sw, off);
+		if (staged && tlen) {
+			if (tile_slow) {
+				char *p = s_stage + off;
 				#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
-				wk = k0; wv = v;
-			} else if (has) atomicAdd(bacc.bins + bacc.k, (unsigned long long)bacc.acc);
+				for (int i = 0; i < NGS_CIPT; ++i) if (len[i]) p += bed_line_bytes(p, A.nt, ctg, i ? E[i - 1] : S0, E[i], D[i]);
+			} else {
+				/* the prefixes of H0 / H0 + 1 live in shared memory; a thread keeps those of its current H in registers */
+				uint32_t hcur = 2u, nH = 0, nh0 = 0, nh1 = 0, nh2 = 0, nh3 = 0, th0 = 0, th1 = 0, hbase = 0;
+				uint32_t hlast = 2u, L4last = 0;                    /* four digits of the previous line's end, valid under H index hlast */
+				#pragma unroll
+				for (int i = 0; i < NGS_CIPT; ++i) {
+					if (!len[i]) { hlast = 2u; continue; }
+					const uint32_t start = i ? E[i - 1] : S0, pos = E[i];
+					const uint32_t he = pos >= Hb, hs = start >= Hb;
+					if (start < pos0 || (uint32_t)D[i] >= 10000u || hs != he) {
+						const uint4 q = lw_generic_line(L.w, L.carry, L.k, n_lo, n_hi, nl, start, pos, (uint32_t)D[i]);
+						L.w += q.x; L.carry = q.y; L.k = q.z; hlast = 2u; continue;
+					}
+					if (he != hcur) {
+						const ngs_hcache &c = s_hc[he];
+						hcur = he; nH = c.nH; nh0 = c.nh0; nh1 = c.nh1; nh2 = c.nh2; nh3 = c.nh3; th0 = c.th0; th1 = c.th1; hbase = c.H * 10000u;
+					}
+					const uint32_t L4s = hlast == he ? L4last : ngs_ascii4(start - hbase);
+					const uint32_t L4e = ngs_ascii4(pos - hbase);
+					uint32_t dq0, dq1, dc;
+					ngs_small_piece((uint32_t)D[i], 0x0Au, dq0, dq1, dc);
+					L.put16(nh0, nh1, nh2, nh3, nl + nH);
+					L.put12(L4s, th0, th1, 5u + nH);
+					L.put12(L4e, 0x09u | (dq0 << 8), (dq0 >> 24) | (dq1 << 8), 5u + dc);
+					L4last = L4e; hlast = he;
+				}
+			}
 		}
-		const unsigned wr = __reduce_add_sync(full, my_runs), wl = __reduce_add_sync(full, my_len);
+		__syncthreads();                                        /* every head word stored */
+		if (staged && !tile_slow && tlen && L.k) atomicOr(L.w, L.carry);
+		if (bt == 0) {
+			if (tile > 0 && !(A.debug & 1)) goff = lookback_bytes(A.stF, tile, total, s_li, s_lb, A.st);
+			else __syncthreads();
+			if (A.debug & 1) goff = tile * 12000ull;
+			if (t == 0 && tile == A.n_tiles - 1) A.st->fmt_bytes = goff + total;
+		} else __syncthreads();
+		if (goff + total <= A.out_cap) {                        /* otherwise the host sees fmt_bytes > capacity */
+			char *g = A.out + goff + done_bytes;
+			if (!staged) {                                      /* lines too long for the staging area: straight to global */
+				char *p = g + off;
+				#pragma unroll
+				for (int i = 0; i < NGS_CIPT; ++i) if (len[i]) p += bed_line_bytes(p, A.nt, ctg, i ? E[i - 1] : S0, E[i], D[i]);
+			} else if (btotal) {
+				/* copy-out: head bytes up to the first 16-byte boundary of the output, aligned 128-bit stores whose source
+				 * starts (16 - mis) bytes into the staging area, tail bytes */
+				const uint32_t mis = (uint32_t)((uintptr_t)g & 15);
+				uint32_t hb = (16u - mis) & 15u;
+				if (hb > btotal) hb = btotal;
+				if ((uint32_t)t < hb) g[t] = s_stage[t];
+				const uint32_t nv = (btotal - hb) >> 4;
+				int4 *dst = reinterpret_cast<int4 *>(g + hb);
+				const int4 *src = reinterpret_cast<const int4 *>(s_stage);
+				if (hb == 0) {
+					for (uint32_t c = t; c < nv; c += NGS_COVER_THREADS) dst[c] = src[c];
+				} else {
+					const uint32_t wsh = hb >> 2, sel = 0x3210u + 0x1111u * (hb & 3u);
+					for (uint32_t c = t; c < nv; c += NGS_COVER_THREADS) {
+						const int4 a = src[c], b = src[c + 1];
+						uint32_t v0, v1, v2, v3, v4;
+						if (wsh == 0) { v0 = a.x; v1 = a.y; v2 = a.z; v3 = a.w; v4 = b.x; }
+						else if (wsh == 1) { v0 = a.y; v1 = a.z; v2 = a.w; v3 = b.x; v4 = b.y; }
+						else if (wsh == 2) { v0 = a.z; v1 = a.w; v2 = b.x; v3 = b.y; v4 = b.z; }
+						else { v0 = a.w; v1 = b.x; v2 = b.y; v3 = b.z; v4 = b.w; }
+						int4 o;
+						o.x = (int)__byte_perm(v0, v1, sel); o.y = (int)__byte_perm(v1, v2, sel);
+						o.z = (int)__byte_perm(v2, v3, sel); o.w = (int)__byte_perm(v3, v4, sel);
+						dst[c] = o;
+					}
+				}
+				const uint32_t tb = hb + (nv << 4);
+				if (tb + (uint32_t)t < btotal) g[tb + t] = s_stage[tb + t];
+			}
+		}
+		done_bytes += btotal;
+		if (bt + 1 < n_batches) __syncthreads();                /* staging area free for the next batch */
+	}
+
+	/* ---- warp- then block-level aggregation of the pending window contribution and the statistics
+	 * (one global atomic per distinct window per tile instead of one per thread) */
+	{
+		if (bacc.k >= 0 && bacc.acc != 0) atomicAdd(bacc.bins + bacc.k, (unsigned long long)bacc.acc);   /* rare: a run leaving the tile's first window */
+		long long wk = (long long)kt, wv = facc;
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) wv += __shfl_xor_sync(full, wv, o);
+		const unsigned wr = __reduce_add_sync(full, my_runs);
 		const int wmax = __reduce_max_sync(full, my_max), wmin = __reduce_min_sync(full, my_min);
 		const unsigned wfirst = __reduce_min_sync(full, my_first), wlast = __reduce_max_sync(full, my_last);
 		if (lane == 0) {
 			s_bk[warp] = wk; s_bv[warp] = wv;
-			s_wr[warp] = wr; s_wmax[warp] = wmax; s_wmin[warp] = wmin; s_rfirst[warp] = wfirst; s_rlast[warp] = wlast; s_wlen[warp] = wl;
+			s_wr[warp] = wr; s_wmax[warp] = wmax; s_wmin[warp] = wmin; s_rfirst[warp] = wfirst; s_rlast[warp] = wlast;
 		}
 	}
 	__syncthreads();
-	unsigned int total = 0;                              /* text bytes of the tile */
-	#pragma unroll
-	for (int w = 0; w < 8; ++w) total += s_wlen[w];
 	if (t == 0) {
-		if (TEXT) st_relaxed_u64(&A.stF[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | total);
 		long long ck = -1, cv = 0;
 		unsigned long long nr = 0; unsigned int fr = 0xffffffffu, lr = 0; int mx = 0, mn = 0;
-		for (int w = 0; w < 8; ++w) {
+		for (int w = 0; w < NGS_CNW; ++w) {
 			if (s_bk[w] >= 0) {
 				if (s_bk[w] == ck) cv += s_bv[w];
 				else { if (ck >= 0 && cv) atomicAdd(bacc.bins + ck, (unsigned long long)cv); ck = s_bk[w]; cv = s_bv[w]; }
@@ -715,139 +886,6 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 			A.tile_last[tile] = make_uint4(lr ? pos0 + c_pos[lr - 1] : first_start, pos0 + c_pos[lr], (uint32_t)(c_dep[lr] + icarry), ctg);
 			atomicMin(&A.st->first_tile, (unsigned long long)tile_g); atomicMax(&A.st->last_tile_p1, (unsigned long long)tile_g + 1);
 		}
-	}
-	if (!TEXT) return;
-
-	/* ---- text: batches of 1024 boundaries (four consecutive ones per thread), lines assembled in registers and
-	 * staged in shared memory as in k_format_bed; the byte-offset look-back runs after the first batch is assembled */
-	const unsigned long long name8 = A.nt.name8[ctg];
-	const uint32_t n_lo = (uint32_t)name8, n_hi = (uint32_t)(name8 >> 32);
-	uint32_t *sw = reinterpret_cast<uint32_t *>(s_stage);
-	unsigned long long goff = 0; uint32_t done_bytes = 0;
-	const unsigned int n_batches = (tot_cnt + 1023u) >> 10;
-	for (unsigned int bt = 0; bt < n_batches; ++bt) {
-		const unsigned int r0 = (bt << 10) + 4u * (unsigned)t;
-		uint32_t S0 = 0, E[4]; int D[4];
-		#pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			const bool in = r0 + i < tot_cnt;
-			E[i] = in ? pos0 + c_pos[r0 + i] : 0; D[i] = in ? c_dep[r0 + i] + icarry : 0;
-		}
-		if (r0 < tot_cnt) S0 = r0 ? pos0 + c_pos[r0 - 1] : first_start;
-		ngs_hcache hc; hc.H = 0xffffffffu; hc.hlo = hc.sh = hc.nH = hc.selA = hc.selB = hc.selC = 0;
-		hc.nh0 = hc.nh1 = hc.nh2 = hc.nh3 = hc.th0 = hc.th1 = 0;
-		uint32_t L4e[4], L4s0 = 0, len[4], tlen = 0;
-		int bad = nl > 8u;
-		auto pos_digits = [&](uint32_t p, uint32_t &L4) -> uint32_t {
-			const uint32_t H = p / 10000u, raw = ngs_digits4_raw(p - H * 10000u);
-			L4 = raw + 0x30303030u;
-			if (H == 0) return raw ? 4u - ngs_low_byte_index(raw) : 1u;
-			if (H >= 100000u) { bad = 1; return 10u; }
-			if (H != hc.H) ngs_hcache_fill(hc, H, n_lo, n_hi, nl);
-			return hc.nH + 4u;
-		};
-		{
-			bool any = false;
-			#pragma unroll
-			for (int i = 0; i < 4; ++i) { any |= D[i] != 0; len[i] = 0; L4e[i] = 0; }
-			if (any && nl <= 8u) {
-				uint32_t n_prev = pos_digits(S0, L4s0);
-				#pragma unroll
-				for (int i = 0; i < 4; ++i) {
-					const uint32_t ns = n_prev;
-					const uint32_t ne = pos_digits(E[i], L4e[i]);
-					n_prev = ne;
-					if (D[i] != 0) {
-						uint32_t nd;
-						if ((uint32_t)D[i] < 10000u) nd = 1u + ((uint32_t)D[i] >= 10u) + ((uint32_t)D[i] >= 100u) + ((uint32_t)D[i] >= 1000u);
-						else if ((uint32_t)D[i] < 1000000000u) nd = ngs_ndigits((uint32_t)D[i]);
-						else { bad = 1; nd = ngs_len_i32(D[i]); }
-						len[i] = nl + ns + ne + nd + 3u;
-					}
-					tlen += len[i];
-				}
-			} else if (any) {
-				#pragma unroll
-				for (int i = 0; i < 4; ++i) {
-					if (D[i] != 0) len[i] = nl + ngs_ndigits(i ? E[i - 1] : S0) + ngs_ndigits(E[i]) + ngs_len_i32(D[i]) + 3u;
-					tlen += len[i];
-				}
-			}
-		}
-		uint32_t inc = tlen;
-		#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(full, inc, o); if (lane >= o) inc += v; }
-		if (lane == 31) s_w[warp] = inc;
-		const bool slow = __syncthreads_or(bad) != 0;
-		uint32_t wpre = 0, btotal = 0;
-		#pragma unroll
-		for (int w = 0; w < 8; ++w) { if (w < warp) wpre += s_w[w]; btotal += s_w[w]; }
-		const uint32_t off = wpre + inc - tlen;
-		const bool staged = btotal + 32u <= A.stage_bytes;
-		if (t == 0 && staged && !slow) sw[btotal >> 2] = 0;         /* the batch's last, partial word is only ever OR-ed into */
-		ngs_lw<uint32_t *> L;
-		L.begin(sw, off);
-		if (staged && btotal) {
-			if (slow) {
-				char *p = s_stage + off;
-				#pragma unroll
-				for (int i = 0; i < 4; ++i) if (len[i]) p += bed_line_bytes(p, A.nt, ctg, i ? E[i - 1] : S0, E[i], D[i]);
-			} else if (tlen) {
-				#pragma unroll
-				for (int i = 0; i < 4; ++i) {
-					if (len[i]) {
-						if (i == 0) L.bed_line_cached(hc, n_lo, n_hi, nl, S0, L4s0, E[0], L4e[0], (uint32_t)D[0]);
-						else L.bed_line_cached(hc, n_lo, n_hi, nl, E[i - 1], L4e[i - 1], E[i], L4e[i], (uint32_t)D[i]);
-					}
-				}
-			}
-		}
-		__syncthreads();                                        /* every head word stored */
-		if (staged && !slow && tlen && L.k) atomicOr(L.w, L.carry);
-		if (bt == 0) {
-			if (tile > 0 && !(A.debug & 1)) goff = lookback_bytes(A.stF, tile, total, s_li, s_lb, A.st);
-			else __syncthreads();
-			if (A.debug & 1) goff = tile * 24000ull;
-			if (t == 0 && tile == A.n_tiles - 1) A.st->fmt_bytes = goff + total;
-		} else __syncthreads();
-		if (goff + total > A.out_cap) return;                   /* block-uniform; the host sees fmt_bytes > capacity */
-		char *g = A.out + goff + done_bytes;
-		if (!staged) {                                          /* lines too long for the staging area: straight to global */
-			char *p = g + off;
-			#pragma unroll
-			for (int i = 0; i < 4; ++i) if (len[i]) p += bed_line_bytes(p, A.nt, ctg, i ? E[i - 1] : S0, E[i], D[i]);
-		} else if (btotal) {
-			/* copy-out: head bytes up to the first 16-byte boundary of the output, aligned 128-bit stores whose source
-			 * starts (16 - mis) bytes into the staging area, tail bytes */
-			const uint32_t mis = (uint32_t)((uintptr_t)g & 15);
-			uint32_t hb = (16u - mis) & 15u;
-			if (hb > btotal) hb = btotal;
-			if ((uint32_t)t < hb) g[t] = s_stage[t];
-			const uint32_t nv = (btotal - hb) >> 4;
-			int4 *dst = reinterpret_cast<int4 *>(g + hb);
-			const int4 *src = reinterpret_cast<const int4 *>(s_stage);
-			if (hb == 0) {
-				for (uint32_t c = t; c < nv; c += NGS_COVER_THREADS) dst[c] = src[c];
-			} else {
-				const uint32_t wsh = hb >> 2, sel = 0x3210u + 0x1111u * (hb & 3u);
-				for (uint32_t c = t; c < nv; c += NGS_COVER_THREADS) {
-					const int4 a = src[c], b = src[c + 1];
-					uint32_t v0, v1, v2, v3, v4;
-					if (wsh == 0) { v0 = a.x; v1 = a.y; v2 = a.z; v3 = a.w; v4 = b.x; }
-					else if (wsh == 1) { v0 = a.y; v1 = a.z; v2 = a.w; v3 = b.x; v4 = b.y; }
-					else if (wsh == 2) { v0 = a.z; v1 = a.w; v2 = b.x; v3 = b.y; v4 = b.z; }
-					else { v0 = a.w; v1 = b.x; v2 = b.y; v3 = b.z; v4 = b.w; }
-					int4 o;
-					o.x = (int)__byte_perm(v0, v1, sel); o.y = (int)__byte_perm(v1, v2, sel);
-					o.z = (int)__byte_perm(v2, v3, sel); o.w = (int)__byte_perm(v3, v4, sel);
-					dst[c] = o;
-				}
-			}
-			const uint32_t tb = hb + (nv << 4);
-			if (tb + (uint32_t)t < btotal) g[tb + t] = s_stage[tb + t];
-		}
-		done_bytes += btotal;
-		__syncthreads();                                        /* staging area free for the next batch */
 	}
 }
 

@@ -473,7 +473,10 @@ typedef struct {
 #define NGS_ENT_CDELTA_MAX 6u
 #define NGS_ROW_SLOTS   256            /* entries per row = threads of an owner CTA */
 #define NGS_NEAR_H      512            /* positions before a tile from which records are visible to its owner */
-#define NGS_CT          4096           /* positions per owner tile (k_cover) = elements per difference-array tile */
+#ifndef NGS_CT
+#define NGS_CT          4096           /* positions per owner tile (k_cover) */
+#endif
+#define NGS_CPT         (4096 / NGS_CT) /* owner tiles per difference-array tile (NGS_TILE / NGS_CT) */
 #define NGS_KEY_NONE    0xFFFFFFFFFFFFFFFFull
 #define NGS_ROW_UNSORTED 0x80000000u   /* row.special: record keys decrease inside the row */
 #define NGS_ROW_OVERFLOW 0x40000000u   /* row.special: more entries than slots -- the whole row goes the RED way */
@@ -532,24 +535,31 @@ NGS_HD int ngs_classify_record(const ngs_walk_cfg &cfg, const ngs_hdr &h, uint32
 	if (si < 0 || h.n_cigar == 0) return 0;
 	/* walk the CIGAR: M intervals with abutting ones merged */
 	const uint32_t pos = (uint32_t)h.pos;
-	uint32_t p = pos, na = 0, a0 = 0, b0 = 0, a1 = 0, b1 = 0, ca = 0, cb = 0;
-	int open = 0, wrapped = 0;
-	for (uint32_t i = 0; i < h.n_cigar; ++i) {
-		const uint32_t w = cig(i), op = w & 0xf, len = w >> 4;
-		if (op == 0) {
-			if (len == 0) continue;
-			if (open && cb == p) cb = p + len;
-			else {
-				if (open) { if (na == 0) { a0 = ca; b0 = cb; } else if (na == 1) { a1 = ca; b1 = cb; } ++na; }
-				ca = p; cb = p + len; open = 1;
-			}
-			if (p + len < p) wrapped = 1;
-			p += len;
-		} else if (op == 2 || op == 3) { if (p + len < p) wrapped = 1; p += len; }
+	uint32_t na = 0, a0 = 0, b0 = 0, a1 = 0, b1 = 0, cb = 0;
+	int wrapped = 0;
+	const uint32_t w0 = cig(0);
+	if (h.n_cigar == 1) {                                /* the common case, "<len>M": no loop, no divergence among the lanes of a walk */
+		if ((w0 & 0xf) != 0 || (w0 >> 4) == 0) return 0;
+		a0 = pos; b0 = cb = pos + (w0 >> 4); na = 1;     /* pos < 2^29, len < 2^28: no 32-bit wrap */
+	} else {
+		uint32_t p = pos, ca = 0; int open = 0;
+		for (uint32_t i = 0; i < h.n_cigar; ++i) {
+			const uint32_t w = i ? cig(i) : w0, op = w & 0xf, len = w >> 4;
+			if (op == 0) {
+				if (len == 0) continue;
+				if (open && cb == p) cb = p + len;
+				else {
+					if (open) { if (na == 0) { a0 = ca; b0 = cb; } else if (na == 1) { a1 = ca; b1 = cb; } ++na; }
+					ca = p; cb = p + len; open = 1;
+				}
+				if (p + len < p) wrapped = 1;
+				p += len;
+			} else if (op == 2 || op == 3) { if (p + len < p) wrapped = 1; p += len; }
+		}
+		if (!open) return 0;                             /* no M at all */
+		if (na == 0) { a0 = ca; b0 = cb; } else if (na == 1) { a1 = ca; b1 = cb; }
+		++na;
 	}
-	if (!open) return 0;                                 /* no M at all */
-	if (na == 0) { a0 = ca; b0 = cb; } else if (na == 1) { a1 = ca; b1 = cb; }
-	++na;
 	cnt.m_ops += na;
 	const ngs_seg &sg = cfg.seg[si];
 	/* entirely inside the tracked range of the segment and below the 28-bit key wrap? */
