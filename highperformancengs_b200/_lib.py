@@ -56,6 +56,9 @@ SYMBOLS = {
     "ngscov_push_bgzf": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     "ngscov_halo_get": (C.c_int, [_H, C.POINTER(Halo)]),
     "ngscov_halo_put": (C.c_int, [_H, C.c_int, C.c_uint32]),
+    "ngscov_halo_device": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
+    "ngscov_stitch_device": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
+    "ngscov_bins_device": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ngscov_bins_count": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
     "ngscov_bins_get": (C.c_int, [_H, C.POINTER(C.c_uint64), C.c_uint64]),
     "ngscov_bins_put": (C.c_int, [_H, C.POINTER(C.c_uint64), C.c_uint64]),

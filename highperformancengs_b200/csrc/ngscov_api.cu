@@ -100,6 +100,9 @@ struct ngscov {
 	size_t bed_begin;                        /* halo: bytes of the dropped first line */
 	std::string bed_tail; size_t bed_tail_old; /* halo: replacement of the last line, and how many bytes it replaces */
 	bool bed_patched;
+	long long *d_halo;                       /* the shard's running halo record (device), see k_halo_gather */
+	unsigned long long *d_patch, *h_patch;   /* device-side stitch: [0] first byte, [1] end of the shard's bedGraph text */
+	bool dev_stitched;
 
 	ngscov_stats_t stats;
 	int sm_count;
@@ -312,7 +315,6 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 			acc += cfg->ref_len[i];
 		}
 	}
-	h->stream_fin = cfg->slice_end == 0 && !(getenv("NGSCOV_STREAM_FINALIZE") && atoi(getenv("NGSCOV_STREAM_FINALIZE")) == 0);
 	h->ingest_mode = 0;
 	if (getenv("NGSCOV_FUSED") && atoi(getenv("NGSCOV_FUSED")) == 1) h->ingest_mode = 1;
 	if (h->ingest_mode == 1 && getenv("NGSCOV_TILES") && atoi(getenv("NGSCOV_TILES")) == 1) h->ingest_mode = 2;
@@ -322,6 +324,9 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	}
 	h->fused = h->ingest_mode != 0;
 	h->cover = !(getenv("NGSCOV_INGEST") || getenv("NGSCOV_FUSED") || (getenv("NGSCOV_PIPELINE") && !strcmp(getenv("NGSCOV_PIPELINE"), "classic")));
+	/* streamed per-contig finalize: the cover pipeline also streams region shards (their halo only patches the first and
+	 * last line afterwards); the classic kernels need the whole shard before the halo is known */
+	h->stream_fin = (cfg->slice_end == 0 || h->cover) && !(getenv("NGSCOV_STREAM_FINALIZE") && atoi(getenv("NGSCOV_STREAM_FINALIZE")) == 0);
 	if (h->cover) {
 		const size_t nt = std::max<uint64_t>(1, h->n_tiles) * NGS_CPT;      /* owner tiles */
 		CK(cudaMalloc((void **)&h->d_far_flag, nt * 4)); CK(cudaMemset(h->d_far_flag, 0, nt * 4));
@@ -330,6 +335,9 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 		CK(cudaMalloc((void **)&h->d_stF, nt * 8));
 		CK(cudaMalloc((void **)&h->d_tile_first, nt * 16)); CK(cudaMalloc((void **)&h->d_tile_last, nt * 16));
 		h->h_tmpl->first_tile = ~0ull;
+		CK(cudaMalloc((void **)&h->d_halo, 9 * 8));
+		CK(cudaMalloc((void **)&h->d_patch, 2 * 8));
+		CK(cudaHostAlloc((void **)&h->h_patch, 2 * 8, cudaHostAllocDefault));
 	}
 	h->shift = 0;
 	const char *env = getenv("NGSCOV_SUBCHUNK");
@@ -346,7 +354,7 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	                h->d_name_off, h->d_wighdr, h->d_wighdr_off, h->d_chunk[0], h->d_chunk[1], h->d_carry, h->d_entry, h->d_exit,
 	                h->d_bmax, h->d_count, h->d_slots, h->d_ctr, h->d_st, h->d_run_start, h->d_run_end, h->d_run_depth, h->d_rec_base, h->d_stA, h->d_stB,
 	                h->d_fmt_status, h->d_text[0], h->d_text[1], h->d_text[2], h->d_text[3],
-	                h->d_ent, h->d_rows, h->d_rkmax, h->d_kbmax, h->d_far_flag, h->d_row_a, h->d_row_b, h->d_stF, h->d_stC, h->d_tile_first, h->d_tile_last };
+	                h->d_ent, h->d_rows, h->d_rkmax, h->d_kbmax, h->d_far_flag, h->d_row_a, h->d_row_b, h->d_stF, h->d_stC, h->d_tile_first, h->d_tile_last, h->d_halo, h->d_patch };
 	for (void *p : dev) if (p) cudaFree(p);
 	for (int i = 0; i < 2; ++i) if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
 	for (int i = 0; i < 4; ++i) if (h->h_text[i]) cudaFreeHost(h->h_text[i]);
@@ -355,6 +363,7 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	if (h->h_recb) cudaFreeHost(h->h_recb);
 	if (h->h_st2) cudaFreeHost(h->h_st2);
 	if (h->h_tmpl) cudaFreeHost(h->h_tmpl);
+	if (h->h_patch) cudaFreeHost(h->h_patch);
 	if (h->s_out) cudaStreamDestroy(h->s_out);
 	if (h->ev_fmt) cudaEventDestroy(h->ev_fmt);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
@@ -401,7 +410,8 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	h->next_fin_seg = 0; h->mops_fin = 0; h->bins_zeroed = false; h->bed_off = 0; h->bed_d2h = 0;
 	h->acc_boundaries = h->acc_runs = 0; h->acc_max = h->acc_min = 0;
 	h->rows_used = 0; h->red_mode = false; h->halo_have = false;
-	h->bed_begin = 0; h->bed_tail.clear(); h->bed_tail_old = 0; h->bed_patched = false;
+	h->bed_begin = 0; h->bed_tail.clear(); h->bed_tail_old = 0; h->bed_patched = false; h->dev_stitched = false;
+	if (h->d_halo) { CK(cudaMemsetAsync(h->d_halo, 0, 9 * 8, h->s_main)); CK(cudaStreamSynchronize(h->s_main)); }
 	return 0;
 }
 
@@ -602,7 +612,10 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 		for (int i = 0; i < NGS_CTR_STRIPES; ++i) h->h_st->m_ops += h->h_ctr[i * 16 + 2];
 	}
 	if (allow_stream && h->stream_fin && !(h->h_st->flags & (NGS_FLAG_EFORMAT | NGS_FLAG_ERANGE)) && h->h_st->max_ref_p1 > 1) {
-		const size_t upto = std::min<size_t>(h->h_st->max_ref_p1 - 1, h->seg.size());
+		/* complete contigs -> complete segments (a region shard only holds the contigs that intersect its slice) */
+		const uint32_t done_ctg = h->h_st->max_ref_p1 - 1;
+		size_t upto = h->next_fin_seg;
+		while (upto < h->seg.size() && h->seg[upto].contig < done_ctg) ++upto;
 		if (upto > h->next_fin_seg) return stream_finalize(h, upto);
 	}
 	return 0;
@@ -955,6 +968,7 @@ static int scan_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_b
 }
 
 static int format_bed_range(ngscov *h, size_t s0, size_t s1);
+static int grow_host_text(ngscov *h, int which, size_t need, size_t keep);
 static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_bound);
 
 /* Finalize segments [next_fin_seg, seg_end) while the rest of the stream is still arriving. */
@@ -1114,6 +1128,45 @@ extern "C" int ngscov_halo_put(ngscov_t *h, int drop_first, uint32_t new_last_en
 	if (h->next_fin_seg > 0) return NGSCOV_ESTATE;           /* streamed finalize: the text is already made */
 	h->drop_idx = drop_first ? h->h_st2->first_run : ~0ull;
 	if (new_last_end) { h->mod_idx = h->h_st2->last_run; h->mod_end = new_last_end; } else h->mod_idx = ~0ull;
+	return 0;
+}
+
+extern "C" int ngscov_halo_device(ngscov_t *h, const void **dev_halo)
+{
+	if (!h || !dev_halo) return NGSCOV_EINVAL;
+	if (!h->runs_done || !h->cover || h->red_mode) return NGSCOV_ESTATE;
+	*dev_halo = h->d_halo;
+	return 0;
+}
+
+extern "C" int ngscov_bins_device(ngscov_t *h, void **dev_bins, uint64_t *n)
+{
+	if (!h || !dev_bins || !n) return NGSCOV_EINVAL;
+	if (!h->runs_done) return NGSCOV_ESTATE;
+	*dev_bins = h->d_bins; *n = h->n_bins;
+	return 0;
+}
+
+extern "C" int ngscov_stitch_device(ngscov_t *h, const void *dev_all_halos, int world, int rank)
+{
+	if (!h || !dev_all_halos || world < 1 || rank < 0 || rank >= world) return NGSCOV_EINVAL;
+	if (!h->runs_done || h->formatted || !h->cover || h->red_mode) return NGSCOV_ESTATE;
+	CK(cudaSetDevice(h->device));
+	const int do_text = h->cfg.mode == NGSCOV_MODE_DEPTH ? 1 : 0;
+	NameTable nt = { h->d_names, h->d_name_off, h->d_name8 };
+	k_stitch<<<1, 32, 0, h->s_main>>>((const long long *)dev_all_halos, world, rank, do_text ? h->d_text[NGSCOV_OUT_BEDGRAPH] : nullptr, h->bed_off, nt,
+	                                  h->d_bins, h->d_win_base, h->d_ref_len, h->cfg.window, h->cfg.mode == NGSCOV_MODE_WIG ? 1 : 0, do_text, h->d_patch, h->h_patch);
+	h->stats.launches += 1;
+	CK(cudaGetLastError());
+	h->dev_stitched = true;
+	if (do_text && h->bed_d2h) {
+		/* streamed finalize already sent the text to the host: send the (possibly rewritten) last line again */
+		const size_t win = (size_t)h->max_name_tab + 64, lo = h->bed_off > win ? h->bed_off - win : 0, hi = h->bed_off + 32;
+		int r = grow_host_text(h, NGSCOV_OUT_BEDGRAPH, hi, h->bed_d2h);
+		if (r) return r;
+		CK(cudaStreamSynchronize(h->s_out));
+		CK(cudaMemcpyAsync(h->h_text[NGSCOV_OUT_BEDGRAPH] + lo, h->d_text[NGSCOV_OUT_BEDGRAPH] + lo, hi - lo, cudaMemcpyDeviceToHost, h->s_main));
+	}
 	return 0;
 }
 
@@ -1307,7 +1360,7 @@ static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_
 			CK(cudaFuncSetAttribute(k_cover<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
 			k_cover<true><<<(unsigned)(t1 - t0), NGS_COVER_THREADS, stage, h->s_main>>>(A);
 		} else k_cover<false><<<(unsigned)(t1 - t0), NGS_COVER_THREADS, 0, h->s_main>>>(A);
-		k_halo_gather<<<1, 32, 0, h->s_main>>>(h->d_st, h->d_tile_first, h->d_tile_last);
+		k_halo_gather<<<1, 32, 0, h->s_main>>>(h->d_st, h->d_tile_first, h->d_tile_last, h->d_halo);
 		h->stats.launches += 3;
 		CK(cudaGetLastError());
 	}
@@ -1432,6 +1485,13 @@ extern "C" int ngscov_output_device(ngscov_t *h, int which, const void **dev_buf
 {
 	if (!h || which < 0 || which > 2 || !dev_buf || !len) return NGSCOV_EINVAL;
 	if (!h->text_ready[which]) return NGSCOV_ESTATE;
+	if (which == NGSCOV_OUT_BEDGRAPH && h->dev_stitched) {
+		CK(cudaSetDevice(h->device));
+		CK(cudaStreamSynchronize(h->s_main));
+		const size_t b = (size_t)h->h_patch[0], e = (size_t)h->h_patch[1];
+		*dev_buf = h->d_text[which] + (b < e ? b : 0); *len = b < e ? e - b : 0;
+		return 0;
+	}
 	if (which == NGSCOV_OUT_BEDGRAPH && h->cover && !h->red_mode && (h->bed_begin || h->bed_tail_old)) {
 		/* halo decisions: skip the dropped first line, overwrite the last line in place (the buffer has slack) */
 		CK(cudaSetDevice(h->device));
@@ -1462,7 +1522,7 @@ extern "C" int ngscov_output(ngscov_t *h, int which, const char **buf, size_t *l
 		h->h_text_valid[which] = true;
 	}
 	if (!h->h_text_valid[which]) {
-		const size_t n = h->text_len[which];
+		const size_t n = h->text_len[which] + ((which == NGSCOV_OUT_BEDGRAPH && h->dev_stitched && h->text_len[which]) ? 32 : 0);   /* a rewritten last line may be a few bytes longer */
 		if (n > h->h_text_cap[which] || !h->h_text[which]) {
 			if (h->h_text[which]) cudaFreeHost(h->h_text[which]);
 			h->h_text[which] = nullptr; h->h_text_cap[which] = 0;
@@ -1476,6 +1536,12 @@ extern "C" int ngscov_output(ngscov_t *h, int which, const char **buf, size_t *l
 		h->h_text_valid[which] = true;
 	}
 	*buf = h->h_text[which]; *len = h->text_len[which];
+	if (which == NGSCOV_OUT_BEDGRAPH && h->dev_stitched) {
+		CK(cudaStreamSynchronize(h->s_main));
+		const size_t b = (size_t)h->h_patch[0], e = (size_t)h->h_patch[1];
+		*buf = h->h_text[which] + (b < e ? b : 0); *len = b < e ? e - b : 0;
+		return 0;
+	}
 	if (which == NGSCOV_OUT_BEDGRAPH && h->cover && !h->red_mode && (h->bed_begin || h->bed_tail_old)) {
 		if (h->bed_begin >= h->bed_off) { *len = 0; return 0; }
 		const size_t body = h->bed_off - h->bed_tail_old;

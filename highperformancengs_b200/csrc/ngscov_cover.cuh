@@ -889,12 +889,69 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 	}
 }
 
-/* after a cover launch: the halo candidates of the first / last tile that produced a run -> the state block */
-__global__ void k_halo_gather(ngs_dev_state *st, const uint4 *tile_first, const uint4 *tile_last)
+/* after a cover launch: the halo candidates of the first / last tile that produced a run -> the state block, and the
+ * shard's running halo record (9 x int64: n_runs, first{contig,start,end,depth}, last{..}) that the device-side stitch
+ * of region shards exchanges */
+__global__ void k_halo_gather(ngs_dev_state *st, const uint4 *tile_first, const uint4 *tile_last, long long *halo)
 {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
 	if (st->last_tile_p1 == 0) return;
 	const uint4 a = tile_first[st->first_tile], b = tile_last[st->last_tile_p1 - 1];
 	st->halo_first[0] = a.x; st->halo_first[1] = a.y; st->halo_first[2] = a.z; st->halo_first[3] = a.w;
 	st->halo_last[0] = b.x; st->halo_last[1] = b.y; st->halo_last[2] = b.z; st->halo_last[3] = b.w;
+	if (halo[0] == 0) { halo[1] = a.w; halo[2] = a.x; halo[3] = a.y; halo[4] = (int)a.z; }
+	halo[5] = b.w; halo[6] = b.x; halo[7] = b.y; halo[8] = (int)b.z;
+	halo[0] += (long long)st->n_runs;
+}
+
+/* ---- device-side stitch of region shards (shard.py stitch() / host/ngscov_shard.h stitch() restated) --
+ * Every rank runs the same sequential rule over all ranks' halo records (gathered over NVLink by the caller) and applies
+ * what concerns it: its first line is skipped when that run continues the previous shard's last run, its last line is
+ * rewritten when a later shard extends it, and the window bins of a merged run are corrected by the rank whose first run
+ * merged (the bam2wig window arithmetic is not additive over the pieces of a run); the bins are summed over ranks after. */
+struct DevBinAdd { unsigned long long *bins; long long sign; __device__ void operator()(uint32_t k, int64_t v) const { bins[k] += (unsigned long long)(sign * v); } };
+
+__global__ void k_stitch(const long long *halos, int world, int rank, char *text, unsigned long long bed_off, NameTable nt,
+                         unsigned long long *bins, const unsigned long long *win_base, const uint32_t *ref_len, uint32_t window, int variant,
+                         int do_text, unsigned long long *patch, unsigned long long *patch_host)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	int have = 0, owner = 0, drop_me = 0; uint32_t new_end_me = 0;
+	long long cc = 0, cs = 0, ce = 0, cd = 0;
+	for (int r = 0; r < world; ++r) {
+		const long long *h = halos + 9 * r;
+		if (h[0] == 0) { have = 0; continue; }
+		int merged = 0;
+		if (have && cc == h[1] && ce == h[2] && cd == h[4]) {
+			merged = 1;
+			if (r == rank) {
+				const uint32_t L = ref_len[cc], nw = L / window + 1;
+				DevBinAdd sub = { bins + win_base[cc], -1 }, add = { bins + win_base[cc], +1 };
+				ngs_bin_run(variant, (uint32_t)cs, (uint32_t)ce, cd, window, L, nw, sub);
+				ngs_bin_run(variant, (uint32_t)h[2], (uint32_t)h[3], h[4], window, L, nw, sub);
+				ngs_bin_run(variant, (uint32_t)cs, (uint32_t)h[3], cd, window, L, nw, add);
+				drop_me = 1;
+			}
+			ce = h[3];
+			if (owner == rank) new_end_me = (uint32_t)ce;
+		}
+		if (merged && h[0] == 1) continue;               /* the whole shard was one run: it stays open into the next shard */
+		cc = h[5]; cs = h[6]; ce = h[7]; cd = h[8]; owner = r; have = 1;
+	}
+	unsigned long long begin = 0, end = bed_off;
+	const long long *me = halos + 9 * rank;
+	if (do_text && me[0]) {
+		char tmp[16];
+		auto line_len = [&](uint32_t c, uint32_t s, uint32_t e, int d) -> uint32_t {
+			return (nt.name_off[c + 1] - nt.name_off[c]) + ngs_put_u32(tmp, s) + ngs_put_u32(tmp, e) + ngs_put_i32(tmp, d) + 3u;
+		};
+		if (drop_me) begin = me[0] == 1 ? bed_off : line_len((uint32_t)me[1], (uint32_t)me[2], (uint32_t)me[3], (int)me[4]);
+		if (new_end_me && !(drop_me && me[0] == 1)) {
+			const uint32_t old = line_len((uint32_t)me[5], (uint32_t)me[6], (uint32_t)me[7], (int)me[8]);
+			end = bed_off - old + bed_line_bytes(text + bed_off - old, nt, (uint32_t)me[5], (uint32_t)me[6], new_end_me, (int)me[8]);
+		}
+	}
+	patch[0] = begin; patch[1] = end;
+	patch_host[0] = begin; patch_host[1] = end;
+	__threadfence_system();
 }

@@ -13,6 +13,13 @@ OUT_BEDGRAPH, OUT_DEPTH, OUT_WIG, OUT_CHROMSIZE = 0, 1, 2, 3
 PUSH_LAST, PUSH_TRUNCATED_OK = 1, 2
 
 
+class DeviceArray:
+    """a device pointer the library owns, wrapped for torch.as_tensor / cupy (zero copy, __cuda_array_interface__)"""
+
+    def __init__(self, ptr, n, typestr="<i8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
 class CoverageEngine:
     def __init__(self, ref_names, ref_lens, mode=MODE_DEPTH, window=20000, emit_wig=False, device=0,
                  slice_beg=0, slice_end=0, staging_bytes=0):
@@ -184,6 +191,21 @@ class CoverageEngine:
 
     def halo_put(self, drop_first, new_last_end):
         self._check(self.lib.ngscov_halo_put(self.h, 1 if drop_first else 0, int(new_last_end)), "ngscov_halo_put")
+
+    # -- device-side stitch of region shards (no host round trip)
+    def halo_device(self):
+        """device address of the shard's halo record (9 x int64), valid after finish_runs"""
+        p = C.c_void_p()
+        self._check(self.lib.ngscov_halo_device(self.h, C.byref(p)), "ngscov_halo_device")
+        return p.value
+
+    def stitch_device(self, dev_all_halos, world, rank):
+        self._check(self.lib.ngscov_stitch_device(self.h, C.c_void_p(dev_all_halos), world, rank), "ngscov_stitch_device")
+
+    def bins_device(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.ngscov_bins_device(self.h, C.byref(p), C.byref(n)), "ngscov_bins_device")
+        return p.value, n.value
 
     def bins(self):
         n = C.c_uint64()

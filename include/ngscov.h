@@ -167,6 +167,20 @@ int ngscov_slice_done(ngscov_t *h, int *done);
 int ngscov_halo_get(ngscov_t *h, ngscov_halo *halo);
 int ngscov_halo_put(ngscov_t *h, int drop_first, uint32_t new_last_end);
 
+/* Device-side stitch (no host round trip; the cover pipeline, i.e. the default kernels).  After ngscov_finish_runs:
+ *   ngscov_halo_device   device address of this shard's halo record, 9 x int64 {n_runs, first.contig, first.start,
+ *                        first.end, first.depth, last.contig, last.start, last.end, last.depth}; the caller gathers the
+ *                        records of all shards in rank order (NCCL all_gather over NVLink, cudaMemcpyPeerAsync, ...)
+ *   ngscov_stitch_device queues ONE kernel on ngscov_stream that applies the stitch rule to this shard from the gathered
+ *                        records: skips its first line / rewrites its last line in the device text and corrects its
+ *                        window bins for the merged runs it owns.  Replaces ngscov_halo_get + host logic +
+ *                        ngscov_halo_put + ngscov_bins_apply_run.
+ *   ngscov_bins_device   device address of the window bins (uint64 x n), to be summed over shards in place
+ *                        (NCCL all_reduce) before rank 0 formats the .depth / wig text. */
+int ngscov_halo_device(ngscov_t *h, const void **dev_halo);
+int ngscov_stitch_device(ngscov_t *h, const void *dev_all_halos, int world, int rank);
+int ngscov_bins_device(ngscov_t *h, void **dev_bins, uint64_t *n);
+
 /* Window bins (sum over bases of depth, per window, all contigs concatenated: contig c owns
  * ref_len[c]/window + 1 consecutive entries).  get copies device -> host, put host -> device. */
 int ngscov_bins_count(ngscov_t *h, uint64_t *n);

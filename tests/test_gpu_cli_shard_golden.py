@@ -153,3 +153,64 @@ def test_sharded_low_coverage_long_runs(oracle):
         got = _sharded(names, lens, recs, mode, 20000, 8)
         for k in (("bedgraph", "depth", "wig") if mode == 0 else ("wig",)):
             assert got[k] == exp[k], (mode, k)
+
+
+def _sharded_device(names, lens, recs, mode, window, n, staging_bytes=0):
+    """the same n engines, stitched on the DEVICE: halo records gathered with device-to-device copies (what the NCCL
+    all_gather does between GPUs), ngscov_stitch_device on every shard, window bins summed in device memory"""
+    import torch
+    from highperformancengs_b200 import CoverageEngine, shard
+    from highperformancengs_b200.engine import DeviceArray
+    slices = [(b, e) for b, e in shard.plan_slices(lens, n) if e > b]
+    engs = [CoverageEngine(names, lens, mode=mode, window=window, emit_wig=True, slice_beg=b, slice_end=e, staging_bytes=staging_bytes) for b, e in slices]
+    try:
+        for e in engs:
+            e.push_host(recs, last=True)
+            e.finish_runs()
+            e.sync()
+        world = len(engs)
+        allh = torch.cat([torch.as_tensor(DeviceArray(e.halo_device(), 9), device="cuda").clone() for e in engs])
+        torch.cuda.synchronize()
+        for r, e in enumerate(engs):
+            e.stitch_device(allh.data_ptr(), world, r)
+            e.sync()
+        bins = [torch.as_tensor(DeviceArray(*e.bins_device()), device="cuda") for e in engs]
+        total = torch.stack(bins).sum(0)
+        bins[0].copy_(total)
+        torch.cuda.synchronize()
+        bed = b""
+        for i, e in enumerate(engs):
+            e.format(e.default_mask() if i == 0 else ((1 << 0) if mode == 0 else 0))
+            if mode == 0:
+                bed += e.output(0)
+        return {"bedgraph": bed, "depth": engs[0].output(1) if mode == 0 else b"", "wig": engs[0].output(2), "chromsize": engs[0].output(3)}
+    finally:
+        for e in engs:
+            e.close()
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("staging", [0, 16384])
+def test_sharded_device_stitch_equals_whole(oracle, n, mode, staging):
+    """device-side stitch (ngscov_halo_device / ngscov_stitch_device / ngscov_bins_device), also with small pushes so
+    that the shards' contigs are finalized while the stream is still arriving (streamed finalize of region shards)"""
+    names, lens, reads = bamutil.random_case(5, n_reads=6000, contigs=((b"c1", 150000), (b"c2", 40000), (b"c3", 300000)))
+    recs = bamutil.records(reads, seq=False)
+    for window in (1000, 777):
+        exp = oracle.run(recs, names, lens, mode, window)
+        got = _sharded_device(names, lens, recs, mode, window, n, staging_bytes=staging)
+        for k in (("bedgraph", "depth", "wig", "chromsize") if mode == 0 else ("wig", "chromsize")):
+            assert got[k] == exp[k], f"n={n} mode={mode} w={window} staging={staging}: {k} differs"
+
+
+def test_sharded_device_stitch_long_runs(oracle):
+    """constant-depth runs that span whole shards (chained merges), stitched on the device"""
+    names, lens = [b"c1"], [200000]
+    reads = [(0, 100, 0, "150000M"), (0, 120000, 0, "70000M"), (0, 199000, 0, "1000M")]
+    recs = bamutil.records(reads, seq=False)
+    for mode in (0, 1):
+        exp = oracle.run(recs, names, lens, mode, 20000)
+        got = _sharded_device(names, lens, recs, mode, 20000, 8)
+        for k in (("bedgraph", "depth", "wig") if mode == 0 else ("wig",)):
+            assert got[k] == exp[k], (mode, k)

@@ -331,3 +331,67 @@ def test_large_scale_properties(tmp_path):
         eng.push_bgzf(raw, skip=hdr_len, last=True)
         eng.finish()
         assert zlib.adler32(np.array(eng.output_view(0), copy=False)) == ref_sum
+
+
+def test_unsorted_input_takes_the_red_path(oracle):
+    """records that are not coordinate sorted: the owner tiles cannot find them by key; the library notices (sort keys are
+    checked while the records are framed) and falls back to REDs + the classic scan -- same output as the oracle, which
+    groups by contig"""
+    import random
+    names, lens, reads = bamutil.random_case(21, n_reads=3000)
+    rnd = random.Random(3)
+    rnd.shuffle(reads)
+    recs = bamutil.records(reads, seq=False)
+    for mode, _ in MODES:
+        exp = oracle.run(recs, names, lens, mode, 400)
+        got = run_engine(names, lens, recs, mode, 400)
+        check(got, exp, mode, "unsorted")
+        got = run_engine(names, lens, recs, mode, 400, staging_bytes=16384)     # detected in a later chunk: catch-up pass
+        check(got, exp, mode, "unsorted, small pushes")
+
+
+def test_long_and_spliced_reads_far_deltas(oracle):
+    """reads longer than the owner's view (NGS_NEAR_H = 512), pairs with large gaps, many-op CIGARs: far deltas go through
+    REDs + the far flags, CHAIN entries are decoded from the stream"""
+    import random
+    rnd = random.Random(11)
+    names, lens = [b"chrL", b"chrM"], [400000, 90000]
+    reads = []
+    for c, L in enumerate(lens):
+        p = 0
+        while p < L - 30000:
+            p += rnd.randrange(1, 400)
+            k = rnd.randrange(6)
+            if k == 0:
+                cig = "%dM" % rnd.randrange(600, 9000)                       # far end
+            elif k == 1:
+                cig = "%dM%dN%dM" % (rnd.randrange(20, 200), rnd.randrange(1, 60), rnd.randrange(20, 200))     # PAIR entry
+            elif k == 2:
+                cig = "%dM%dN%dM" % (rnd.randrange(20, 200), rnd.randrange(500, 20000), rnd.randrange(20, 200))   # CHAIN
+            elif k == 3:
+                cig = "5S%dM2I%dM3D%dM%dN%dM4S" % tuple(rnd.randrange(10, 120) for _ in range(5))
+            elif k == 4:
+                cig = "%dM" % rnd.randrange(30, 300)
+            else:
+                cig = "%dM%dD%dM" % (rnd.randrange(10, 100), rnd.randrange(1, 30), rnd.randrange(10, 4090))
+            reads.append((c, p, rnd.choice([0, 16, 0x400, 0x100]), cig))
+    recs = bamutil.records(reads, seq=False)
+    for mode, _ in MODES:
+        for window in (300, 20000):
+            exp = oracle.run(recs, names, lens, mode, window)
+            got = run_engine(names, lens, recs, mode, window)
+            check(got, exp, mode, f"far deltas mode={mode} w={window}")
+            got = run_engine(names, lens, recs, mode, window, staging_bytes=32768)
+            check(got, exp, mode, f"far deltas, streamed, mode={mode} w={window}")
+
+
+def test_classic_pipeline_still_matches(oracle, monkeypatch):
+    """NGSCOV_PIPELINE=classic: K1 framing + K2 REDs + scan + format kernels (the round-1 organisation), kept as the
+    fallback for unsorted input and as a second implementation to compare with"""
+    monkeypatch.setenv("NGSCOV_PIPELINE", "classic")
+    names, lens, reads = bamutil.random_case(4)
+    recs = bamutil.records(reads)
+    for mode, _ in MODES:
+        exp = oracle.run(recs, names, lens, mode, 500)
+        got = run_engine(names, lens, recs, mode, 500)
+        check(got, exp, mode, "classic")
