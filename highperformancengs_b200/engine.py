@@ -106,8 +106,9 @@ class CoverageEngine:
         flags = (PUSH_LAST if last else 0) | (PUSH_TRUNCATED_OK if truncated_ok else 0)
         self._check(self.lib.ngscov_push_bgzf(self.h, C.c_void_p(a.ctypes.data), a.size, skip, flags), "ngscov_push_bgzf")
 
-    def push_bgzf_ptr(self, host_ptr, nbytes, skip=0, last=True):
-        self._check(self.lib.ngscov_push_bgzf(self.h, C.c_void_p(host_ptr), nbytes, skip, PUSH_LAST if last else 0), "ngscov_push_bgzf")
+    def push_bgzf_ptr(self, host_ptr, nbytes, skip=0, last=True, truncated_ok=False):
+        flags = (PUSH_LAST if last else 0) | (PUSH_TRUNCATED_OK if truncated_ok else 0)
+        self._check(self.lib.ngscov_push_bgzf(self.h, C.c_void_p(host_ptr), nbytes, skip, flags), "ngscov_push_bgzf")
 
     def push_device(self, dev_ptr, nbytes, last=True):
         self._check(self.lib.ngscov_push_device(self.h, C.c_void_p(dev_ptr), nbytes, PUSH_LAST if last else 0), "ngscov_push_device")
