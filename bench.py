@@ -409,6 +409,7 @@ def main():
     import torch.distributed as dist
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     if world > 1:
         # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment; stdout is reserved for the
@@ -542,7 +543,10 @@ def main():
                 "d2h_bytes_per_step": int(tb2[1].item()), "ms_per_step": te[0].item(), "steps": k}
 
     e2e = None
+    probe = None
     if not args.no_e2e:
+        probe = pcie_probe(torch, dist, world)
+        probe["numa_binding"] = numa
         e2e = time_e2e(job.step_e2e_host, job.nbytes)
         e2e["input"] = "inflated BAM record stream in pinned host memory (ngscov_push_host); host BGZF inflate is I/O, not timed"
         if not args.no_bgzf:
@@ -600,6 +604,7 @@ def main():
                 "parity": parity,
                 "clocks": clk.summary(), "gpu_launches": int(n_launch)}
         if e2e:
+            e2e["pcie_probe"] = probe
             line["e2e"] = e2e
         if not args.no_cpu and world == 1:
             try:
@@ -615,6 +620,60 @@ def main():
     job.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa(local):
+    """Pin this process (and with it the pinned host buffers it allocates from now on) to the CPUs of the NUMA node the
+    GPU hangs off: with one process per GPU and unbound processes, half of the device<->host copies cross the socket
+    interconnect.  Also undoes torchrun's OMP_NUM_THREADS=1 for the input generator."""
+    info = {"node": None}
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node >= 0:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info = {"node": node, "cpus": len(cpus)}
+    except Exception as ex:
+        info = {"node": None, "error": str(ex)[:80]}
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // (world if info.get("node") is None else 1)))
+    return info
+
+
+def pcie_probe(torch, dist, world, nbytes=1 << 30):
+    """plain pinned H2D / D2H copy bandwidth of every rank, all ranks at once: the ceiling of the end-to-end legs"""
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    res = []
+    for src, dst in ((h, d), (d, h)):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        res.append(3 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    t = torch.tensor(res, dtype=torch.float64, device="cuda")
+    lo, hi = t.clone(), t.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return {"h2d_GBps_per_rank_min": round(lo[0].item(), 1), "h2d_GBps_per_rank_max": round(hi[0].item(), 1),
+            "d2h_GBps_per_rank_min": round(lo[1].item(), 1), "d2h_GBps_per_rank_max": round(hi[1].item(), 1),
+            "what": f"{nbytes >> 20} MiB pinned copies, {world} rank(s) concurrently"}
 
 
 def cli_wall(cfg, seq, window, scale):
