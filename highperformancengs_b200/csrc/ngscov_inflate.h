@@ -214,6 +214,9 @@ NGS_HD int ngs_inf_block_tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables 
 /* Decoding loop with the output left to a policy:
  *   void literal(uint32_t pos, uint32_t byte); void match(uint32_t pos, uint32_t len, uint32_t dist);
  *   void stored(uint32_t pos, const uint8_t *src, uint32_t len); void finish();   (finish: nothing may stay pending)
+ *   int tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables &T);   builds the block's tables, normally by calling
+ *       ngs_inf_block_tables; the device policy lets ONE lane build them in the warp's shared-memory slice and hands the
+ *       advanced bit reader to the other lanes
  * `in` must be readable up to in_len + 7.  Returns the number of bytes produced, or -1 (malformed stream / output
  * larger than out_len). */
 template <class Out>
@@ -237,7 +240,7 @@ NGS_HD long ngs_inflate_stream(const uint8_t *in, uint32_t in_len, uint32_t out_
 			b.in_pos = at + len; b.buf = 0; b.cnt = 0;
 		} else if (btype == 3u) return -1;
 		else {
-			if (ngs_inf_block_tables(b, btype, T)) return -1;
+			if (out.tables(b, btype, T)) return -1;
 			for (;;) {
 				/* literal/length: at most 15 code bits + 5 extra bits */
 				if (b.cnt < 32u) ngs_inf_refill32(b);

@@ -1668,6 +1668,19 @@ struct WarpInflateOut {
 	 * and only then does the warp touch the loaded value (the load latency was 29 % of the stall samples) */
 	uint8_t *pend_dst; uint32_t pend_val; bool pend;
 	__device__ __forceinline__ void finish() { if (pend) { if (pend_dst) *pend_dst = (uint8_t)pend_val; pend = false; } }
+	/* the block's Huffman tables are built by lane 0 alone (32 lanes writing the same values to the same shared words is
+	 * harmless but is what compute-sanitizer's racecheck reports); the other lanes take over the bit reader it advanced */
+	__device__ __forceinline__ int tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables &T)
+	{
+		int r = 0;
+		__syncwarp();
+		if (lane == 0) r = ngs_inf_block_tables(b, btype, T);
+		__syncwarp();
+		r = __shfl_sync(0xffffffffu, r, 0);
+		b.in_pos = __shfl_sync(0xffffffffu, b.in_pos, 0); b.cnt = __shfl_sync(0xffffffffu, b.cnt, 0);
+		b.buf = __shfl_sync(0xffffffffu, b.buf, 0);
+		return r;
+	}
 	__device__ __forceinline__ void literal(uint32_t pos, uint32_t b) { if (lane == 0) o[pos] = (uint8_t)b; }
 	__device__ __forceinline__ void match(uint32_t pos, uint32_t len, uint32_t dist)
 	{

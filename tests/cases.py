@@ -20,6 +20,14 @@ CASES = [
     ("c1_full", "gen", (1, 1.0), [("depth", 20000)]),
 ]
 
+# full-size configurations 4 and 5 (BASELINE.json): 20 M spliced reads / 50 M reads piled on 200 kb.  The reference binary
+# ran them here once (tests/golden/make_golden.py); the CPU oracle needs minutes on them, so only the GPU tests (md5 of
+# the engine's output against the reference's) and the generator consume these.
+FULL_CASES = [
+    ("c4_full", "gen", (4, 1.0), [("wig", 20000), ("wig", 100)]),
+    ("c5_full", "gen", (5, 1.0), [("depth", 20000)]),
+]
+
 
 def case_input(kind, params):
     """-> (names, lens, records uint8 array, generator or None)"""

@@ -37,8 +37,12 @@ def run_reference(tool, window, bam, workdir):
 
 
 def main():
-    gold = {}
-    for name, kind, params, runs in cases.CASES:
+    only = set(sys.argv[1:])          # optional case names: regenerate just those and merge into the existing file
+    path = os.path.join(ROOT, "tests", "golden", "reference_outputs.json")
+    gold = json.load(open(path)) if only and os.path.exists(path) else {}
+    for name, kind, params, runs in cases.CASES + cases.FULL_CASES:
+        if only and name not in only:
+            continue
         names, lens, recs, g = cases.case_input(kind, params)
         with tempfile.TemporaryDirectory(prefix="ngscov_gold_") as d:
             bam = os.path.join(d, name + ".bam")
@@ -55,7 +59,7 @@ def main():
                         entry[k]["text"] = v.decode()
                 gold[f"{name}|{tool}|{window}"] = entry
                 print(name, tool, window, {k: e["size"] for k, e in entry.items()})
-    with open(os.path.join(ROOT, "tests", "golden", "reference_outputs.json"), "w") as f:
+    with open(path, "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
 
 

@@ -19,6 +19,7 @@ struct SeqOut {
 	void match(uint32_t pos, uint32_t len, uint32_t dist) { for (uint32_t i = 0; i < len; ++i) o[pos + i] = o[pos - dist + i]; }
 	void stored(uint32_t pos, const uint8_t *src, uint32_t len) { memcpy(o + pos, src, len); }
 	void finish() {}
+	int tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables &T) { return ngs_inf_block_tables(b, btype, T); }
 };
 /* the lane-parallel copy rule of the kernel: byte i of a match comes from pos - dist + (i % dist), all old bytes */
 struct ParOut {
@@ -32,6 +33,7 @@ struct ParOut {
 	}
 	void stored(uint32_t pos, const uint8_t *src, uint32_t len) { memcpy(o + pos, src, len); }
 	void finish() {}
+	int tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables &T) { return ngs_inf_block_tables(b, btype, T); }
 };
 
 static std::vector<uint8_t> deflate_raw(const std::vector<uint8_t> &in, int level, int strategy)

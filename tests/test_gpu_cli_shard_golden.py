@@ -214,3 +214,43 @@ def test_sharded_device_stitch_long_runs(oracle):
         got = _sharded_device(names, lens, recs, mode, 20000, 8)
         for k in (("bedgraph", "depth", "wig") if mode == 0 else ("wig",)):
             assert got[k] == exp[k], (mode, k)
+
+
+@pytest.mark.parametrize("tag,key", __import__("tests.test_oracle_golden", fromlist=["ST_PARAMS"]).ST_PARAMS)
+def test_engine_on_samtools_examples(tag, key):
+    """the files the reference itself ships (samtools examples/toy.sam, ex1.sam.gz) through the engine: md5 of every output
+    equals that of the unmodified reference binaries"""
+    from tests.test_oracle_golden import samtools_example, check_samtools_example
+    from highperformancengs_b200 import CoverageEngine
+    names, lens, recs = samtools_example(tag)
+    tool, w = key.split("|")
+    mode = 0 if tool == "depth" else 1
+    with CoverageEngine(names, lens, mode=mode, window=int(w), emit_wig=True) as eng:
+        eng.push_host(recs, last=True)
+        eng.finish()
+        got = {"wig": eng.output(2), "chromsize": eng.output(3)}
+        if mode == 0:
+            got.update(bedgraph=eng.output(0), depth=eng.output(1))
+    check_samtools_example(got, tag, key)
+
+
+@pytest.mark.parametrize("name,kind,params,runs", cases.FULL_CASES, ids=[c[0] for c in cases.FULL_CASES])
+def test_full_size_configs_4_and_5(name, kind, params, runs):
+    """BASELINE configs 4 (20 M spliced reads, bam2wig) and 5 (50 M reads piled on 200 kb, depth > 10^4) at FULL size:
+    md5 of the engine's files against those the reference binary wrote for the same input (tests/golden)"""
+    from highperformancengs_b200 import CoverageEngine
+    names, lens, recs, g = cases.case_input(kind, params)
+    for tool, w in runs:
+        mode = 0 if tool == "depth" else 1
+        with CoverageEngine(names, lens, mode=mode, window=w, emit_wig=True) as eng:
+            eng.push_host(recs, last=True)
+            eng.finish()
+            got = {"wig": eng.output(2), "chromsize": eng.output(3)}
+            if mode == 0:
+                got.update(bedgraph=eng.output(0), depth=eng.output(1))
+            st = eng.stats()
+        assert st["records"] == g.n_reads
+        check_against_gold(got, f"{name}|{tool}|{w}")
+        if name == "c5_full":
+            depths = np.fromiter((int(ln.rsplit(b"\t", 1)[1]) for ln in got["bedgraph"].splitlines()), dtype=np.int64)
+            assert depths.max() > 10000, "config 5 is the depth > 10^4 pile-up workload"
