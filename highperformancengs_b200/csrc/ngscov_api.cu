@@ -341,7 +341,7 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	}
 	h->shift = 0;
 	const char *env = getenv("NGSCOV_SUBCHUNK");
-	if (env && atoi(env) >= 64) { int v = atoi(env), s = 6; while ((1 << (s + 1)) <= v) ++s; h->shift = s; }
+	if (env && atoi(env) >= 64) { int v = atoi(env), s = 6; while ((1 << (s + 1)) <= v) ++s; h->shift = s > 15 ? 15 : s; }   /* 16-bit record slots */
 	return ngscov_reset(h);
 }
 
@@ -859,7 +859,11 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 		t_stage += now() - t0; t0 = now();
 		const size_t sk = std::min(skip, c.ulen);
 		skip -= sk;
-		if (c.ulen == sk) continue;                                  /* header-only chunk */
+		if (c.ulen == sk) {                                          /* header-only chunk: nothing is submitted, so nothing orders the
+		                                                                inflate that reads d_comp / d_desc[idx] before their reuse */
+			CK(cudaStreamSynchronize(h->s_main));
+			continue;
+		}
 		if (!h->shift) {
 			int32_t bs = 0;
 			CK(cudaMemcpyAsync(&bs, data + sk, 4, cudaMemcpyDeviceToHost, h->s_main));
@@ -1095,6 +1099,15 @@ extern "C" int ngscov_slice_done(ngscov_t *h, int *done)
 	CK(cudaStreamSynchronize(h->s_main));
 	mr = h->h_st->max_ref_p1;
 	*done = mr >= (unsigned int)h->end_ctg + 2u ? 1 : 0;
+	return 0;
+}
+
+extern "C" int ngscov_contigs_done(ngscov_t *h, uint32_t *n)
+{
+	if (!h || !n) return NGSCOV_EINVAL;
+	if (h->runs_done) { *n = (uint32_t)h->n_ref; return 0; }
+	*n = h->next_fin_seg < h->seg.size() ? h->seg[h->next_fin_seg].contig : (h->next_fin_seg ? (uint32_t)h->n_ref : 0u);
+	if (h->next_fin_seg == 0) *n = 0;
 	return 0;
 }
 

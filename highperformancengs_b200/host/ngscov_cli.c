@@ -67,10 +67,12 @@ static FILE *open_out(const char *prefix, const char *suffix)
 	if (strncmp(name, "-", 1) == 0 || !strcmp(name, "")) fd = STDOUT_FILENO;
 	else {
 		fd = open(name, O_CREAT | O_WRONLY | O_TRUNC, 0666);
-		if (fd == -1) fprintf(stderr, "Failed to create output file (%s)", name);
+		if (fd == -1) { fprintf(stderr, "Failed to create output file (%s)\n", name); exit(1); }   /* the reference carries on and crashes later */
 	}
 	free(name);
-	return fdopen(fd, "wb");
+	FILE *f = fdopen(fd, "wb");
+	if (!f) { fprintf(stderr, "Failed to open output stream\n"); exit(1); }
+	return f;
 }
 
 static int have_bai(const char *fn)
@@ -122,6 +124,51 @@ static int inflate_blocks(blk_t *b, size_t n, int nthreads)
 }
 
 #define DIE(...) do { fprintf(stderr, __VA_ARGS__); exit(1); } while (0)
+
+/* ------------------------------------------------------------------ output
+ * The reference fprintf()s one line at a time; here a finished text sits in pinned host memory.  Regular files are
+ * written by several threads with pwrite() on disjoint ranges (a single fwrite of the 25 GB bedGraph of a 30x genome
+ * takes several times longer than the whole GPU job); pipes and terminals get a plain fwrite. */
+typedef struct { int fd; const char *buf; size_t off, len; int err; } wjob_t;
+static void *write_worker(void *arg)
+{
+	wjob_t *w = (wjob_t *)arg;
+	size_t done = 0;
+	while (done < w->len) {
+		const ssize_t k = pwrite(w->fd, w->buf + done, w->len - done > (64u << 20) ? (64u << 20) : w->len - done, (off_t)(w->off + done));
+		if (k <= 0) { w->err = 1; break; }
+		done += (size_t)k;
+	}
+	return NULL;
+}
+static int write_out(FILE *f, const char *buf, size_t len, size_t *pos, int nthreads)
+{
+	if (!len) return 0;
+	struct stat sb;
+	const int fd = fileno(f);
+	if (len < (32u << 20) || fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { *pos += len; return fwrite(buf, 1, len, f) == len ? 0 : 1; }
+	fflush(f);
+	if (nthreads > 16) nthreads = 16;
+	if (nthreads < 1) nthreads = 1;
+	pthread_t th[16]; wjob_t job[16];
+	const size_t per = (len + (size_t)nthreads - 1) / (size_t)nthreads;
+	int n = 0, err = 0;
+	for (size_t o = 0; o < len; o += per, ++n) {
+		job[n].fd = fd; job[n].buf = buf + o; job[n].off = *pos + o; job[n].len = len - o < per ? len - o : per; job[n].err = 0;
+		if (pthread_create(&th[n], NULL, write_worker, &job[n])) { write_worker(&job[n]); th[n] = 0; }
+	}
+	for (int i = 0; i < n; ++i) { if (th[i]) pthread_join(th[i], NULL); err |= job[i].err; }
+	*pos += len;
+	if (fseeko(f, (off_t)*pos, SEEK_SET)) err = 1;
+	return err;
+}
+/* "<contig> at <t> s" (reference bam2depth.c:338): one line per contig, printed when the engine reports it finalized */
+static void report_contigs(ngscov_t *h, char **ref_name, int n_ref, int *printed, long long begin, int all)
+{
+	uint32_t done = 0;
+	if (all) done = (uint32_t)n_ref; else if (ngscov_contigs_done(h, &done)) return;
+	for (; *printed < (int)done && *printed < n_ref; ++*printed) fprintf(stderr, "%s at %.3f s\n", ref_name[*printed], (double)(usec() - begin) / 1e6);
+}
 
 /* ------------------------------------------------------------------ region shards (NGSCOV_GPUS=N)
  * No counterpart in the single-process reference.  The genome is cut at multiples of 16 384 bp (the BAI linear
@@ -183,7 +230,7 @@ static void *shard_worker(void *arg)
 		return NULL;
 	}
 	if (s->empty) { rc = ngscov_push(s->h, 0, 0, NGSCOV_PUSH_LAST); if (rc) { snprintf(s->err, sizeof s->err, "%s", ngscov_strerror(rc)); s->rc = rc; return NULL; } }
-	uint8_t *tmp = (uint8_t *)malloc(65536);
+	uint8_t *tmp = (uint8_t *)malloc(65536);        /* (freed on every path below: the loop only leaves through `break`) */
 	blk_t *mine = (blk_t *)malloc(4096 * sizeof(blk_t));
 	while (!last) {
 		const long long t0 = usec();
@@ -366,6 +413,7 @@ int main(int argc, char *argv[])
 				{	uint64_t want = (64u << 20); if (getenv("NGSCOV_STAGING_MB")) want = (uint64_t)atoll(getenv("NGSCOV_STAGING_MB")) << 20; s->cfg.staging_bytes = want; }
 				++ns;
 			}
+			if (ns == 0) DIE("bam2bed: %s: nothing to shard (empty genome)\n", fn);
 			for (int g = 0; g < ns; ++g) if (pthread_create(&th[g], NULL, shard_worker, &sh[g])) DIE("bam2bed: cannot start shard thread\n");
 			for (int g = 0; g < ns; ++g) pthread_join(th[g], NULL);
 			for (int g = 0; g < ns; ++g) if (sh[g].rc) DIE("bam2bed: shard %d: %s\n", g, sh[g].err);
@@ -394,10 +442,11 @@ int main(int argc, char *argv[])
 			FILE *outs2[4] = { f_bed, f_depth, f_wig, f_chr };
 			for (int k = 0; k < 4; ++k) {
 				if (!outs2[k]) continue;
+				size_t pos = 0;
 				for (int g = 0; g < (k == 0 ? ns : 1); ++g) {
 					const char *buf; size_t len;
 					if ((rc2 = ngscov_output(sh[g].h, which2[k], &buf, &len))) DIE("bam2bed: %s\n", ngscov_strerror(rc2));
-					if (len && fwrite(buf, 1, len, outs2[k]) != len) DIE("bam2bed: write failed\n");
+					if (write_out(outs2[k], buf, len, &pos, nthreads)) DIE("bam2bed: write failed\n");
 				}
 			}
 			for (int j = 0; j < n_ref; ++j) fprintf(stderr, "%s at %.3f s\n", ref_name[j], (double)(usec() - begin) / 1e6);
@@ -427,9 +476,20 @@ int main(int argc, char *argv[])
 
 		const int gpu_inflate = getenv("NGSCOV_GPU_INFLATE") && atoi(getenv("NGSCOV_GPU_INFLATE")) != 0;
 		long long t_io = 0;
+		int printed = 0;
 		if (gpu_inflate) {
-			/* the whole file goes to the device compressed; the inflated BAM header (hdr_len bytes) is skipped there */
-			if ((rc = ngscov_push_bgzf(h, file, off, hdr_len, NGSCOV_PUSH_LAST))) DIE("bam2bed: %s: %s (%s)\n", fn, ngscov_strerror(rc), ngscov_last_cuda_error(h));
+			/* the file goes to the device compressed, a few hundred blocks at a time so that finished contigs can be reported;
+			 * the inflated BAM header (hdr_len bytes) is skipped on the device */
+			size_t b0 = 0, skip = hdr_len;
+			const size_t step = 4096;                              /* blocks per call: ~64 MB of BAM */
+			while (b0 < nblk) {
+				const size_t b1 = b0 + step < nblk ? b0 + step : nblk;
+				const uint8_t *p0 = blk[b0].src - 18, *p1 = b1 < nblk ? blk[b1].src - 18 : file + off;
+				if ((rc = ngscov_push_bgzf(h, p0, (size_t)(p1 - p0), skip, b1 >= nblk ? NGSCOV_PUSH_LAST : 0))) DIE("bam2bed: %s: %s (%s)\n", fn, ngscov_strerror(rc), ngscov_last_cuda_error(h));
+				skip = 0; b0 = b1;
+				report_contigs(h, ref_name, n_ref, &printed, begin, 0);
+			}
+			if (nblk == 0 && (rc = ngscov_push_bgzf(h, file, 0, 0, NGSCOV_PUSH_LAST))) DIE("bam2bed: %s: %s\n", fn, ngscov_strerror(rc));
 		}
 		/* stream: [tail of the header blocks] then the remaining blocks, inflated in parallel into staging */
 		int idx = 0; size_t b = hb;
@@ -451,19 +511,20 @@ int main(int argc, char *argv[])
 			t_io += usec() - t0;
 			pushed_last = b >= nblk;
 			if ((rc = ngscov_push(h, idx, fill, pushed_last ? NGSCOV_PUSH_LAST : 0))) DIE("bam2bed: %s: %s\n", fn, ngscov_strerror(rc));
+			report_contigs(h, ref_name, n_ref, &printed, begin, 0);
 			idx ^= 1;
 		}
 		if ((rc = ngscov_finish(h))) DIE("bam2bed: %s: %s (%s)\n", fn, ngscov_strerror(rc), ngscov_last_cuda_error(h));
 
 		const int which[4] = { NGSCOV_OUT_BEDGRAPH, NGSCOV_OUT_DEPTH, NGSCOV_OUT_WIG, NGSCOV_OUT_CHROMSIZE };
 		FILE *outs[4] = { f_bed, f_depth, f_wig, f_chr };
+		report_contigs(h, ref_name, n_ref, &printed, begin, 1);
 		for (int k = 0; k < 4; ++k) {
 			if (!outs[k]) continue;
-			const char *buf; size_t len;
+			const char *buf; size_t len, pos = 0;
 			if ((rc = ngscov_output(h, which[k], &buf, &len))) DIE("bam2bed: %s\n", ngscov_strerror(rc));
-			if (len && fwrite(buf, 1, len, outs[k]) != len) DIE("bam2bed: write failed\n");
+			if (write_out(outs[k], buf, len, &pos, nthreads)) DIE("bam2bed: write failed\n");
 		}
-		for (int j = 0; j < n_ref; ++j) fprintf(stderr, "%s at %.3f s\n", ref_name[j], (double)(usec() - begin) / 1e6);
 		if (verbose) {
 			ngscov_stats_t st; ngscov_stats(h, &st);
 			fprintf(stderr, "ngscov: %llu records (%llu kept), %llu runs; host read+inflate %.3f s (%d threads); device: h2d %.3f ms ingest %.3f ms "

@@ -164,6 +164,10 @@ int ngscov_finish_runs(ngscov_t *h);
  * pushing and close the input with NGSCOV_PUSH_LAST | NGSCOV_PUSH_TRUNCATED_OK.  Completes the pending push first
  * (synchronises); call it only near the expected end.  Always 0 for a handle without a slice. */
 int ngscov_slice_done(ngscov_t *h, int *done);
+/* Streamed finalize: how many leading contigs of the header are finished by now (their runs, bins and bedGraph text
+ * exist and the text is on its way to the host).  Non-blocking; used by the drivers for the reference's per-contig
+ * progress line (bam2depth.c:338).  Equals n_ref after ngscov_finish_runs. */
+int ngscov_contigs_done(ngscov_t *h, uint32_t *n);
 int ngscov_halo_get(ngscov_t *h, ngscov_halo *halo);
 int ngscov_halo_put(ngscov_t *h, int drop_first, uint32_t new_last_end);
 
