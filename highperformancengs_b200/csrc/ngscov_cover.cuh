@@ -448,6 +448,37 @@ __device__ __noinline__ uint32_t bed_line_bytes(char *dst, const NameTable nt, u
 	return (uint32_t)(p - dst);
 }
 /* one line through the register writer with full conversions (a start before the tile, depth of five digits or more) */
+/* The register line writer of ngscov_hd.h (ngs_lw) on a 32-bit shared-memory address, with the word stores predicated
+ * in PTX: written as C `if`s the three conditional stores of a piece become a ladder of divergent branches (BSSY / BRA /
+ * BSYNC per piece, a fifth of the instructions of a line); a predicated st.shared is one instruction. */
+__device__ __forceinline__ void sts_if(uint32_t addr, uint32_t v, bool p)
+{
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u32 [%0], %1;\n\t}" :: "r"(addr), "r"(v), "r"((uint32_t)p) : "memory");
+}
+struct ngs_lws {
+	uint32_t a;          /* shared address of the word the next byte goes to */
+	uint32_t carry, k;   /* the k (0..3) low bytes of that word already produced */
+	__device__ __forceinline__ void begin(uint32_t base, uint32_t byte_off) { a = base + (byte_off & ~3u); k = byte_off & 3u; carry = 0; }
+	__device__ __forceinline__ void put12(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t cnt)   /* cnt in 1..12 */
+	{
+		const uint32_t sel = 0x7654u - 0x1111u * k;
+		const uint32_t x0 = __byte_perm(0u, q0, sel) | carry, x1 = __byte_perm(q0, q1, sel), x2 = __byte_perm(q1, q2, sel), x3 = __byte_perm(q2, 0u, sel);
+		const uint32_t tot = k + cnt, nw = tot >> 2;
+		sts_if(a, x0, nw > 0u); sts_if(a + 4u, x1, nw > 1u); sts_if(a + 8u, x2, nw > 2u);
+		carry = nw < 2u ? (nw == 0u ? x0 : x1) : (nw == 2u ? x2 : x3);
+		a += nw << 2; k = tot & 3u;
+	}
+	__device__ __forceinline__ void put16(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, uint32_t cnt)   /* cnt in 1..16 */
+	{
+		const uint32_t sel = 0x7654u - 0x1111u * k;
+		const uint32_t x0 = __byte_perm(0u, q0, sel) | carry, x1 = __byte_perm(q0, q1, sel), x2 = __byte_perm(q1, q2, sel), x3 = __byte_perm(q2, q3, sel), x4 = __byte_perm(q3, 0u, sel);
+		const uint32_t tot = k + cnt, nw = tot >> 2;
+		sts_if(a, x0, nw > 0u); sts_if(a + 4u, x1, nw > 1u); sts_if(a + 8u, x2, nw > 2u); sts_if(a + 12u, x3, nw > 3u);
+		carry = nw < 2u ? (nw == 0u ? x0 : x1) : (nw == 2u ? x2 : (nw == 3u ? x3 : x4));
+		a += nw << 2; k = tot & 3u;
+	}
+};
+
 /* (the writer state travels by value: a reference would pin it in local memory for the whole text loop) */
 __device__ __noinline__ uint4 lw_generic_line(uint32_t *w, uint32_t carry, uint32_t k, uint32_t n_lo, uint32_t n_hi, uint32_t nl, uint32_t s, uint32_t e, uint32_t d)
 {
@@ -456,6 +487,17 @@ __device__ __noinline__ uint4 lw_generic_line(uint32_t *w, uint32_t carry, uint3
 	ngs_num_conv(s, xs); ngs_num_conv(e, xe); ngs_num_conv(d, xd);
 	L.bed_line(n_lo, n_hi, nl, xs, xe, xd);
 	return make_uint4((uint32_t)(L.w - w), L.carry, L.k, 0u);
+}
+/* cold paths kept out of line: the hot loop of k_cover must stay small enough for the instruction cache */
+struct AtomicBinAdd { unsigned long long *bins; __device__ void operator()(uint32_t k, int64_t v) const { atomicAdd(bins + k, (unsigned long long)v); } };
+__device__ __noinline__ void bin_run_slow(int variant, uint32_t s, uint32_t e, int d, uint32_t W, uint32_t L, uint32_t n_win, unsigned long long *bins)
+{
+	AtomicBinAdd add = { bins };
+	ngs_bin_run(variant, s, e, (int64_t)d, W, L, n_win, add);
+}
+__device__ __noinline__ uint32_t line_len_generic(uint32_t nl, uint32_t s, uint32_t e, int d)
+{
+	return nl + ngs_ndigits(s) + ngs_ndigits(e) + ngs_len_i32(d) + 3u;
 }
 /* thread 0 / 1: the cached prefixes "name\tH" and "\tH" for H0 and H0 + 1 (positions of a tile span at most two H) */
 __device__ __noinline__ void fill_tile_hcache(ngs_hcache *dst, uint32_t H, uint32_t n_lo, uint32_t n_hi, uint32_t nl)
@@ -696,7 +738,7 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 		unsigned int my_len = 0;
 		for (unsigned int r = t; r < tot_cnt; r += NGS_COVER_THREADS) {
 			const int depth = c_dep[r] + icarry;
-			if (depth != 0) my_len += nl + ngs_ndigits(r ? pos0 + c_pos[r - 1] : first_start) + ngs_ndigits(pos0 + c_pos[r]) + ngs_len_i32(depth) + 3u;
+			if (depth != 0) my_len += line_len_generic(nl, r ? pos0 + c_pos[r - 1] : first_start, pos0 + c_pos[r], depth);
 		}
 		my_len = __reduce_add_sync(full, my_len);
 		if (lane == 0) s_w[warp] = my_len;
@@ -710,14 +752,15 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 	/* ---- batches of NGS_CBATCH boundaries, NGS_CIPT consecutive ones per thread: window bins, statistics and the
 	 * bedGraph lines (assembled in registers, staged in shared memory as in k_format_bed; the byte-offset look-back runs
 	 * after the first batch is assembled) */
-	BinAcc bacc; bacc.bins = A.bins + sg.bins0; bacc.k = -1; bacc.acc = 0;
+	unsigned long long *const seg_bins = A.bins + sg.bins0;
 	unsigned int my_runs = 0, my_first = 0xffffffffu, my_last = 0; int my_max = 0, my_min = 0;
 	const uint32_t W = A.window;
 	const uint32_t kt = pos0 / W;
 	/* fast path of the bins: run inside the window of the tile's first position and inside the contig (positions and
 	 * windows are below 2^30, so the bounds fit 32 bits) */
 	const uint32_t wlo = kt * W, whi = min(wlo + W - 1u, sg.ref_len);
-	long long facc = 0;                                              /* contribution to window kt */
+	const uint32_t wlo1 = wlo + W, whi1 = min(wlo1 + W - 1u, sg.ref_len);   /* a tile of 4096 positions reaches into window kt + 1 at most when W >= 4096 */
+	long long facc = 0, facc1 = 0;                                   /* contributions to windows kt and kt + 1 */
 	const uint32_t Hb = (H0 + 1u) * 10000u;                          /* positions >= Hb have H = H0 + 1 */
 	const uint32_t nH0 = (TEXT && !tile_slow) ? s_hc[0].nH : 0u, nH1 = (TEXT && !tile_slow) ? s_hc[1].nH : 0u;
 	uint32_t *sw = reinterpret_cast<uint32_t *>(s_stage);
@@ -739,12 +782,13 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 			if (D[i] != 0) {
 				const uint32_t start = i ? E[i - 1] : S0, pos = E[i];
 				if (start >= wlo && pos <= whi) facc += (long long)(pos - start) * D[i];
-				else ngs_bin_run(A.variant, start, pos, (int64_t)D[i], W, sg.ref_len, sg.n_win, bacc);
+				else if (start >= wlo1 && pos <= whi1) facc1 += (long long)(pos - start) * D[i];
+				else bin_run_slow(A.variant, start, pos, D[i], W, sg.ref_len, sg.n_win, seg_bins);   /* rare: a run leaving the tile's first window */
 				++my_runs; my_max = D[i] > my_max ? D[i] : my_max; my_min = D[i] < my_min ? D[i] : my_min;
 				my_first = r0 + i < my_first ? r0 + i : my_first; my_last = r0 + i;
 				if (TEXT) {
 					/* positions inside the tile have the digits of H0 or H0 + 1 in front of four more */
-					if (tile_slow || start < pos0 || (uint32_t)D[i] >= 10000u) len[i] = nl + ngs_ndigits(start) + ngs_ndigits(pos) + ngs_len_i32(D[i]) + 3u;
+					if (tile_slow || start < pos0 || (uint32_t)D[i] >= 10000u) len[i] = line_len_generic(nl, start, pos, D[i]);
 					else {
 						const uint32_t nd = 1u + ((uint32_t)D[i] >= 10u) + ((uint32_t)D[i] >= 100u) + ((uint32_t)D[i] >= 1000u);
 						len[i] = nl + (start >= Hb ? nH1 : nH0) + (pos >= Hb ? nH1 : nH0) + 11u + nd;
@@ -766,8 +810,9 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 		if (!multi) { total = btotal; if (t == 0) st_relaxed_u64(&A.stF[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | total); }
 		const bool staged = btotal + 32u <= A.stage_bytes;
 		if (t == 0 && staged && !tile_slow) sw[btotal >> 2] = 0;    /* the batch's last, partial word is only ever OR-ed into */
-		ngs_lw<uint32_t *> L;
-		L.begin(sw, off);
+		const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sw);
+		ngs_lws L;
+		L.begin(sbase, off);
 		if (staged && tlen) {
 			if (tile_slow) {
 				char *p = s_stage + off;
@@ -783,8 +828,8 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 					const uint32_t start = i ? E[i - 1] : S0, pos = E[i];
 					const uint32_t he = pos >= Hb, hs = start >= Hb;
 					if (start < pos0 || (uint32_t)D[i] >= 10000u || hs != he) {
-						const uint4 q = lw_generic_line(L.w, L.carry, L.k, n_lo, n_hi, nl, start, pos, (uint32_t)D[i]);
-						L.w += q.x; L.carry = q.y; L.k = q.z; hlast = 2u; continue;
+						const uint4 q = lw_generic_line(sw + ((L.a - sbase) >> 2), L.carry, L.k, n_lo, n_hi, nl, start, pos, (uint32_t)D[i]);
+						L.a += q.x << 2; L.carry = q.y; L.k = q.z; hlast = 2u; continue;
 					}
 					if (he != hcur) {
 						const ngs_hcache &c = s_hc[he];
@@ -802,7 +847,7 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 			}
 		}
 		__syncthreads();                                        /* every head word stored */
-		if (staged && !tile_slow && tlen && L.k) atomicOr(L.w, L.carry);
+		if (staged && !tile_slow && tlen && L.k) atomicOr(sw + ((L.a - sbase) >> 2), L.carry);
 		if (bt == 0) {
 			if (tile > 0 && !(A.debug & 1)) goff = lookback_bytes(A.stF, tile, total, s_li, s_lb, A.st);
 			else __syncthreads();
@@ -853,10 +898,15 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 	/* ---- warp- then block-level aggregation of the pending window contribution and the statistics
 	 * (one global atomic per distinct window per tile instead of one per thread) */
 	{
-		if (bacc.k >= 0 && bacc.acc != 0) atomicAdd(bacc.bins + bacc.k, (unsigned long long)bacc.acc);   /* rare: a run leaving the tile's first window */
 		long long wk = (long long)kt, wv = facc;
 		#pragma unroll
 		for (int o = 16; o > 0; o >>= 1) wv += __shfl_xor_sync(full, wv, o);
+		if (__any_sync(full, facc1 != 0)) {
+			long long w1 = facc1;
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) w1 += __shfl_xor_sync(full, w1, o);
+			if (lane == 0 && w1) atomicAdd(seg_bins + kt + 1, (unsigned long long)w1);
+		}
 		const unsigned wr = __reduce_add_sync(full, my_runs);
 		const int wmax = __reduce_max_sync(full, my_max), wmin = __reduce_min_sync(full, my_min);
 		const unsigned wfirst = __reduce_min_sync(full, my_first), wlast = __reduce_max_sync(full, my_last);
@@ -872,12 +922,12 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 		for (int w = 0; w < NGS_CNW; ++w) {
 			if (s_bk[w] >= 0) {
 				if (s_bk[w] == ck) cv += s_bv[w];
-				else { if (ck >= 0 && cv) atomicAdd(bacc.bins + ck, (unsigned long long)cv); ck = s_bk[w]; cv = s_bv[w]; }
+				else { if (ck >= 0 && cv) atomicAdd(seg_bins + ck, (unsigned long long)cv); ck = s_bk[w]; cv = s_bv[w]; }
 			}
 			nr += s_wr[w]; mx = s_wmax[w] > mx ? s_wmax[w] : mx; mn = s_wmin[w] < mn ? s_wmin[w] : mn;
 			fr = s_rfirst[w] < fr ? s_rfirst[w] : fr; lr = s_rlast[w] > lr ? s_rlast[w] : lr;
 		}
-		if (ck >= 0 && cv) atomicAdd(bacc.bins + ck, (unsigned long long)cv);
+		if (ck >= 0 && cv) atomicAdd(seg_bins + ck, (unsigned long long)cv);
 		atomicAdd(&A.st->n_boundaries, (unsigned long long)tot_cnt);
 		if (nr) {
 			atomicAdd(&A.st->n_runs, nr);
