@@ -633,6 +633,7 @@ def bind_to_gpu_numa(local):
         if bus.startswith("00000000:"):
             bus = bus[4:]
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        info = {"node": None, "sysfs_numa_node": node}
         if node >= 0:
             cpus = set()
             for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
@@ -645,7 +646,14 @@ def bind_to_gpu_numa(local):
     except Exception as ex:
         info = {"node": None, "error": str(ex)[:80]}
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // (world if info.get("node") is None else 1)))
+    nthr = max(1, len(os.sched_getaffinity(0)) // (world if info.get("node") is None else 1))
+    os.environ["OMP_NUM_THREADS"] = str(nthr)
+    try:                                  # libgomp is already initialised (torch loaded it) with torchrun's OMP_NUM_THREADS=1
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(nthr)
+    except Exception:
+        pass
+    info["omp_threads"] = nthr
     return info
 
 
