@@ -96,6 +96,7 @@ struct ngscov {
 	uint32_t *d_far_flag, *d_row_a, *d_row_b;
 	unsigned long long *d_stF, *d_stC;       /* look-back words of the owner tiles: bytes / (sum, last boundary) */
 	uint4 *d_tile_first, *d_tile_last;
+	uint64_t fin_tile;                       /* owner tiles already finalized (streamed finalize works at tile granularity) */
 	bool halo_have; ngscov_run cov_first, cov_last;   /* first / last non-zero run over the cover launches so far */
 	size_t bed_begin;                        /* halo: bytes of the dropped first line */
 	std::string bed_tail; size_t bed_tail_old; /* halo: replacement of the last line, and how many bytes it replaces */
@@ -409,7 +410,7 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	CK(cudaStreamSynchronize(h->s_out));
 	h->next_fin_seg = 0; h->mops_fin = 0; h->bins_zeroed = false; h->bed_off = 0; h->bed_d2h = 0;
 	h->acc_boundaries = h->acc_runs = 0; h->acc_max = h->acc_min = 0;
-	h->rows_used = 0; h->red_mode = false; h->halo_have = false;
+	h->rows_used = 0; h->red_mode = false; h->halo_have = false; h->fin_tile = 0;
 	h->bed_begin = 0; h->bed_tail.clear(); h->bed_tail_old = 0; h->bed_patched = false; h->dev_stitched = false;
 	if (h->d_halo) { CK(cudaMemsetAsync(h->d_halo, 0, 9 * 8, h->s_main)); CK(cudaStreamSynchronize(h->s_main)); }
 	return 0;
@@ -562,6 +563,7 @@ static int launch_special(ngscov *h, const IngestArgs &A, int mode)
 
 /* wait for the verification of the chunk in flight; repair mis-speculated sub-chunks; fix the carry */
 static int stream_finalize(ngscov *h, size_t seg_end);
+static int stream_finalize_cover(ngscov *h);
 
 static int resolve_pending(ngscov *h, bool allow_stream = false)
 {
@@ -593,7 +595,7 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 		/* the input is not coordinate sorted: the owner tiles cannot find their records by key.  Everything pushed so far
 		 * already had its rare deltas added to the global array; add the ordinary ones too (needs only the table) and go
 		 * on with REDs + the classic scan.  Contigs that were already finalized cannot be taken back. */
-		if (h->next_fin_seg > 0) { h->sticky_err = NGSCOV_EUNSORTED; h->pending = false; return NGSCOV_EUNSORTED; }
+		if (h->next_fin_seg > 0 || h->fin_tile > 0) { h->sticky_err = NGSCOV_EUNSORTED; h->pending = false; return NGSCOV_EUNSORTED; }
 		h->red_mode = true; h->stream_fin = false;
 		IngestArgs A = make_ingest_args(h, h->p_base, h->p_n, h->p_nsub, h->p_from_state, h->p_fixed0);
 		A.rows = h->d_rows; A.ent = h->d_ent; A.rkmax = h->d_rkmax; A.n_sub = (int64_t)h->rows_used;
@@ -610,6 +612,10 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 		/* these variants count in striped counters: fold the stripes of the verification-time snapshot (K2 of the
 		 * chunks before this one; the contigs it reports complete were decoded entirely by those) */
 		for (int i = 0; i < NGS_CTR_STRIPES; ++i) h->h_st->m_ops += h->h_ctr[i * 16 + 2];
+	}
+	if (allow_stream && h->stream_fin && h->cover && !h->red_mode) {
+		if (h->h_st->flags & (NGS_FLAG_EFORMAT | NGS_FLAG_ERANGE)) return 0;
+		return stream_finalize_cover(h);
 	}
 	if (allow_stream && h->stream_fin && !(h->h_st->flags & (NGS_FLAG_EFORMAT | NGS_FLAG_ERANGE)) && h->h_st->max_ref_p1 > 1) {
 		/* complete contigs -> complete segments (a region shard only holds the contigs that intersect its slice) */
@@ -973,7 +979,8 @@ static int scan_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_b
 
 static int format_bed_range(ngscov *h, size_t s0, size_t s1);
 static int grow_host_text(ngscov *h, int which, size_t need, size_t keep);
-static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_bound);
+static int cover_tiles(ngscov *h, uint64_t t0, uint64_t t1, unsigned long long mops_bound);
+static int stream_finalize_cover(ngscov *h);
 
 /* Finalize segments [next_fin_seg, seg_end) while the rest of the stream is still arriving. */
 static int stream_finalize_impl(ngscov *h, size_t seg_end);
@@ -989,12 +996,6 @@ static int stream_finalize_impl(ngscov *h, size_t seg_end)
 	int r;
 	const unsigned long long mops_now = h->h_st->m_ops;
 	const size_t s0 = h->next_fin_seg;
-	if (h->cover && !h->red_mode) {
-		if ((r = cover_range(h, s0, seg_end, mops_now - h->mops_fin))) return r;
-		h->mops_fin += h->h_st2->n_boundaries / 2;
-		h->next_fin_seg = seg_end;
-		return 0;
-	}
 	if ((r = scan_range(h, s0, seg_end, mops_now - h->mops_fin))) return r;
 	/* how many of the intervals seen so far belong to the finished contigs is not known exactly; every interval
 	 * makes at most two boundaries, so boundaries/2 is a safe lower bound of what they consumed */
@@ -1041,7 +1042,7 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 	if (st.flags & NGS_FLAG_ERANGE) return h->sticky_err = NGSCOV_ERANGE;
 
 	if (h->cover && !h->red_mode) {
-		if (h->next_fin_seg < h->seg.size() && (r = cover_range(h, h->next_fin_seg, h->seg.size(), st.m_ops - h->mops_fin))) return r;
+		if (!h->seg.empty() && h->fin_tile < h->n_tiles * NGS_CPT && (r = cover_tiles(h, h->fin_tile, h->n_tiles * NGS_CPT, st.m_ops - h->mops_fin))) return r;
 		if (h->cfg.mode == NGSCOV_MODE_DEPTH) { h->text_ready[NGSCOV_OUT_BEDGRAPH] = true; h->text_len[NGSCOV_OUT_BEDGRAPH] = h->bed_off; }
 		h->next_fin_seg = h->seg.size();
 		h->diff_dirty = false;
@@ -1316,14 +1317,20 @@ static int run_format(ngscov *h, int which, unsigned long long n_items, const Pr
 
 static uint32_t dig(uint64_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n; } return n; }
 
-/* Cover pipeline: owner tiles over segments [s0, s1) -- accumulate, scan, window bins and (DEPTH mode) the bedGraph
- * text appended at bed_off, one kernel.  h_st2 receives the counters. */
-static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_bound)
+/* Cover pipeline: owner tiles [t0, t1) (global owner-tile indices, any range: a launch may start and end inside a
+ * contig) -- accumulate, scan, window bins and (DEPTH mode) the bedGraph text appended at bed_off, one kernel.
+ * h_st2 receives the counters. */
+static int cover_tiles(ngscov *h, uint64_t t0, uint64_t t1, unsigned long long mops_bound)
 {
 	int r;
 	const bool text = h->cfg.mode == NGSCOV_MODE_DEPTH;
-	const uint64_t t0 = h->seg[s0].tile0 * NGS_CPT, t1 = (s1 < h->seg.size() ? h->seg[s1].tile0 : h->n_tiles) * NGS_CPT;   /* owner tiles */
+	const uint64_t total_tiles = h->n_tiles * NGS_CPT;
 	const uint64_t elems = (t1 - t0) * (uint64_t)NGS_CT;
+	/* segments the range touches */
+	size_t s0 = 0, s1 = h->seg.size();
+	while (s0 + 1 < h->seg.size() && h->seg[s0 + 1].tile0 * NGS_CPT <= t0) ++s0;
+	while (s1 > s0 + 1 && h->seg[s1 - 1].tile0 * NGS_CPT >= t1) --s1;
+	const bool continues = t0 > h->seg[s0].tile0 * NGS_CPT;     /* the range starts inside a contig: carry from the tile before */
 	size_t bound = 0; uint32_t stage = 0;
 	if (text) {
 		/* boundaries: at most two per accumulated interval, never more than tracked positions; depth <= intervals */
@@ -1337,8 +1344,8 @@ static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_
 			typ_line = std::max(typ_line, nm + 2 * pd + 2 + std::min<uint32_t>(dd, 5) + 1);
 		}
 		bound = nb * max_line;
-		/* the staging area of a batch (1024 lines) is sized for depths below 10^5; a batch that needs more writes its
-		 * lines straight to global memory */
+		/* the staging area of a batch is sized for depths below 10^5; a batch that needs more writes its lines straight
+		 * to global memory */
 		stage = (uint32_t)std::min<size_t>(NGS_CBATCH * typ_line + 32, 64 * 1024);
 		if (getenv("NGSCOV_COVER_STAGE")) stage = (uint32_t)atoi(getenv("NGSCOV_COVER_STAGE"));
 		if ((r = grow_text(h, NGSCOV_OUT_BEDGRAPH, h->bed_off + bound + 64, h->bed_off))) return r;
@@ -1362,6 +1369,7 @@ static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_
 		A.ent = h->d_ent; A.rows = h->d_rows; A.row_a = h->d_row_a + t0; A.row_b = h->d_row_b + t0;
 		A.diff = h->d_diff + t0 * (uint64_t)NGS_CT; A.far_flag = h->d_far_flag + t0;
 		A.stB = h->d_stC + t0; A.stF = h->d_stF + t0;
+		A.prev = continues ? h->d_stC + t0 - 1 : nullptr;
 		A.bins = h->d_bins; A.window = h->cfg.window; A.variant = h->cfg.mode == NGSCOV_MODE_WIG ? 1 : 0;
 		A.tile_first = h->d_tile_first + t0; A.tile_last = h->d_tile_last + t0;
 		A.nt.names = h->d_names; A.nt.name_off = h->d_name_off; A.nt.name8 = h->d_name8;
@@ -1395,7 +1403,7 @@ static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_
 		h->bed_off += (size_t)s2.fmt_bytes;
 		h->text_len[NGSCOV_OUT_BEDGRAPH] = h->bed_off;
 		h->stats.out_bytes[NGSCOV_OUT_BEDGRAPH] = h->bed_off;
-		const bool streamed = h->stream_fin && (h->next_fin_seg > 0 || s1 < h->seg.size() || s0 > 0);
+		const bool streamed = h->stream_fin && (t0 > 0 || t1 < total_tiles);
 		if (streamed && h->bed_off > h->bed_d2h && !getenv("NGSCOV_DEBUG_NOD2H")) {
 			if ((r = grow_host_text(h, NGSCOV_OUT_BEDGRAPH, h->bed_off, h->bed_d2h))) return r;
 			CK(cudaMemcpyAsync(h->h_text[NGSCOV_OUT_BEDGRAPH] + h->bed_d2h, h->d_text[NGSCOV_OUT_BEDGRAPH] + h->bed_d2h, h->bed_off - h->bed_d2h,
@@ -1403,7 +1411,40 @@ static int cover_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_
 			h->bed_d2h = h->bed_off;
 		}
 	}
+	h->fin_tile = t1;
+	size_t ns = 0;                                              /* segments entirely below the finalized tiles */
+	while (ns < h->seg.size() && (ns + 1 < h->seg.size() ? h->seg[ns + 1].tile0 : h->n_tiles) * NGS_CPT <= t1) ++ns;
+	if (t1 >= total_tiles) ns = h->seg.size();
+	h->next_fin_seg = ns;
 	return 0;
+}
+
+/* Streamed finalize of the cover pipeline, at tile granularity.  The input is coordinate sorted (checked), so with
+ * (contig kc, position kp) the largest record key verified so far every contig before kc is complete and so is every
+ * position of kc below kp: no later record can add a delta there.  Finalizing whole tiles below that point while the
+ * stream is still arriving lets the device -> host copy of the text overlap the input from the first chunks on, also for
+ * a region shard that holds one or two contigs. */
+static int stream_finalize_cover(ngscov *h)
+{
+	const unsigned long long key = h->h_st->key_chunk_max;
+	if (key == 0 || h->seg.empty()) return 0;
+	const uint32_t kc = (uint32_t)(key >> 32), kp = (uint32_t)key ? (uint32_t)key - 1u : 0u;
+	uint64_t upto = h->fin_tile;
+	for (size_t s = 0; s < h->seg.size(); ++s) {
+		const ngs_seg &sg = h->seg[s];
+		const uint64_t t_beg = sg.tile0 * NGS_CPT, t_end = (s + 1 < h->seg.size() ? h->seg[s + 1].tile0 : h->n_tiles) * NGS_CPT;
+		if (kc == 0xFFFFFFFFu || sg.contig < kc || (h->end_ctg == (int32_t)kc && sg.contig == kc && kp >= h->end_pos)) upto = std::max(upto, t_end);
+		else if (sg.contig == kc && kp > sg.clip_lo) upto = std::max(upto, std::min<uint64_t>(t_end, t_beg + (kp - sg.clip_lo) / NGS_CT));
+	}
+	const uint64_t min_tiles = getenv("NGSCOV_STREAM_MIN_TILES") ? (uint64_t)atoll(getenv("NGSCOV_STREAM_MIN_TILES")) : 2048;
+	if (upto < h->fin_tile + min_tiles) return 0;               /* not worth a launch yet */
+	const auto t0 = std::chrono::steady_clock::now();
+	/* the interval counters lag one chunk behind the keys: allow for every record the pending chunk can hold */
+	const unsigned long long mops = h->h_st->m_ops - h->mops_fin + (unsigned long long)(h->p_n / 36 + 1) * 2;
+	int r = cover_tiles(h, h->fin_tile, upto, mops);
+	if (!r) h->mops_fin += h->h_st2->n_boundaries / 2;
+	h->fin_wall += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++h->fin_calls;
+	return r;
 }
 
 /* bedGraph text of segments [s0, s1) from the records of the scan_range that just ran over them; appended at

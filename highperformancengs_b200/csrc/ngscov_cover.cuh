@@ -397,8 +397,11 @@ __global__ void __launch_bounds__(256) k_special_reds(const __grid_constant__ In
 	DevMem mem = { A.base, A.n };
 	FarSink sink = { A.diff, A.far_flag, &A.st->flags, mode == 0 ? 1 : 0 };
 	unsigned int s_rec = 0, s_kept = 0, s_mops = 0, s_cig = 0, s_max = 0, s_sp = 0;
-	for (int64_t r0 = wid * 32; r0 < A.n_sub; r0 += n_warps * 32) {
-		const int64_t c = r0 + lane;
+	/* rows are dealt out round robin (lane l of warp w takes rows w + l * n_warps of a stripe): special rows come in
+	 * bursts of consecutive rows -- the records hanging into a region shard from the left -- and a burst inside one
+	 * warp's 32 rows was processed row after row (0.19 ms per shard at N > 1) */
+	for (int64_t base = 0; base < A.n_sub; base += n_warps * 32) {
+		const int64_t c = base + (int64_t)lane * n_warps + wid;
 		uint4 b = make_uint4(0, 0, 0xffffffffu, 0), d = make_uint4(0, 0, 0, 0);
 		if (c < A.n_sub) { b = reinterpret_cast<const uint4 *>(A.rows + c)[1]; d = reinterpret_cast<const uint4 *>(A.rows + c)[2]; }
 		/* b = count, special, ctg, nrec ; d = nkept, nmops, ncig, max_ref_p1 */
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(256) k_special_reds(const __grid_constant__ In
 			const int src = __ffs(todo) - 1; todo &= todo - 1;
 			const unsigned int count = __shfl_sync(full, b.x, src), special = __shfl_sync(full, b.y, src);
 			const int ctg0 = (int)__shfl_sync(full, b.z, src);
-			const int64_t row = r0 + src;
+			const int64_t row = base + (int64_t)src * n_warps + wid;
 			if (special & NGS_ROW_OVERFLOW) {
 				if (mode != 2 && lane == 0) {         /* the whole row goes the classic way: sequential walk, run-length combined REDs */
 					long long hi = (row + 1) << A.shift; if (hi > A.n) hi = A.n;
@@ -487,6 +490,8 @@ struct CoverArgs {
 	const uint32_t *row_a, *row_b;
 	int *diff; uint32_t *far_flag;       /* far array */
 	unsigned long long *stB, *stF;       /* look-back words: status:2 | lastb:30 | sum:32  and  status:2 | bytes:62 */
+	const unsigned long long *prev;      /* launch that continues inside a contig: the inclusive (sum, last boundary) word of the
+	                                        tile before its first one, published by the previous launch; else null */
 	unsigned long long *bins; uint32_t window; int variant;
 	uint4 *tile_first, *tile_last;       /* first / last non-zero run of each tile (halo candidates) */
 	NameTable nt;
@@ -735,7 +740,8 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 	const int psum = __shfl_up_sync(full, isum, 1);
 	const unsigned int pcnt = __shfl_up_sync(full, icnt, 1);
 	const uint32_t agg_lastb = tot_last ? pos0 + tot_last : 0;     /* 1 + contig position, 0 = none */
-	if (t == 0) st_relaxed_u64(&A.stB[tile], ((tile == 0 ? NGS_ST_INC : NGS_ST_AGG) << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
+	const bool has_pred = tile > 0 || A.prev != nullptr;
+	if (t == 0) st_relaxed_u64(&A.stB[tile], ((has_pred ? NGS_ST_AGG : NGS_ST_INC) << 62) | ((unsigned long long)agg_lastb << 32) | (uint32_t)(int)tot_sum);
 
 	/* ---- compact the boundaries (tile-relative position, depth before it WITHOUT the carry) while the predecessors
 	 * publish their aggregates */
@@ -752,16 +758,16 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 
 	/* ---- decoupled look-back over (sum, last boundary) */
 	long long carry = 0; unsigned int tile_last = 0;
-	if (tile > 0 && !(A.debug & 1)) {
+	if (has_pred && !(A.debug & 1)) {
 		long long base = (long long)tile - 1;
 		for (;;) {
 			const long long idx = base - t;
-			unsigned long long b = NGS_ST_INC << 62;
+			unsigned long long b = NGS_ST_INC << 62;             /* virtual tiles before the launch's first: inclusive zero ... */
 			if (idx >= 0) {
 				unsigned int polls = 0;
 				do { b = ld_relaxed_u64(&A.stB[idx]); } while ((b >> 62) == NGS_ST_EMPTY && ++polls < NGS_WATCHDOG_POLLS);
 				if ((b >> 62) == NGS_ST_EMPTY) { atomicOr(&A.st->flags, NGS_FLAG_STALL); b = NGS_ST_INC << 62; }
-			}
+			} else if (idx == -1 && A.prev) b = ld_relaxed_u64(A.prev);   /* ... or the carry of the launch that finalized the tiles before */
 			const unsigned int im = __ballot_sync(full, (b >> 62) == NGS_ST_INC);
 			if (lane == 0) s_lb_inc[warp] = im ? (unsigned)(warp * 32 + __ffs(im) - 1) : 0xffffffffu;
 			__syncthreads();
