@@ -101,6 +101,9 @@ struct ngscov {
 	size_t bed_begin;                        /* halo: bytes of the dropped first line */
 	std::string bed_tail; size_t bed_tail_old; /* halo: replacement of the last line, and how many bytes it replaces */
 	bool bed_patched;
+	/* NGSCOV_MODE_SLIDE (bam_sliding_count) */
+	bool slide; unsigned int *d_sl_cnt, *d_sl_len, *d_sl_ctg; unsigned long long *d_sl_gc, *d_sl_ncount; uint32_t *d_sl_nwin;
+	std::string slide_text; unsigned long long slide_ncount;
 	long long *d_halo;                       /* the shard's running halo record (device), see k_halo_gather */
 	unsigned long long *d_patch, *h_patch;   /* device-side stitch: [0] first byte, [1] end of the shard's bedGraph text */
 	bool dev_stitched;
@@ -225,7 +228,8 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 {
 	if (!out || !cfg || cfg->n_ref < 0 || (cfg->n_ref && (!cfg->ref_len || !cfg->ref_name))) return NGSCOV_EINVAL;
 	if (cfg->window < 1 || cfg->window > (1u << 30)) return NGSCOV_EINVAL;
-	if (cfg->mode != NGSCOV_MODE_DEPTH && cfg->mode != NGSCOV_MODE_WIG) return NGSCOV_EINVAL;
+	if (cfg->mode != NGSCOV_MODE_DEPTH && cfg->mode != NGSCOV_MODE_WIG && cfg->mode != NGSCOV_MODE_SLIDE) return NGSCOV_EINVAL;
+	if (cfg->mode == NGSCOV_MODE_SLIDE && (cfg->slice_end || cfg->window > 0x7fffffffu)) return NGSCOV_EINVAL;
 	if (cfg->slice_end && cfg->slice_end <= cfg->slice_beg) return NGSCOV_EINVAL;
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) return NGSCOV_ECUDA;
@@ -328,6 +332,17 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	/* streamed per-contig finalize: the cover pipeline also streams region shards (their halo only patches the first and
 	 * last line afterwards); the classic kernels need the whole shard before the halo is known */
 	h->stream_fin = (cfg->slice_end == 0 || h->cover) && !(getenv("NGSCOV_STREAM_FINALIZE") && atoi(getenv("NGSCOV_STREAM_FINALIZE")) == 0);
+	h->slide = cfg->mode == NGSCOV_MODE_SLIDE;
+	if (h->slide) {
+		if (!h->cover) return NGSCOV_EINVAL;                              /* the table pipeline only */
+		h->stream_fin = false;
+		const size_t nb = std::max<uint64_t>(1, h->n_bins);
+		CK(cudaMalloc((void **)&h->d_sl_cnt, nb * 4)); CK(cudaMalloc((void **)&h->d_sl_len, nb * 4)); CK(cudaMalloc((void **)&h->d_sl_gc, nb * 8));
+		CK(cudaMalloc((void **)&h->d_sl_ctg, ((size_t)h->n_ref + 1) * 4)); CK(cudaMalloc((void **)&h->d_sl_ncount, 8));
+		std::vector<uint32_t> nw((size_t)h->n_ref + 1, 0);
+		for (int i = 0; i < h->n_ref; ++i) nw[i] = h->ref_len[i] / h->cfg.window + 1;
+		CKC(dev_upload(h, &h->d_sl_nwin, nw));
+	}
 	if (h->cover) {
 		const size_t nt = std::max<uint64_t>(1, h->n_tiles) * NGS_CPT;      /* owner tiles */
 		CK(cudaMalloc((void **)&h->d_far_flag, nt * 4)); CK(cudaMemset(h->d_far_flag, 0, nt * 4));
@@ -355,7 +370,8 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	                h->d_name_off, h->d_wighdr, h->d_wighdr_off, h->d_chunk[0], h->d_chunk[1], h->d_carry, h->d_entry, h->d_exit,
 	                h->d_bmax, h->d_count, h->d_slots, h->d_ctr, h->d_st, h->d_run_start, h->d_run_end, h->d_run_depth, h->d_rec_base, h->d_stA, h->d_stB,
 	                h->d_fmt_status, h->d_text[0], h->d_text[1], h->d_text[2], h->d_text[3],
-	                h->d_ent, h->d_rows, h->d_rkmax, h->d_kbmax, h->d_far_flag, h->d_row_a, h->d_row_b, h->d_stF, h->d_stC, h->d_tile_first, h->d_tile_last, h->d_halo, h->d_patch };
+	                h->d_ent, h->d_rows, h->d_rkmax, h->d_kbmax, h->d_far_flag, h->d_row_a, h->d_row_b, h->d_stF, h->d_stC, h->d_tile_first, h->d_tile_last, h->d_halo, h->d_patch,
+	                h->d_sl_cnt, h->d_sl_len, h->d_sl_gc, h->d_sl_ctg, h->d_sl_ncount, h->d_sl_nwin };
 	for (void *p : dev) if (p) cudaFree(p);
 	for (int i = 0; i < 2; ++i) if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
 	for (int i = 0; i < 4; ++i) if (h->h_text[i]) cudaFreeHost(h->h_text[i]);
@@ -413,6 +429,13 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	h->rows_used = 0; h->red_mode = false; h->halo_have = false; h->fin_tile = 0;
 	h->bed_begin = 0; h->bed_tail.clear(); h->bed_tail_old = 0; h->bed_patched = false; h->dev_stitched = false;
 	if (h->d_halo) { CK(cudaMemsetAsync(h->d_halo, 0, 9 * 8, h->s_main)); CK(cudaStreamSynchronize(h->s_main)); }
+	if (h->slide) {
+		const size_t nb = std::max<uint64_t>(1, h->n_bins);
+		CK(cudaMemsetAsync(h->d_sl_cnt, 0, nb * 4, h->s_main)); CK(cudaMemsetAsync(h->d_sl_len, 0, nb * 4, h->s_main)); CK(cudaMemsetAsync(h->d_sl_gc, 0, nb * 8, h->s_main));
+		CK(cudaMemsetAsync(h->d_sl_ctg, 0, ((size_t)h->n_ref + 1) * 4, h->s_main)); CK(cudaMemsetAsync(h->d_sl_ncount, 0, 8, h->s_main));
+		CK(cudaStreamSynchronize(h->s_main));
+		h->slide_text.clear(); h->slide_ncount = 0;
+	}
 	return 0;
 }
 
@@ -555,6 +578,15 @@ static int launch_special(ngscov *h, const IngestArgs &A, int mode)
 {
 	/* a warp takes 32 rows per step */
 	const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((A.n_sub + 255) / 256, (int64_t)h->sm_count * 8));
+	if (h->slide) {
+		SlideArgs S;
+		S.cnt = h->d_sl_cnt; S.len = h->d_sl_len; S.gc = h->d_sl_gc; S.ctg_reads = h->d_sl_ctg; S.win_base = h->d_win_base; S.n_win = h->d_sl_nwin;
+		S.window = (int)h->cfg.window; S.n_count = h->d_sl_ncount;
+		k_slide_accumulate<<<grid, 256, 0, h->s_main>>>(A, S);
+		h->stats.launches += 1;
+		CK(cudaGetLastError());
+		return 0;
+	}
 	k_special_reds<<<grid, 256, 0, h->s_main>>>(A, mode);
 	h->stats.launches += 1;
 	CK(cudaGetLastError());
@@ -574,7 +606,8 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 		const unsigned long long key = h->h_st->first_bad_key;
 		if ((key & 1) || iter > 100000) { h->sticky_err = NGSCOV_EFORMAT; h->pending = false; return NGSCOV_EFORMAT; }
 		IngestArgs A = make_ingest_args(h, h->p_base, h->p_n, h->p_nsub, h->p_from_state, h->p_fixed0);
-		if (h->cover) k_repair_classify<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
+		if (h->cover && h->slide) k_repair_classify<true><<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
+		else if (h->cover) k_repair_classify<false><<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
 		else if (h->fused) k_repair<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
 		else k_repair_chain<<<1, 32, 0, h->s_main>>>(A, (long long)(key >> 1), h->d_bmax);
 		h->stats.launches += 1;
@@ -591,7 +624,7 @@ static int resolve_pending(ngscov *h, bool allow_stream = false)
 		}
 		h->p_k2_done = true;
 	}
-	if (h->cover && h->h_st->unsorted && !h->red_mode) {
+	if (h->cover && h->h_st->unsorted && !h->red_mode && !h->slide) {
 		/* the input is not coordinate sorted: the owner tiles cannot find their records by key.  Everything pushed so far
 		 * already had its rare deltas added to the global array; add the ordinary ones too (needs only the table) and go
 		 * on with REDs + the classic scan.  Contigs that were already finalized cannot be taken back. */
@@ -651,7 +684,8 @@ static int submit_chunk(ngscov *h, const uint8_t *base, int64_t n, bool from_sta
 	CK(cudaEventRecord(next_event(h->ev_ing, h->n_ing), h->s_main));
 	if (h->cover) {
 		/* K1: frame AND classify (speculative chain walk, one 8-byte table entry per contributing record) */
-		k_chain_classify<<<(unsigned)((n_sub + 255) / 256), 256, 0, h->s_main>>>(A);
+		if (h->slide) k_chain_classify<true><<<(unsigned)((n_sub + 255) / 256), 256, 0, h->s_main>>>(A);
+		else k_chain_classify<false><<<(unsigned)((n_sub + 255) / 256), 256, 0, h->s_main>>>(A);
 		h->rows_used += (size_t)n_sub;
 	} else if (!h->fused) {
 		/* K1: frame the records (speculative chain walk, no atomics, full occupancy) */
@@ -1005,6 +1039,76 @@ static int stream_finalize_impl(ngscov *h, size_t seg_end)
 	return 0;
 }
 
+/* bam_sliding_count: the per-window sums come back (a few MB), calc_winGC (bam_sliding_count.c:126-138) and
+ * output_count_GC (:140-165) run on the host in the reference's own types -- float arithmetic included -- over
+ * O(windows) values. */
+static int slide_finish(ngscov *h)
+{
+	const size_t nb = (size_t)h->n_bins;
+	std::vector<unsigned int> cnt(nb + 1), len(nb + 1), ctg((size_t)h->n_ref + 1);
+	std::vector<unsigned long long> gc(nb + 1);
+	CK(cudaMemcpyAsync(cnt.data(), h->d_sl_cnt, nb * 4, cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaMemcpyAsync(len.data(), h->d_sl_len, nb * 4, cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaMemcpyAsync(gc.data(), h->d_sl_gc, nb * 8, cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaMemcpyAsync(ctg.data(), h->d_sl_ctg, (size_t)h->n_ref * 4, cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaMemcpyAsync(&h->slide_ncount, h->d_sl_ncount, 8, cudaMemcpyDeviceToHost, h->s_main));
+	CK(cudaStreamSynchronize(h->s_main));
+	std::vector<float> GC(nb + 1);
+	/* the reference adds the per-read counts in a float, in file order: exact below 2^24, otherwise redone its way */
+	std::vector<uint32_t> redo;
+	for (size_t k = 0; k < nb; ++k) { GC[k] = (float)gc[k]; if (gc[k] >= (1ull << 24)) redo.push_back((uint32_t)k); }
+	if (!redo.empty()) {
+		if (h->h_st->unsorted) return h->sticky_err = NGSCOV_EUNSORTED;            /* file order is not table order */
+		for (uint32_t k : redo) {
+			const size_t c = std::upper_bound(h->win_base.begin(), h->win_base.begin() + h->n_ref, (uint64_t)k) - h->win_base.begin() - 1;
+			if (h->ref_len[c] / h->cfg.window + 1 > 65536u) return h->sticky_err = NGSCOV_ERANGE;   /* window index wraps in the reference's unsigned short */
+		}
+		uint32_t *d_list = nullptr; float *d_out = nullptr; unsigned int *d_err = nullptr;
+		CK(cudaMalloc((void **)&d_list, redo.size() * 4)); CK(cudaMalloc((void **)&d_out, redo.size() * 4)); CK(cudaMalloc((void **)&d_err, 4));
+		CK(cudaMemcpyAsync(d_list, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, h->s_main));
+		CK(cudaMemsetAsync(d_err, 0, 4, h->s_main));
+		k_slide_seqfloat<<<(unsigned)((redo.size() + 63) / 64), 64, 0, h->s_main>>>(d_list, (uint32_t)redo.size(), h->d_ent, h->d_rows, h->d_rkmax, (uint32_t)h->rows_used,
+		                                                                       h->d_win_base, (uint32_t)h->n_ref, (int)h->cfg.window, d_out, d_err);
+		h->stats.launches += 1;
+		std::vector<float> out(redo.size()); unsigned int err = 0;
+		CK(cudaMemcpyAsync(out.data(), d_out, redo.size() * 4, cudaMemcpyDeviceToHost, h->s_main));
+		CK(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, h->s_main));
+		CK(cudaStreamSynchronize(h->s_main));
+		cudaFree(d_list); cudaFree(d_out); cudaFree(d_err);
+		if (err) return h->sticky_err = NGSCOV_ERANGE;
+		for (size_t i = 0; i < redo.size(); ++i) GC[redo[i]] = out[i];
+	}
+	const int window = (int)h->cfg.window;
+	std::string &t = h->slide_text;
+	t.clear();
+	char buf[512];
+	t += "#chr\tchr_len\tchr_sum_read_count\tchr_sum_base\tchr_mean_cov\tchr_mean_GC%";
+	uint32_t max_len = 0;
+	for (unsigned short i = 0; i < h->n_ref; ++i) max_len = h->ref_len[i] > max_len ? h->ref_len[i] : max_len;      /* max(), :198-205 */
+	const uint32_t max_target_window = max_len / window + 1;
+	for (uint32_t k = 0; k < max_target_window; ++k) { snprintf(buf, sizeof buf, "\t%u\tcount\tGC%%", k + 1); t += buf; }
+	t += "\n";
+	for (int j = 0; j < h->n_ref; ++j) {
+		if (ctg[j] == 0) continue;                                  /* windows[j] == 0: no mapped read on this contig */
+		const uint32_t windows = (unsigned int)h->ref_len[j] / window + 1;
+		const size_t b0 = (size_t)h->win_base[j];
+		unsigned int sum_count = 0; unsigned long sum_base = 0; float sum_GC = 0;
+		for (uint32_t k = 0; k < windows; ++k) {                    /* calc_winGC */
+			sum_count += cnt[b0 + k];
+			sum_GC += GC[b0 + k];
+			sum_base += len[b0 + k];
+			GC[b0 + k] = GC[b0 + k] != 0 ? GC[b0 + k] / len[b0 + k] * 100 : GC[b0 + k];
+		}
+		sum_GC = sum_GC / sum_base * 100;
+		snprintf(buf, sizeof buf, "%s\t%d\t%u\t%lu\t%f\t%f", h->ref_name[j].c_str(), h->ref_len[j], sum_count, sum_base, (double)sum_base / h->ref_len[j], sum_GC);
+		t += buf;
+		for (uint32_t k = 0; k < windows; ++k) { snprintf(buf, sizeof buf, "\t%d\t%u\t%f", k + 1, cnt[b0 + k], GC[b0 + k]); t += buf; }
+		t += "\n";
+	}
+	h->stats.out_bytes[0] = t.size();
+	return 0;
+}
+
 extern "C" int ngscov_finish_runs(ngscov_t *h)
 {
 	if (!h) return NGSCOV_EINVAL;
@@ -1041,6 +1145,11 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 	if ((st.entry_next != 0 || st.carry_len != 0) && !(h->last_flags & NGSCOV_PUSH_TRUNCATED_OK)) return h->sticky_err = NGSCOV_EFORMAT;
 	if (st.flags & NGS_FLAG_ERANGE) return h->sticky_err = NGSCOV_ERANGE;
 
+	if (h->slide) {
+		if ((r = slide_finish(h))) return r;
+		h->diff_dirty = false; h->runs_done = true;
+		return 0;
+	}
 	if (h->cover && !h->red_mode) {
 		if (!h->seg.empty() && h->fin_tile < h->n_tiles * NGS_CPT && (r = cover_tiles(h, h->fin_tile, h->n_tiles * NGS_CPT, st.m_ops - h->mops_fin))) return r;
 		if (h->cfg.mode == NGSCOV_MODE_DEPTH) { h->text_ready[NGSCOV_OUT_BEDGRAPH] = true; h->text_len[NGSCOV_OUT_BEDGRAPH] = h->bed_off; }
@@ -1486,6 +1595,7 @@ extern "C" int ngscov_format(ngscov_t *h, uint32_t which_mask)
 {
 	if (!h) return NGSCOV_EINVAL;
 	if (!h->runs_done) return NGSCOV_ESTATE;
+	if (h->slide) { h->formatted = true; return 0; }
 	CK(cudaSetDevice(h->device));
 	int r = 0;
 	NameTable nt = { h->d_names, h->d_name_off, h->d_name8 };
@@ -1528,6 +1638,7 @@ extern "C" int ngscov_finish(ngscov_t *h)
 	int r = ngscov_finish_runs(h);
 	if (r) return r;
 	uint32_t mask;
+	if (h->slide) return ngscov_format(h, 1u << NGSCOV_OUT_SLIDE);
 	if (h->cfg.mode == NGSCOV_MODE_DEPTH) {
 		mask = (1u << NGSCOV_OUT_BEDGRAPH) | (1u << NGSCOV_OUT_DEPTH);
 		if (h->cfg.emit_wig) mask |= (1u << NGSCOV_OUT_WIG) | (1u << NGSCOV_OUT_CHROMSIZE);
@@ -1565,6 +1676,11 @@ extern "C" int ngscov_output_device(ngscov_t *h, int which, const void **dev_buf
 
 extern "C" int ngscov_output(ngscov_t *h, int which, const char **buf, size_t *len)
 {
+	if (h && which == NGSCOV_OUT_SLIDE && buf && len) {
+		if (!h->slide || !h->runs_done) return NGSCOV_ESTATE;
+		*buf = h->slide_text.data(); *len = h->slide_text.size();
+		return 0;
+	}
 	if (!h || which < 0 || which > 3 || !buf || !len) return NGSCOV_EINVAL;
 	if (!h->text_ready[which]) return NGSCOV_ESTATE;
 	if (which == NGSCOV_OUT_CHROMSIZE) { *buf = h->chromsize.data(); *len = h->chromsize.size(); return 0; }

@@ -38,8 +38,44 @@ struct CigReader {
 	__device__ __forceinline__ uint32_t operator()(uint32_t i) const { return mem.u32(co + 4ll * i); }
 };
 
-/* walk + classify the records starting in [entry, hi): entries -> row[], metadata -> m */
+/* ---- bam_sliding_count (reference bam_sliding_count.c:84-124) --------------------------------
+ * The same table and the same verification serve a second tool: per window the number of mapped reads STARTING in it,
+ * the sum of their l_qseq and the number of C / G bases in their SEQ.  An entry is x = POS | contig-delta << 29,
+ * y = GC count (16 bits, the reference's unsigned short) << 16 | l_qseq (16 bits).  Records that do not fit (l_qseq >=
+ * 65535, POS < 0, more than seven contigs in a row) flag their row for the sequential path of k_slide_accumulate. */
 template <class Mem>
+__device__ __forceinline__ uint32_t ngs_seq_gc(const Mem &mem, int64_t so, int32_t l_seq)
+{
+	/* 4-bit codes, two per byte (bam1_seqi): count the nibbles equal to 2 (C) or 4 (G), eight per 32-bit word */
+	uint32_t gc = 0;
+	const int64_t nb = ((int64_t)l_seq + 1) >> 1;
+	for (int64_t i = 0; i < nb; i += 4) {
+		uint32_t w = mem.u32(so + i);
+		const int64_t left = nb - i;
+		if (left < 4) w &= (1u << (8 * (uint32_t)left)) - 1u;      /* bytes past the sequence: code 0, never counted */
+		uint32_t a = w ^ 0x22222222u, b = w ^ 0x44444444u;          /* a nibble is zero where the code is 2 / 4 */
+		a |= a >> 1; a |= a >> 2; b |= b >> 1; b |= b >> 2;
+		gc += 16u - (uint32_t)__popc(a & 0x11111111u) - (uint32_t)__popc(b & 0x11111111u);
+	}
+	return gc;
+}
+/* returns 1 = entry y, 2 = record needs the sequential path, 0 = dropped (tid < 0 or BAM_FUNMAP, :96-97) */
+template <class Mem, class Cnt>
+__device__ __forceinline__ int ngs_slide_record(const Mem &mem, int64_t o, const ngs_hdr &h, uint32_t &y, Cnt &cnt)
+{
+	cnt.records += 1; cnt.cigar_words += h.n_cigar;
+	const uint32_t r1 = (uint32_t)(h.ref_id + 1);
+	if (r1 > cnt.max_ref_p1) cnt.max_ref_p1 = r1;
+	if (h.ref_id < 0 || (h.flag & 4u)) return 0;
+	cnt.kept += 1;
+	if (h.pos < 0 || h.l_seq >= 0xFFFF) return 2;
+	const uint32_t gc = ngs_seq_gc(mem, o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar, h.l_seq) & 0xFFFFu;
+	y = (gc << 16) | (uint32_t)h.l_seq;
+	return 1;
+}
+
+/* walk + classify the records starting in [entry, hi): entries -> row[], metadata -> m */
+template <bool SLIDE, class Mem>
 __device__ __forceinline__ long long chain_classify(const ngs_walk_cfg &cfg, const Mem &mem, long long entry, int64_t hi,
                                                     uint2 *row, ngs_row &m)
 {
@@ -56,7 +92,7 @@ __device__ __forceinline__ long long chain_classify(const ngs_walk_cfg &cfg, con
 		mem.hdr_lite(o, h);
 		for (;;) {
 			if (!ngs_hdr_valid(h, cfg.n_ref)) { result = NGS_EXIT_INVALID; break; }
-			if (o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar > n) { result = NGS_EXIT_PARTIAL(o); break; }
+			if (o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar + (SLIDE ? ((int64_t)h.l_seq + 1) / 2 : 0) > n) { result = NGS_EXIT_PARTIAL(o); break; }
 			/* the next header is requested before this record is classified: the chain of dependent loads stays as
 			 * short as in the framing-only walk, the CIGAR loads ride along */
 			const int64_t nx = o + 4 + (int64_t)h.block_size;
@@ -67,12 +103,18 @@ __device__ __forceinline__ long long chain_classify(const ngs_walk_cfg &cfg, con
 			if (fk == NGS_KEY_NONE) fk = key;
 			if (key < prev) special |= NGS_ROW_UNSORTED;
 			prev = key;
-			uint32_t y; int sp = 0;
+			uint32_t y = 0; int sp = 0;
 			CigReader<Mem> cig = { mem, o + 36 + (int64_t)h.l_qname };
-			if (ngs_classify_record(cfg, h, (uint32_t)(o - entry), cig, y, sp, cnt)) {
+			int got;
+			if (SLIDE) { got = ngs_slide_record(mem, o, h, y, cnt); if (got == 2) { special |= NGS_ROW_OVERFLOW; got = 0; } }
+			else got = ngs_classify_record(cfg, h, (uint32_t)(o - entry), cig, y, sp, cnt);
+			if (got) {
 				if (ctg0 < 0) ctg0 = h.ref_id;
 				uint32_t cd = (uint32_t)(h.ref_id - ctg0);
-				if (cd > NGS_ENT_CDELTA_MAX) { cd = 7u; y = (NGS_ENT_CHAIN << 30) | (uint32_t)(o - entry); sp = 1; }
+				if (cd > NGS_ENT_CDELTA_MAX) {
+					if (SLIDE) special |= NGS_ROW_OVERFLOW;
+					else { cd = 7u; y = (NGS_ENT_CHAIN << 30) | (uint32_t)(o - entry); sp = 1; }
+				}
 				if (count < NGS_ROW_SLOTS) row[count] = make_uint2((uint32_t)h.pos | (cd << 29), y);
 				++count; special += (uint32_t)sp;
 			}
@@ -81,7 +123,7 @@ __device__ __forceinline__ long long chain_classify(const ngs_walk_cfg &cfg, con
 			h = hn; o = nx;
 		}
 	}
-	if (count > NGS_ROW_SLOTS) { count = 0; special = (special & NGS_ROW_UNSORTED) | NGS_ROW_OVERFLOW; }
+	if (count > NGS_ROW_SLOTS || (special & NGS_ROW_OVERFLOW)) { count = 0; special = (special & NGS_ROW_UNSORTED) | NGS_ROW_OVERFLOW; }
 	m.fk = fk; m.lk = prev; m.count = count; m.special = special; m.ctg = ctg0;
 	m.nrec = cnt.records; m.nkept = cnt.kept; m.nmops = cnt.m_ops; m.ncig = cnt.cigar_words; m.max_ref_p1 = cnt.max_ref_p1;
 	m.pad0 = 0; m.pad1 = 0;
@@ -109,6 +151,7 @@ __device__ __forceinline__ void store_row(ngs_row *dst, const ngs_row &m)
  * Written straight from the lanes (8 bytes per lane into 32 different rows per store) the entries cost 4.1 of the
  * kernel's 12.9 ms on the 30x workload (618 M partial-sector write transactions; 8.8 ms with the stores removed, 5.9 ms
  * for framing alone): staged, the kernel takes 11.3 ms. */
+template <bool SLIDE>
 __global__ void __launch_bounds__(256, NGS_K1_MINB) k_chain_classify(const __grid_constant__ IngestArgs A)
 {
 	__shared__ uint2 s_buf[8][32][NGS_K1_BUF + 1];           /* + 1: lanes hit different banks */
@@ -167,7 +210,7 @@ __global__ void __launch_bounds__(256, NGS_K1_MINB) k_chain_classify(const __gri
 	while (__any_sync(full, active)) {
 		if (active) {
 			if (!ngs_hdr_valid(h, A.cfg.n_ref)) { result = NGS_EXIT_INVALID; active = false; }
-			else if (o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar > n) { result = NGS_EXIT_PARTIAL(o); active = false; }
+			else if (o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar + (SLIDE ? ((int64_t)h.l_seq + 1) / 2 : 0) > n) { result = NGS_EXIT_PARTIAL(o); active = false; }
 			else {
 				/* the next header is requested before this record is classified: the chain of dependent loads stays as
 				 * short as in a framing-only walk, the CIGAR loads ride along */
@@ -179,12 +222,18 @@ __global__ void __launch_bounds__(256, NGS_K1_MINB) k_chain_classify(const __gri
 				if (fk == NGS_KEY_NONE) fk = key;
 				if (key < prev) special |= NGS_ROW_UNSORTED;
 				prev = key;
-				uint32_t y; int sp = 0;
+				uint32_t y = 0; int sp = 0;
 				CigReader<DevMem> cig = { mem, o + 36 + (int64_t)h.l_qname };
-				if (ngs_classify_record(A.cfg, h, (uint32_t)(o - entry), cig, y, sp, cnt)) {
+				int got;
+				if (SLIDE) { got = ngs_slide_record(mem, o, h, y, cnt); if (got == 2) { special |= NGS_ROW_OVERFLOW; got = 0; } }
+				else got = ngs_classify_record(A.cfg, h, (uint32_t)(o - entry), cig, y, sp, cnt);
+				if (got) {
 					if (ctg0 < 0) ctg0 = h.ref_id;
 					uint32_t cd = (uint32_t)(h.ref_id - ctg0);
-					if (cd > NGS_ENT_CDELTA_MAX) { cd = 7u; y = (NGS_ENT_CHAIN << 30) | (uint32_t)(o - entry); sp = 1; }
+					if (cd > NGS_ENT_CDELTA_MAX) {
+						if (SLIDE) special |= NGS_ROW_OVERFLOW;
+						else { cd = 7u; y = (NGS_ENT_CHAIN << 30) | (uint32_t)(o - entry); sp = 1; }
+					}
 					s_buf[warp][lane][nbuf++] = make_uint2((uint32_t)h.pos | (cd << 29), y);
 					++count; special += (uint32_t)sp;
 				}
@@ -196,7 +245,7 @@ __global__ void __launch_bounds__(256, NGS_K1_MINB) k_chain_classify(const __gri
 		if (++it == NGS_K1_BUF) { flush(); it = 0; }
 	}
 	flush();
-	if (count > NGS_ROW_SLOTS) { count = 0; special = (special & NGS_ROW_UNSORTED) | NGS_ROW_OVERFLOW; }
+	if (count > NGS_ROW_SLOTS || (special & NGS_ROW_OVERFLOW)) { count = 0; special = (special & NGS_ROW_UNSORTED) | NGS_ROW_OVERFLOW; }
 	ngs_row m;
 	m.fk = fk; m.lk = prev; m.count = count; m.special = special; m.ctg = ctg0;
 	m.nrec = cnt.records; m.nkept = cnt.kept; m.nmops = cnt.m_ops; m.ncig = cnt.cigar_words; m.max_ref_p1 = cnt.max_ref_p1;
@@ -208,6 +257,7 @@ __global__ void __launch_bounds__(256, NGS_K1_MINB) k_chain_classify(const __gri
 
 /* Rare path, single thread: zip the true chain forward from the first mismatching sub-chunk until it meets an
  * already-framed entry, rewriting entry / exit / row on the way (k_repair_chain for the table) */
+template <bool SLIDE>
 __global__ void k_repair_classify(IngestArgs A, long long first_bad, const long long *bexcl)
 {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -230,7 +280,7 @@ __global__ void k_repair_classify(IngestArgs A, long long first_bad, const long 
 		if (A.entry[cc] == cur) break;                  /* converged */
 		long long hi = (cc + 1) << A.shift; if (hi > A.n) hi = A.n;
 		ngs_row m;
-		const long long x = chain_classify(A.cfg, mem, cur, hi, A.ent + (size_t)cc * NGS_ROW_SLOTS, m);
+		const long long x = chain_classify<SLIDE>(A.cfg, mem, cur, hi, A.ent + (size_t)cc * NGS_ROW_SLOTS, m);
 		A.entry[cc] = cur; A.exit[cc] = x; A.rows[cc] = m; ++repaired;
 		c = cc + 1;
 		cur = (x == NGS_EXIT_INVALID || x >= NGS_EXIT_INF) ? A.n : x;
@@ -1016,6 +1066,130 @@ __global__ void __launch_bounds__(NGS_COVER_THREADS, NGS_COVER_MINB) k_cover(con
 			atomicMin(&A.st->first_tile, (unsigned long long)tile_g); atomicMax(&A.st->last_tile_p1, (unsigned long long)tile_g + 1);
 		}
 	}
+}
+
+/* ---- bam_sliding_count: accumulation from the verified table ---------------------------------------------------- */
+struct SlideArgs {
+	unsigned int *cnt, *len;             /* [n_bins] reads starting in the window, sum of l_qseq (the reference's unsigned int: wraps) */
+	unsigned long long *gc;              /* [n_bins] sum of the per-read GC counts, exact integer */
+	unsigned int *ctg_reads;             /* [n_ref] mapped reads seen per contig (the reference allocates a contig's windows on its first read) */
+	const unsigned long long *win_base;  /* [n_ref + 1] */
+	const uint32_t *n_win;               /* [n_ref] target_len / window + 1 */
+	int window;
+	unsigned long long *n_count;
+};
+__device__ __forceinline__ void slide_add(const SlideArgs &S, uint32_t ctg, int32_t pos, uint32_t gc, uint32_t lq)
+{
+	atomicAdd(&S.ctg_reads[ctg], 1u);
+	const uint32_t w = (uint32_t)(unsigned short)(pos / S.window);            /* (unsigned short)(c->pos / window), :116 */
+	if (w >= S.n_win[ctg]) return;                                             /* the reference writes out of bounds (POS beyond the contig) */
+	const unsigned long long k = S.win_base[ctg] + w;
+	atomicAdd(&S.cnt[k], 1u); atomicAdd(&S.len[k], lq); atomicAdd(&S.gc[k], (unsigned long long)gc);
+}
+__global__ void __launch_bounds__(256) k_slide_accumulate(const __grid_constant__ IngestArgs A, const __grid_constant__ SlideArgs S)
+{
+	const unsigned full = 0xffffffffu;
+	{
+		const ngs_dev_state *st = A.st;
+		if (st->n_bad != 0 || (st->flags & NGS_FLAG_EFORMAT)) return;      /* launched optimistically behind the verification */
+	}
+	const int lane = threadIdx.x & 31;
+	const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5, wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	DevMem mem = { A.base, A.n };
+	unsigned int s_rec = 0, s_kept = 0, s_cig = 0, s_max = 0;
+	unsigned long long n_count = 0;
+	for (int64_t base = 0; base < A.n_sub; base += n_warps * 32) {
+		const int64_t c = base + (int64_t)lane * n_warps + wid;
+		uint4 b = make_uint4(0, 0, 0xffffffffu, 0), d = make_uint4(0, 0, 0, 0);
+		if (c < A.n_sub) { b = reinterpret_cast<const uint4 *>(A.rows + c)[1]; d = reinterpret_cast<const uint4 *>(A.rows + c)[2]; }
+		s_rec += b.w; s_kept += d.x; s_cig += d.z; s_max = d.w > s_max ? d.w : s_max;
+		unsigned todo = __ballot_sync(full, b.x != 0 || (b.y & NGS_ROW_OVERFLOW));
+		while (todo) {
+			const int src = __ffs(todo) - 1; todo &= todo - 1;
+			const unsigned int count = __shfl_sync(full, b.x, src), special = __shfl_sync(full, b.y, src);
+			const int ctg0 = (int)__shfl_sync(full, b.z, src);
+			const int64_t row = base + (int64_t)src * n_warps + wid;
+			if (special & NGS_ROW_OVERFLOW) {
+				if (lane == 0) {                      /* a record that does not fit an entry: the row is walked again, record by record */
+					long long hi = (row + 1) << A.shift; if (hi > A.n) hi = A.n;
+					int64_t o = A.entry[row];
+					while (o < hi) {
+						ngs_hdr h; mem.hdr_lite(o, h);
+						if (h.ref_id >= 0 && !(h.flag & 4u)) {
+							const uint32_t gc = ngs_seq_gc(mem, o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar, h.l_seq) & 0xFFFFu;
+							slide_add(S, (uint32_t)h.ref_id, h.pos, gc, (uint32_t)h.l_seq);
+							++n_count;
+						}
+						o += 4 + (int64_t)h.block_size;
+					}
+				}
+				continue;
+			}
+			for (unsigned int k0 = 0; k0 < count; k0 += 32) {
+				const unsigned int k = k0 + lane;
+				const bool on = k < count;
+				uint2 e = make_uint2(0, 0);
+				if (on) e = A.ent[(size_t)row * NGS_ROW_SLOTS + k];
+				const uint32_t ctg = (uint32_t)(ctg0 + (int)(e.x >> 29)), pos = e.x & 0x1FFFFFFFu;
+				const uint32_t w = (uint32_t)(unsigned short)((int32_t)pos / S.window);
+				/* sorted input: the lanes of a warp mostly share one window -- one atomic per distinct window and field */
+				const unsigned long long key = on ? (((unsigned long long)ctg << 32) | w) : ~0ull;
+				const unsigned grp = __match_any_sync(full, key);
+				const unsigned int gl = __reduce_add_sync(grp, on ? (e.y & 0xFFFFu) : 0u), gg = __reduce_add_sync(grp, on ? (e.y >> 16) : 0u);
+				if (on && lane == __ffs(grp) - 1) {
+					const unsigned int nrd = (unsigned int)__popc(grp);
+					atomicAdd(&S.ctg_reads[ctg], nrd);
+					if (w < S.n_win[ctg]) {
+						const unsigned long long kk = S.win_base[ctg] + w;
+						atomicAdd(&S.cnt[kk], nrd); atomicAdd(&S.len[kk], gl); atomicAdd(&S.gc[kk], (unsigned long long)gg);
+					}
+					n_count += nrd;
+				}
+			}
+		}
+	}
+	const unsigned v0 = __reduce_add_sync(full, s_rec), v1 = __reduce_add_sync(full, s_kept), v3 = __reduce_add_sync(full, s_cig), v4 = __reduce_max_sync(full, s_max);
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) n_count += __shfl_xor_sync(full, n_count, o);
+	if (lane == 0 && v0) {
+		unsigned long long *c4 = A.ctr + (size_t)(wid % NGS_CTR_STRIPES) * 16;
+		atomicAdd(c4 + 0, (unsigned long long)v0);
+		if (v1) atomicAdd(c4 + 1, (unsigned long long)v1);
+		if (v3) atomicAdd(c4 + 3, (unsigned long long)v3);
+		if (v4 > A.st->max_ref_p1) atomicMax(&A.st->max_ref_p1, v4);
+		if (n_count) atomicAdd(S.n_count, n_count);
+	}
+}
+
+/* The reference accumulates the GC count of a window in a FLOAT, read after read in file order (:120): exact while the
+ * sum stays below 2^24, order dependent beyond.  Windows whose exact integer sum reaches 2^24 are redone here the
+ * reference's way: one thread per window walks the window's table entries in file order and adds in float. */
+__global__ void k_slide_seqfloat(const uint32_t *list, uint32_t n_list, const uint2 *ent, const ngs_row *rows, const unsigned long long *rkmax, uint32_t n_rows,
+                                 const unsigned long long *win_base, uint32_t n_ref, int window, float *out, unsigned int *err)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_list) return;
+	const uint32_t bin = list[i];
+	uint32_t lo = 0, hi = n_ref;                        /* contig of the bin */
+	while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (win_base[mid] <= bin) lo = mid; else hi = mid; }
+	const uint32_t ctg = lo, w = bin - (uint32_t)win_base[ctg];
+	const unsigned long long p0 = (unsigned long long)w * (unsigned)window, p1 = p0 + (unsigned)window;
+	const unsigned long long ka = ((unsigned long long)ctg << 32) | (p0 + 1), kb = ((unsigned long long)ctg << 32) | (p1 + 1);
+	uint32_t a = 0, b = n_rows;
+	while (a < b) { const uint32_t mid = (a + b) >> 1; if (rkmax[mid] < ka) a = mid + 1; else b = mid; }
+	float f = 0.0f;
+	for (uint32_t r = a; r < n_rows; ++r) {
+		const ngs_row &rw = rows[r];
+		if (rw.special & NGS_ROW_OVERFLOW) { atomicOr(err, 1u); break; }     /* records outside the table: cannot be replayed in order */
+		for (uint32_t k = 0; k < rw.count; ++k) {
+			const uint2 e = ent[(size_t)r * NGS_ROW_SLOTS + k];
+			if ((uint32_t)(rw.ctg + (int)(e.x >> 29)) != ctg) continue;
+			const uint32_t pos = e.x & 0x1FFFFFFFu;
+			if (pos >= p0 && pos < p1) f += (float)(e.y >> 16);
+		}
+		if (rkmax[r] >= kb) break;
+	}
+	out[i] = f;
 }
 
 /* after a cover launch: the halo candidates of the first / last tile that produced a run -> the state block, and the

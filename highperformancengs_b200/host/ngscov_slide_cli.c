@@ -1,0 +1,132 @@
+/* host/ngscov_slide_cli.c -- the drop-in bam_sliding_count command line on top of libngscov_cuda (NGSCOV_MODE_SLIDE).
+ *
+ * Kept from the reference main (reference bam_sliding_count.c:333-435): getopt string "o:w:r:s:h?", defaults
+ * (-o "out", -w 20000), atoi parsing, the table <outfile>.txt (output_count_GC, :140-165: first input file only, as the
+ * reference prints `databuf`, not `databuf + i`), the progress lines on stderr including the read count.  Not produced:
+ * <bam>_hits.png (draw_hits needs libgd, :276-331) and the -r region mode (:393-409), which exits with a message.
+ * The BAM file goes to the device compressed (ngscov_push_bgzf); record framing, SEQ GC counting and the per-window
+ * sums run on the GPU, the O(windows) float post-processing of calc_winGC and the printing on the host. */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <getopt.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <zlib.h>
+#include "../../include/ngscov.h"
+
+#define DIE(...) do { fprintf(stderr, __VA_ARGS__); exit(1); } while (0)
+static long long usec(void) { struct timeval tv; gettimeofday(&tv, NULL); return (long long)tv.tv_sec * 1000000 + tv.tv_usec; }
+
+static void usage(const char *prog)
+{
+	fprintf(stderr, "\nUsage: %s [-o OUTFILE] [-w WINDOW_SIZE] [-s 0] [-h] bamFile1 bamFile2 ..\n"
+	        "  B200-native drop-in for the HighPerformanceNGS bam_sliding_count tool: reads count and GC content per window.\n"
+	        "   [-o OUTPUT_FILE]  = output prefix (<prefix>.txt), default out.      [option]\n"
+	        "   [-w WINDOW_SIZE]  = window size, default 20000.                     [option]\n"
+	        "   [-r]              = region mode of the reference: not supported.     [option]\n"
+	        "   [-s]              = accepted and ignored, like the reference.       [option]\n"
+	        "   Infiles           = BAM file(s); the table is that of the first.    [required]\n\n", prog);
+	exit(1);
+}
+
+int main(int argc, char *argv[])
+{
+	const char *outfile = "out", *region = "-"; int window = 20000, opt;
+	if (argc < 2) usage(argv[0]);
+	while ((opt = getopt(argc, argv, "o:w:r:s:h?")) != -1) {
+		switch (opt) {
+		case 'o': outfile = optarg; break;
+		case 'w': window = atoi(optarg); break;
+		case 'r': region = optarg; break;          /* (the reference falls through into -s here) */
+		case 's': break;
+		case '?': case 'h': usage(argv[0]); break;
+		default: fprintf(stderr, "error parameter!\n"); break;
+		}
+	}
+	if (strncmp(region, "-", 6) != 0) DIE("bam_sliding_count: the -r region mode is not supported by the GPU build\n");
+	if (optind >= argc) usage(argv[0]);
+	if (window < 1) DIE("bam_sliding_count: bad window size\n");
+	const long long begin = usec();
+	const char *fn = argv[optind];
+	int fd = open(fn, O_RDONLY);
+	struct stat sb;
+	if (fd < 0 || fstat(fd, &sb) != 0 || sb.st_size < 28) DIE("bam2bed: Fail to open BAM file %s\n", fn);
+	const size_t fsz = (size_t)sb.st_size;
+	const uint8_t *file = (const uint8_t *)mmap(NULL, fsz, PROT_READ, MAP_PRIVATE, fd, 0);
+	if (file == MAP_FAILED) DIE("bam2bed: cannot map %s\n", fn);
+	/* header: inflate leading blocks until it is complete (samtools bam.c:81-121 layout) */
+	size_t off = 0, hbytes = 0, hcap = 1 << 20, hdr_len = 0;
+	uint8_t *hbuf = (uint8_t *)malloc(hcap);
+	int n_ref = -1; uint32_t *ref_len = NULL; char **ref_name = NULL;
+	while (n_ref < 0) {
+		if (off + 18 > fsz) DIE("bam2bed: %s has no BAM header\n", fn);
+		const uint8_t *p = file + off;
+		if (p[0] != 0x1f || p[1] != 0x8b || p[12] != 'B' || p[13] != 'C') DIE("bam2bed: %s is not a BGZF file\n", fn);
+		const size_t bsize = (size_t)(p[16] | p[17] << 8) + 1;
+		uint32_t ulen; memcpy(&ulen, p + bsize - 4, 4);
+		if (hbytes + ulen > hcap) { hcap = (hbytes + ulen) * 2; hbuf = (uint8_t *)realloc(hbuf, hcap); }
+		z_stream zs; memset(&zs, 0, sizeof zs);
+		if (inflateInit2(&zs, -15) != Z_OK) DIE("bam2bed: zlib\n");
+		zs.next_in = (Bytef *)(p + 18); zs.avail_in = (uInt)(bsize - 26); zs.next_out = hbuf + hbytes; zs.avail_out = ulen;
+		if (ulen && inflate(&zs, Z_FINISH) != Z_STREAM_END) DIE("bam2bed: inflate failed in %s\n", fn);
+		inflateEnd(&zs);
+		hbytes += ulen; off += bsize;
+		if (hbytes < 12) continue;
+		if (memcmp(hbuf, "BAM\1", 4)) DIE("bam2bed: %s is not a BAM file\n", fn);
+		uint32_t l_text; memcpy(&l_text, hbuf + 4, 4);
+		size_t q = 8 + (size_t)l_text;
+		if (q + 4 > hbytes) continue;
+		int32_t nr; memcpy(&nr, hbuf + q, 4); q += 4;
+		size_t q0 = q; int complete = 1;
+		for (int i = 0; i < nr; ++i) {
+			if (q + 4 > hbytes) { complete = 0; break; }
+			uint32_t ln; memcpy(&ln, hbuf + q, 4);
+			if (q + 4 + ln + 4 > hbytes) { complete = 0; break; }
+			q += 4 + ln + 4;
+		}
+		if (!complete) continue;
+		n_ref = nr; hdr_len = q;
+		ref_len = (uint32_t *)calloc((size_t)nr + 1, 4); ref_name = (char **)calloc((size_t)nr + 1, sizeof(char *));
+		q = q0;
+		for (int i = 0; i < nr; ++i) {
+			uint32_t ln; memcpy(&ln, hbuf + q, 4); q += 4;
+			ref_name[i] = strndup((const char *)hbuf + q, ln); q += ln;
+			memcpy(&ref_len[i], hbuf + q, 4); q += 4;
+		}
+	}
+	/* whole blocks of the file */
+	size_t end = 0;
+	while (end + 18 <= fsz) { const size_t bs = (size_t)(file[end + 16] | file[end + 17] << 8) + 1; if (end + bs > fsz) break; end += bs; }
+
+	ngscov_cfg cfg; memset(&cfg, 0, sizeof cfg);
+	cfg.mode = NGSCOV_MODE_SLIDE; cfg.window = (uint32_t)window; cfg.n_ref = n_ref; cfg.ref_len = ref_len;
+	cfg.ref_name = (const char *const *)ref_name; cfg.device = getenv("NGSCOV_DEVICE") ? atoi(getenv("NGSCOV_DEVICE")) : 0;
+	ngscov_t *h = NULL;
+	int rc = ngscov_create(&h, &cfg);
+	if (rc) DIE("bam2bed: GPU engine unavailable: %s\n", ngscov_strerror(rc));
+	if ((rc = ngscov_push_bgzf(h, file, end, hdr_len, NGSCOV_PUSH_LAST))) DIE("bam2bed: %s: %s (%s)\n", fn, ngscov_strerror(rc), ngscov_last_cuda_error(h));
+	if ((rc = ngscov_finish(h))) DIE("bam2bed: %s: %s (%s)\n", fn, ngscov_strerror(rc), ngscov_last_cuda_error(h));
+	fprintf(stderr, "Done load bam file %s at %.3f s\n", fn, (double)(usec() - begin) / 1e6);
+	ngscov_stats_t st; ngscov_stats(h, &st);
+	fprintf(stderr, "%lu\n", (unsigned long)st.kept);                    /* n_count: reads counted (:104, :421) */
+	const char *txt; size_t len;
+	if ((rc = ngscov_output(h, NGSCOV_OUT_SLIDE, &txt, &len))) DIE("bam2bed: %s\n", ngscov_strerror(rc));
+	char *name = (char *)malloc(strlen(outfile) + 8);
+	sprintf(name, "%s.txt", outfile);
+	FILE *f = fopen(name, "wb");
+	if (!f) DIE("Failed to open file (%s)\n", name);
+	if (len && fwrite(txt, 1, len, f) != len) DIE("bam2bed: write failed\n");
+	fclose(f);
+	fprintf(stderr, "Done output %s.txt at %.3f s\n", outfile, (double)(usec() - begin) / 1e6);
+	ngscov_destroy(h);
+	for (int j = 0; j < n_ref; ++j) free(ref_name[j]);
+	free(ref_name); free(ref_len); free(hbuf); free(name);
+	munmap((void *)file, fsz); close(fd);
+	return 0;
+}

@@ -17,6 +17,7 @@
  *   ngscov_output        the FILE* streams of fcreat_outfile, IO_stream.h:92-97 (the caller writes the
  *                        bytes to the reference's file names)
  *   ngscov_reset         hashtbl_destroy x2 + free(Bins)              bam2depth.c:332-336
+ *   NGSCOV_MODE_SLIDE    fetch_func + cal_GC + calc_winGC + output_count_GC      bam_sliding_count.c:84-165
  *   ngscov_halo_*, ngscov_bins_*   no reference counterpart (the reference is single-process): region
  *                        sharding across GPUs, SURVEY.md section 8(e)
  *
@@ -40,14 +41,18 @@ typedef struct ngscov ngscov_t;
 
 enum {                       /* cfg.mode */
 	NGSCOV_MODE_DEPTH = 0,   /* bam2depth: drop flag & 0x704, half-open windows, bedGraph + .depth */
-	NGSCOV_MODE_WIG   = 1    /* bam2wig:   drop flag & 0x4,   inclusive-end windows, wig + chromSize */
+	NGSCOV_MODE_WIG   = 1,   /* bam2wig:   drop flag & 0x4,   inclusive-end windows, wig + chromSize */
+	NGSCOV_MODE_SLIDE = 2    /* bam_sliding_count: per window the mapped reads STARTING in it, the sum of their l_qseq and the
+	                            GC content of their SEQ -> the <outfile>.txt table (reference bam_sliding_count.c:84-165; the PNG
+	                            it also draws with libgd is not produced).  One GPU, whole genome. */
 };
 
 enum {                       /* ngscov_output `which` */
 	NGSCOV_OUT_BEDGRAPH  = 0,
 	NGSCOV_OUT_DEPTH     = 1,
 	NGSCOV_OUT_WIG       = 2,
-	NGSCOV_OUT_CHROMSIZE = 3
+	NGSCOV_OUT_CHROMSIZE = 3,
+	NGSCOV_OUT_SLIDE     = 4     /* NGSCOV_MODE_SLIDE: the read-count / GC table */
 };
 
 enum {                       /* ngscov_push flags */

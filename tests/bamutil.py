@@ -34,8 +34,9 @@ def parse_cigar(s):
     return [(int(n), op) for n, op in re.findall(r"(\d+)([MIDNSHP=XB])", s)]
 
 
-def record(name, refid, pos, flag, cigar, seq=True, mapq=60, aux=b""):
-    """One BAM record (with the 4-byte block_size prefix).  pos is 0-based."""
+def record(name, refid, pos, flag, cigar, seq=True, mapq=60, aux=b"", rng=None):
+    """One BAM record (with the 4-byte block_size prefix).  pos is 0-based.  rng: numpy RandomState for random SEQ codes
+    (default: the constant 0x12 pattern, enough for the coverage tools, which never read SEQ)."""
     ops = parse_cigar(cigar)
     qlen = sum(n for n, op in ops if op in _QRY_CONSUME)
     rlen = sum(n for n, op in ops if op in _REF_CONSUME)
@@ -47,14 +48,21 @@ def record(name, refid, pos, flag, cigar, seq=True, mapq=60, aux=b""):
         b = reg2bin(pos, pos + (rlen if rlen else 1))
     core = struct.pack("<iiBBHHHiiii", refid, pos, len(qn), mapq if refid >= 0 else 0, b, len(ops), flag, l_seq, -1, -1, 0)
     cig = b"".join(struct.pack("<I", n << 4 | CIGAR_OPS.index(op)) for n, op in ops)
-    sq = bytes([0x12] * ((l_seq + 1) // 2)) + bytes([30] * l_seq)
+    if rng is None:
+        sq = bytes([0x12] * ((l_seq + 1) // 2)) + bytes([30] * l_seq)
+    else:
+        codes = rng.choice(np.array([1, 2, 4, 8, 15, 2, 4], dtype=np.uint8), size=l_seq + (l_seq & 1))      # A C G T N, GC-rich
+        if l_seq & 1:
+            codes[-1] = 0
+        sq = bytes((codes[0::2] << 4 | codes[1::2]).astype(np.uint8).tolist()) + bytes([30] * l_seq)
     body = core + qn + cig + sq + aux
     return struct.pack("<i", len(body)) + body
 
 
-def records(reads, seq=True):
+def records(reads, seq=True, seq_seed=None):
     """reads: iterable of (refid, pos, flag, cigar) -> uint8 array of the record stream."""
-    out = [record("r%d" % i, r[0], r[1], r[2], r[3], seq=seq) for i, r in enumerate(reads)]
+    rng = np.random.RandomState(seq_seed) if seq_seed is not None else None
+    out = [record("r%d" % i, r[0], r[1], r[2], r[3], seq=seq, rng=rng) for i, r in enumerate(reads)]
     return np.frombuffer(b"".join(out), dtype=np.uint8)
 
 

@@ -23,6 +23,9 @@ def lib():
         l.ngscov_oracle_run.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_char_p),
                                         C.c_int, C.c_uint32, C.c_int, C.POINTER(Result)]
         l.ngscov_oracle_free.argtypes = [C.POINTER(Result)]
+        l.ngscov_oracle_slide.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_char_p), C.c_int,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
+        l.ngscov_oracle_slide_free.argtypes = [C.c_void_p]
         _lib = l
     return _lib
 
@@ -43,3 +46,18 @@ def run(records, names, lens, mode, window, emit_wig=True):
     out.update(n_records=r.n_records, n_kept=r.n_kept, n_mops=r.n_mops, cigar_words=r.cigar_words)
     lib().ngscov_oracle_free(C.byref(r))
     return out
+
+
+def slide(records, names, lens, window):
+    """bam_sliding_count restated (oracle/ngscov_slide_oracle.c) -> dict(txt: bytes of <outfile>.txt, n_count)."""
+    rec = np.ascontiguousarray(records, dtype=np.uint8)
+    n = len(names)
+    nm = (C.c_char_p * max(n, 1))(*[x if isinstance(x, bytes) else x.encode() for x in names])
+    ln = (C.c_uint32 * max(n, 1))(*[int(x) for x in lens])
+    p, m, cnt = C.c_void_p(), C.c_size_t(), C.c_uint64()
+    rc = lib().ngscov_oracle_slide(rec.ctypes.data, rec.size, n, ln, nm, int(window), C.byref(p), C.byref(m), C.byref(cnt))
+    if rc:
+        raise RuntimeError(f"slide oracle failed: {rc}")
+    out = C.string_at(p, m.value) if m.value else b""
+    lib().ngscov_oracle_slide_free(p)
+    return {"txt": out, "n_count": cnt.value}
