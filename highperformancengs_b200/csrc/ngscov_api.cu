@@ -94,6 +94,7 @@ struct ngscov {
 	size_t p_row0;                           /* first global row of the pending chunk */
 	unsigned long long *d_kbmax;
 	uint32_t *d_far_flag, *d_row_a, *d_row_b;
+	uint4 *d_heavy; unsigned int *d_heavy_n; size_t heavy_cap;   /* work items of the heavy tiles (k_heavy_plan / k_heavy_gather) */
 	unsigned long long *d_stF, *d_stC;       /* look-back words of the owner tiles: bytes / (sum, last boundary) */
 	uint4 *d_tile_first, *d_tile_last;
 	uint64_t fin_tile;                       /* owner tiles already finalized (streamed finalize works at tile granularity) */
@@ -371,7 +372,7 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	                h->d_bmax, h->d_count, h->d_slots, h->d_ctr, h->d_st, h->d_run_start, h->d_run_end, h->d_run_depth, h->d_rec_base, h->d_stA, h->d_stB,
 	                h->d_fmt_status, h->d_text[0], h->d_text[1], h->d_text[2], h->d_text[3],
 	                h->d_ent, h->d_rows, h->d_rkmax, h->d_kbmax, h->d_far_flag, h->d_row_a, h->d_row_b, h->d_stF, h->d_stC, h->d_tile_first, h->d_tile_last, h->d_halo, h->d_patch,
-	                h->d_sl_cnt, h->d_sl_len, h->d_sl_gc, h->d_sl_ctg, h->d_sl_ncount, h->d_sl_nwin };
+	                h->d_sl_cnt, h->d_sl_len, h->d_sl_gc, h->d_sl_ctg, h->d_sl_ncount, h->d_sl_nwin, h->d_heavy, h->d_heavy_n };
 	for (void *p : dev) if (p) cudaFree(p);
 	for (int i = 0; i < 2; ++i) if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
 	for (int i = 0; i < 4; ++i) if (h->h_text[i]) cudaFreeHost(h->h_text[i]);
@@ -1473,6 +1474,21 @@ static int cover_tiles(ngscov *h, uint64_t t0, uint64_t t1, unsigned long long m
 		if (text) CK(cudaMemsetAsync(h->d_stF + t0, 0, (t1 - t0) * 8, h->s_main));
 		k_tile_rows<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, h->s_main>>>(h->d_rkmax, (uint32_t)h->rows_used, h->d_tile2seg, h->d_seg, t0, t1 - t0,
 		                                                                   h->d_row_a + t0, h->d_row_b + t0);
+		{	/* tiles fed by very many rows are gathered by many CTAs through the far array */
+			const size_t need = h->rows_used / (NGS_HEAVY_SLICE / 2) + 1024;
+			if (need > h->heavy_cap) {
+				CK(cudaStreamSynchronize(h->s_main));
+				if (h->d_heavy) cudaFree(h->d_heavy);
+				h->d_heavy = nullptr; h->heavy_cap = 0;
+				CK(cudaMalloc((void **)&h->d_heavy, (need + need / 4) * sizeof(uint4))); h->heavy_cap = need + need / 4;
+			}
+			if (!h->d_heavy_n) CK(cudaMalloc((void **)&h->d_heavy_n, 4));
+			CK(cudaMemsetAsync(h->d_heavy_n, 0, 4, h->s_main));
+			k_heavy_plan<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, h->s_main>>>(h->d_row_a + t0, h->d_row_b + t0, t1 - t0, h->d_heavy, h->d_heavy_n, (unsigned int)h->heavy_cap);
+			k_heavy_gather<<<(unsigned)h->sm_count * 4, 256, 0, h->s_main>>>(h->d_heavy, h->d_heavy_n, h->d_ent, h->d_rows, h->d_tile2seg, h->d_seg, t0,
+			                                                               h->d_diff + t0 * (uint64_t)NGS_CT, h->d_far_flag + t0);
+			h->stats.launches += 2;
+		}
 		CoverArgs A;
 		A.n_tiles = t1 - t0; A.tile_off = t0; A.tile2seg = h->d_tile2seg; A.seg = h->d_seg;
 		A.ent = h->d_ent; A.rows = h->d_rows; A.row_a = h->d_row_a + t0; A.row_b = h->d_row_b + t0;

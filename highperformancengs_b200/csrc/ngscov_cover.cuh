@@ -532,6 +532,66 @@ __global__ void __launch_bounds__(256) k_tile_rows(const unsigned long long *rkm
 	row_b[tile] = lo < n_rows ? lo + 1 : n_rows;
 }
 
+/* ---- heavy tiles (targeted panels: thousands of reads starting at one base) --------------------------------------
+ * An owner CTA gathers its rows four at a time; a tile fed by thousands of rows (config 5: a million reads in one tile)
+ * would keep one CTA busy for milliseconds while the rest of the GPU idles.  Tiles with more than NGS_HEAVY_ROWS rows
+ * are therefore taken apart: k_heavy_plan cuts their row range into work items of NGS_HEAVY_SLICE rows and empties the
+ * tile's own range; k_heavy_gather accumulates each item in shared memory like the owner would and adds the non-zero
+ * sums to the tile of the far array, whose flag makes the owner merge it. */
+#define NGS_HEAVY_ROWS  96
+#define NGS_HEAVY_SLICE 32
+__global__ void __launch_bounds__(256) k_heavy_plan(uint32_t *row_a, uint32_t *row_b, uint64_t n_tiles, uint4 *items, unsigned int *n_items, unsigned int cap)
+{
+	const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tile >= n_tiles) return;
+	const uint32_t a = row_a[tile], b = row_b[tile];
+	if (b - a <= NGS_HEAVY_ROWS) return;
+	const uint32_t n = (b - a + NGS_HEAVY_SLICE - 1) / NGS_HEAVY_SLICE;
+	const unsigned int at = atomicAdd(n_items, n);
+	if (at + n > cap) { atomicSub(n_items, n); return; }          /* no room (cannot happen: the list is sized from the row count): the owner keeps the tile */
+	for (uint32_t i = 0; i < n; ++i) items[at + i] = make_uint4((uint32_t)tile, a + i * NGS_HEAVY_SLICE, min(b, a + (i + 1) * NGS_HEAVY_SLICE), 0u);
+	row_b[tile] = a;                                              /* the owner gathers nothing itself */
+}
+__global__ void __launch_bounds__(256) k_heavy_gather(const uint4 *items, const unsigned int *n_items, const uint2 *ent, const ngs_row *rows, const uint32_t *tile2seg,
+                                                     const ngs_seg *seg, uint64_t tile_off, int *diff, uint32_t *far_flag)
+{
+	__shared__ int s_acc[NGS_CT];
+	const int t = threadIdx.x;
+	const unsigned int n = *n_items;
+	for (unsigned int it = blockIdx.x; it < n; it += gridDim.x) {
+		const uint4 w = items[it];
+		const uint64_t tile = w.x, tile_g = tile + tile_off;
+		const ngs_seg &sg = seg[tile2seg[tile_g / NGS_CPT]];
+		const uint32_t pos0 = sg.clip_lo + (uint32_t)((tile_g - sg.tile0 * NGS_CPT) * NGS_CT), ctg = sg.contig;
+		const int64_t vis_lo = (int64_t)pos0 - NGS_NEAR_H;
+		for (int i = t; i < NGS_CT; i += 256) s_acc[i] = 0;
+		__syncthreads();
+		for (uint32_t r = w.y; r < w.z; ++r) {
+			const uint4 m = __ldg(reinterpret_cast<const uint4 *>(rows + r) + 1);          /* count, special, ctg, nrec */
+			if ((uint32_t)t >= m.x) continue;
+			const uint2 e = __ldg(ent + (size_t)r * NGS_ROW_SLOTS + t);
+			const uint32_t kind = e.y >> 30, pos = e.x & 0x1FFFFFFFu;
+			if (kind == NGS_ENT_CHAIN || (int)m.z + (int)(e.x >> 29) != (int)ctg || (int64_t)pos < vis_lo) continue;
+			const uint32_t pl = e.y & 0x3FFFFFFFu, a0 = pos - pos0;
+			uint32_t b0;
+			if (kind == NGS_ENT_SIMPLE) b0 = a0 + pl;
+			else {
+				b0 = a0 + (pl & 0xFFFu);
+				const uint32_t a1 = b0 + ((pl >> 12) & 0x3Fu), b1 = a1 + (pl >> 18);
+				if (a1 < NGS_CT) atomicAdd(&s_acc[a1], 1);
+				if (b1 < NGS_CT) atomicAdd(&s_acc[b1], -1);
+			}
+			if (a0 < NGS_CT) atomicAdd(&s_acc[a0], 1);
+			if (b0 < NGS_CT) atomicAdd(&s_acc[b0], -1);
+		}
+		__syncthreads();
+		int *g = diff + tile * (uint64_t)NGS_CT;
+		for (int i = t; i < NGS_CT; i += 256) { const int v = s_acc[i]; if (v) atomicAdd(g + i, v); }
+		if (t == 0) far_flag[tile] = 1u;
+		__syncthreads();
+	}
+}
+
 /* ---- K2..K5 fused: the tile owner -------------------------------------------------------------------------- */
 struct CoverArgs {
 	uint64_t n_tiles, tile_off;          /* tiles of this launch / global index of the first one; per-tile pointers are pre-offset */

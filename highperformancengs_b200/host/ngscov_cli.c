@@ -312,7 +312,11 @@ int main(int argc, char *argv[])
 			sprintf(suffix, ".%u.wig", (unsigned)n); f_wig = open_out(outfile, suffix);
 			sprintf(suffix, ".%u.chromSize.txt", (unsigned)n); f_chr = open_out(outfile, suffix);
 		}
-		if (!have_bai(fn)) DIE("bam2bed: BAM indexing file is not available.\n");
+		/* the reference refuses to run without a .bai (bam2depth.c:112-119) although only bam_fetch needs it; the engine
+		 * walks the whole stream, so NGSCOV_NO_INDEX=1 lifts the requirement for single-GPU runs (region shards still take
+		 * their file offsets from the linear index) */
+		const int no_index = getenv("NGSCOV_NO_INDEX") && atoi(getenv("NGSCOV_NO_INDEX")) != 0;
+		if (!have_bai(fn) && !(no_index && !(getenv("NGSCOV_GPUS") && atoi(getenv("NGSCOV_GPUS")) > 1))) DIE("bam2bed: BAM indexing file is not available.\n");
 
 		struct stat sb;
 		if (fstat(fd, &sb) != 0 || sb.st_size < 28) DIE("%s: bam2bed: Fail to open BAM file %s\n", basename(argv[0]), fn);

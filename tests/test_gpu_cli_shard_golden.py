@@ -254,3 +254,19 @@ def test_full_size_configs_4_and_5(name, kind, params, runs):
         if name == "c5_full":
             depths = np.fromiter((int(ln.rsplit(b"\t", 1)[1]) for ln in got["bedgraph"].splitlines()), dtype=np.int64)
             assert depths.max() > 10000, "config 5 is the depth > 10^4 pile-up workload"
+
+
+def test_c_driver_index_free_mode(tmp_path):
+    """NGSCOV_NO_INDEX=1: a sorted BAM without a .bai (the reference exits with "BAM indexing file is not available")"""
+    exe = os.path.join(ROOT, "highperformancengs_b200", "host", "bam2depth")
+    spec = [c for c in cases.CASES if c[0] == "random1"][0]
+    names, lens, recs, g = cases.case_input(spec[1], spec[2])
+    bam = str(tmp_path / "random1.bam")
+    bamutil.write_bam(bam, names, lens, recs, index=False)
+    r = subprocess.run([exe, "-o", "o", "-w", "150", "-W", bam], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 1 and "indexing file is not available" in r.stderr
+    r = subprocess.run([exe, "-o", "o", "-w", "150", "-W", bam], cwd=str(tmp_path), capture_output=True, text=True, env=dict(os.environ, NGSCOV_NO_INDEX="1"))
+    assert r.returncode == 0, r.stderr
+    got = {"bedgraph": open(str(tmp_path / "random1.bam.1.bedGraph"), "rb").read(), "depth": open(str(tmp_path / "o.1.depth"), "rb").read(),
+           "wig": open(str(tmp_path / "o.1.wig"), "rb").read(), "chromsize": open(str(tmp_path / "o.1.chromSize.txt"), "rb").read()}
+    check_against_gold(got, "random1|depth|150")
