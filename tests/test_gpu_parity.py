@@ -395,3 +395,62 @@ def test_classic_pipeline_still_matches(oracle, monkeypatch):
         exp = oracle.run(recs, names, lens, mode, 500)
         got = run_engine(names, lens, recs, mode, 500)
         check(got, exp, mode, "classic")
+
+
+def _dense_case(seed, L, cov, names=(b"chrD",)):
+    """uniform random short reads at `cov`x coverage: ~2 * cov * 4096 / read_len run boundaries per owner tile"""
+    rng = np.random.RandomState(seed)
+    reads = []
+    for c in range(len(names)):
+        n = int(L * cov / 40)
+        pos = np.sort(rng.randint(0, L - 60, size=n))
+        ln = rng.randint(20, 60, size=n)
+        reads += [(c, int(p), 0, "%dM" % int(l)) for p, l in zip(pos, ln)]
+    return list(names), [L] * len(names), reads
+
+
+def test_dense_tiles_take_several_text_batches(oracle):
+    """more run boundaries in an owner tile than one text batch holds (1280): the length pre-pass and the batch loop of
+    k_cover; a tile with ~3000 boundaries needs three batches"""
+    names, lens, reads = _dense_case(5, 60000, 40.0)
+    recs = bamutil.records(reads, seq=False)
+    for mode, _ in MODES:
+        exp = oracle.run(recs, names, lens, mode, 1000)
+        got = run_engine(names, lens, recs, mode, 1000)
+        check(got, exp, mode, "dense tiles")
+        if mode == 0:
+            assert exp["bedgraph"].count(b"\n") > 2 * 1280 * (60000 // 4096)
+
+
+def test_lines_longer_than_the_staging_area(oracle):
+    """a contig name of 250 characters: the lines of a batch do not fit the shared-memory staging area and go straight
+    to global memory (byte-wise writer), also in tiles with several batches"""
+    names, lens, reads = _dense_case(6, 30000, 30.0, names=(b"N" * 250, b"short"))
+    recs = bamutil.records(reads, seq=False)
+    exp = oracle.run(recs, names, lens, 0, 500)
+    got = run_engine(names, lens, recs, 0, 500)
+    check(got, exp, 0, "long contig name")
+
+
+@pytest.mark.parametrize("staging", [16384, 100000])
+def test_streamed_finalize_inside_contigs(oracle, monkeypatch, staging):
+    """tile-granular streamed finalize: with small pushes and NGSCOV_STREAM_MIN_TILES=1 k_cover is launched over a few
+    tiles at a time in the middle of contigs; depth carry and last boundary travel from launch to launch through the
+    look-back word of the previous launch's last tile"""
+    monkeypatch.setenv("NGSCOV_STREAM_MIN_TILES", "1")
+    names, lens, reads = bamutil.random_case(23, n_reads=9000, contigs=((b"c1", 150000), (b"c2", 9000), (b"c3", 300000)))
+    reads = [r for r in reads if r[0] < 0 or r[3] != "50M1000N100M"] + [(2, 1000, 0, "100M250000N50M")]      # plus one far delta across many tiles
+    reads.sort(key=lambda r: (r[0] if r[0] >= 0 else 1 << 30, r[1]))
+    recs = bamutil.records(reads, seq=False)
+    for mode, _ in MODES:
+        exp = oracle.run(recs, names, lens, mode, 777)
+        got = run_engine(names, lens, recs, mode, 777, staging_bytes=staging)
+        check(got, exp, mode, f"streamed inside contigs, staging={staging}")
+    # long stretches without coverage between launches
+    names, lens = [b"g1"], [2000000]
+    reads = [(0, 100, 0, "150M"), (0, 120, 0, "50M"), (0, 900000, 0, "150M"), (0, 900050, 16, "150M"), (0, 1999000, 0, "100M")]
+    reads = sorted(reads + [(0, 400000 + 37 * i, 0, "30M") for i in range(2000)], key=lambda r: r[1])
+    recs = bamutil.records(reads, seq=False)
+    exp = oracle.run(recs, names, lens, 0, 20000)
+    got = run_engine(names, lens, recs, 0, 20000, staging_bytes=8192)
+    check(got, exp, 0, "streamed with gaps")
