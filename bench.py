@@ -298,11 +298,18 @@ class Job:
         t0 = time.time()
         if self.rank == 0:
             need = int(g.records_size(0, g.n_ref + 1) * 0.2) + (1 << 30)
-            if shutil.disk_usage(os.path.dirname(path)).free < need:
-                path_ok = False
-            else:
+            if shutil.disk_usage(os.path.dirname(path)).free >= need:
+                try:                      # the other ranks wait at the barrier: rank 0 may use every core for the deflate
+                    import ctypes
+                    gomp = ctypes.CDLL("libgomp.so.1")
+                    gomp.omp_set_num_threads(os.cpu_count() or 1)
+                    try:
+                        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+                    except Exception:
+                        pass
+                except Exception:
+                    gomp = None
                 g.write_bam(path, level=1)
-                path_ok = True
         barrier()
         if not os.path.exists(path):
             return None
