@@ -54,6 +54,7 @@ SYMBOLS = {
     "ngscov_finish_runs": (C.c_int, [_H]),
     "ngscov_slice_done": (C.c_int, [_H, C.POINTER(C.c_int)]),
     "ngscov_contigs_done": (C.c_int, [_H, C.POINTER(C.c_uint32)]),
+    "ngscov_set_region": (C.c_int, [_H, C.c_int, C.c_int, C.c_int]),
     "ngscov_push_bgzf": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     "ngscov_halo_get": (C.c_int, [_H, C.POINTER(Halo)]),
     "ngscov_halo_put": (C.c_int, [_H, C.c_int, C.c_uint32]),

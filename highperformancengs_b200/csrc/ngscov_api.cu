@@ -103,6 +103,7 @@ struct ngscov {
 	std::string bed_tail; size_t bed_tail_old; /* halo: replacement of the last line, and how many bytes it replaces */
 	bool bed_patched;
 	/* NGSCOV_MODE_SLIDE (bam_sliding_count) */
+	int reg_ref, reg_beg, reg_end;     /* ngscov_set_region (slide mode); reg_ref < 0: none */
 	bool slide; unsigned int *d_sl_cnt, *d_sl_len, *d_sl_ctg; unsigned long long *d_sl_gc, *d_sl_ncount; uint32_t *d_sl_nwin;
 	std::string slide_text; unsigned long long slide_ncount;
 	long long *d_halo;                       /* the shard's running halo record (device), see k_halo_gather */
@@ -334,6 +335,7 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	 * last line afterwards); the classic kernels need the whole shard before the halo is known */
 	h->stream_fin = (cfg->slice_end == 0 || h->cover) && !(getenv("NGSCOV_STREAM_FINALIZE") && atoi(getenv("NGSCOV_STREAM_FINALIZE")) == 0);
 	h->slide = cfg->mode == NGSCOV_MODE_SLIDE;
+	h->reg_ref = -1; h->reg_beg = 0; h->reg_end = 0;
 	if (h->slide) {
 		if (!h->cover) return NGSCOV_EINVAL;                              /* the table pipeline only */
 		h->stream_fin = false;
@@ -533,6 +535,7 @@ static IngestArgs make_ingest_args(ngscov *h, const uint8_t *base, int64_t n, in
 	A.base = base; A.n = n; A.shift = h->shift; A.n_sub = n_sub; A.entry = h->d_entry; A.exit = h->d_exit;
 	A.cfg.n_ref = h->n_ref; A.cfg.flag_mask = h->cfg.mode == NGSCOV_MODE_DEPTH ? 0x704u : 0x4u;
 	A.cfg.ctg2seg = h->d_ctg2seg; A.cfg.seg = h->d_seg; A.cfg.end_ctg = h->end_ctg; A.cfg.end_pos = h->end_pos;
+	A.cfg.reg_ref = h->reg_ref; A.cfg.reg_beg = h->reg_beg; A.cfg.reg_end = h->reg_end;
 	A.ref_len = h->d_ref_len; A.diff = h->d_diff; A.st = h->d_st;
 	A.count = h->d_count; A.slots = h->d_slots; A.slot_shift = h->shift - 5; A.ctr = h->d_ctr;
 	A.fixed_entry0 = fixed0; A.entry0_from_state = from_state ? 1 : 0;
@@ -805,6 +808,26 @@ extern "C" int ngscov_push_host(ngscov_t *h, const void *host, size_t nbytes, in
 	return 0;
 }
 
+/* the device inflate.  Default: one decoder per warp (k_bgzf_inflate).  NGSCOV_INF_S=2 runs two decoders per warp as a
+ * warp-wide state machine (k_bgzf_inflate_ls): 13 % fewer warp instructions, but half the warps per block of input --
+ * +12 % when a launch covers several waves of blocks, -30 % at the default chunk size.  The
+ * grid fills every SM to its occupancy and the decoders stride over the blocks */
+template <class K>
+static void launch_inflate_k(ngscov_t *h, K kern, int S, int &per_sm, int idx, uint32_t nb, uint8_t *data, int sm)
+{
+	if (!per_sm) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NGS_INF_WARPS * 32, 0); if (per_sm < 1) per_sm = 1; }
+	const size_t per_cta = (size_t)NGS_INF_WARPS * S;
+	const unsigned grid = (unsigned)std::min<size_t>((nb + per_cta - 1) / per_cta, (size_t)sm * per_sm);
+	kern<<<grid, NGS_INF_WARPS * 32, 0, h->s_main>>>(h->d_comp[idx], h->d_desc[idx], nb, data, h->d_st);
+}
+static void launch_inflate(ngscov_t *h, int idx, uint32_t nb, uint8_t *data, int sm)
+{
+	static int occ[2] = { 0, 0 };
+	const char *e = getenv("NGSCOV_INF_S");
+	if (e && atoi(e) == 2) launch_inflate_k(h, k_bgzf_inflate_ls<2>, 2, occ[1], idx, nb, data, sm);
+	else launch_inflate_k(h, k_bgzf_inflate<1>, 1, occ[0], idx, nb, data, sm);
+}
+
 /* BGZF blocks as they lie in the file -> device inflate -> the same chunk pipeline as ngscov_push_host.  The host only
  * walks the 18-byte block headers (BSIZE) and 8-byte footers (ISIZE); samtools bgzf.c:214-238 (inflate_block) runs on
  * the GPU (k_bgzf_inflate).  Compressed bytes of chunk k+1 are copied while chunk k is inflated and ingested. */
@@ -887,9 +910,8 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 		uint8_t *data = h->d_chunk[idx] + NGS_HEADROOM;
 		CK(cudaStreamWaitEvent(h->s_main, h->ev_h2d[idx], 0));
 		const uint32_t nb = (uint32_t)(c.b1 - c.b0);
-		const unsigned grid = (unsigned)std::min<size_t>((nb + NGS_INF_WARPS - 1) / NGS_INF_WARPS, (size_t)sm * 9);
 		CK(cudaEventRecord(next_event(h->ev_inf, h->n_inf), h->s_main));
-		k_bgzf_inflate<<<grid, NGS_INF_WARPS * 32, 0, h->s_main>>>(h->d_comp[idx], h->d_desc[idx], nb, data, h->d_st);
+		launch_inflate(h, idx, nb, data, sm);
 		CK(cudaEventRecord(next_event(h->ev_inf, h->n_inf), h->s_main));
 		h->stats.launches += 1;
 		CK(cudaGetLastError());
@@ -1210,6 +1232,17 @@ extern "C" int ngscov_slice_done(ngscov_t *h, int *done)
 	CK(cudaStreamSynchronize(h->s_main));
 	mr = h->h_st->max_ref_p1;
 	*done = mr >= (unsigned int)h->end_ctg + 2u ? 1 : 0;
+	return 0;
+}
+
+/* NGSCOV_MODE_SLIDE: count only the records bam_fetch(ref, beg, end) hands out -- the `-r` mode of the reference
+ * (bam_sliding_count.c:393-409).  Before the first push; ref < 0 clears the region. */
+extern "C" int ngscov_set_region(ngscov_t *h, int ref, int beg, int end)
+{
+	if (!h) return NGSCOV_EINVAL;
+	if (!h->slide || ref >= h->n_ref) return NGSCOV_EINVAL;
+	if (h->stats.stream_bytes || h->runs_done || h->last_pushed) return NGSCOV_ESTATE;
+	h->reg_ref = ref < 0 ? -1 : ref; h->reg_beg = beg; h->reg_end = end;
 	return 0;
 }
 

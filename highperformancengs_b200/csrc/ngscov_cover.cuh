@@ -61,12 +61,16 @@ __device__ __forceinline__ uint32_t ngs_seq_gc(const Mem &mem, int64_t so, int32
 }
 /* returns 1 = entry y, 2 = record needs the sequential path, 0 = dropped (tid < 0 or BAM_FUNMAP, :96-97) */
 template <class Mem, class Cnt>
-__device__ __forceinline__ int ngs_slide_record(const Mem &mem, int64_t o, const ngs_hdr &h, uint32_t &y, Cnt &cnt)
+__device__ __forceinline__ int ngs_slide_record(const ngs_walk_cfg &cfg, const Mem &mem, int64_t o, const ngs_hdr &h, uint32_t &y, Cnt &cnt)
 {
 	cnt.records += 1; cnt.cigar_words += h.n_cigar;
 	const uint32_t r1 = (uint32_t)(h.ref_id + 1);
 	if (r1 > cnt.max_ref_p1) cnt.max_ref_p1 = r1;
 	if (h.ref_id < 0 || (h.flag & 4u)) return 0;
+	if (cfg.reg_ref >= 0) {                          /* -r: what bam_fetch would not hand out is not counted (:393-409) */
+		const CigReader<Mem> cig = { mem, o + 36 + (int64_t)h.l_qname };
+		if (!ngs_region_pass(cfg, h.ref_id, h.pos, h.n_cigar, cig)) return 0;
+	}
 	cnt.kept += 1;
 	if (h.pos < 0 || h.l_seq >= 0xFFFF) return 2;
 	const uint32_t gc = ngs_seq_gc(mem, o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar, h.l_seq) & 0xFFFFu;
@@ -106,7 +110,7 @@ __device__ __forceinline__ long long chain_classify(const ngs_walk_cfg &cfg, con
 			uint32_t y = 0; int sp = 0;
 			CigReader<Mem> cig = { mem, o + 36 + (int64_t)h.l_qname };
 			int got;
-			if (SLIDE) { got = ngs_slide_record(mem, o, h, y, cnt); if (got == 2) { special |= NGS_ROW_OVERFLOW; got = 0; } }
+			if (SLIDE) { got = ngs_slide_record(cfg, mem, o, h, y, cnt); if (got == 2) { special |= NGS_ROW_OVERFLOW; got = 0; } }
 			else got = ngs_classify_record(cfg, h, (uint32_t)(o - entry), cig, y, sp, cnt);
 			if (got) {
 				if (ctg0 < 0) ctg0 = h.ref_id;
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(256, NGS_K1_MINB) k_chain_classify(const __gri
 				uint32_t y = 0; int sp = 0;
 				CigReader<DevMem> cig = { mem, o + 36 + (int64_t)h.l_qname };
 				int got;
-				if (SLIDE) { got = ngs_slide_record(mem, o, h, y, cnt); if (got == 2) { special |= NGS_ROW_OVERFLOW; got = 0; } }
+				if (SLIDE) { got = ngs_slide_record(A.cfg, mem, o, h, y, cnt); if (got == 2) { special |= NGS_ROW_OVERFLOW; got = 0; } }
 				else got = ngs_classify_record(A.cfg, h, (uint32_t)(o - entry), cig, y, sp, cnt);
 				if (got) {
 					if (ctg0 < 0) ctg0 = h.ref_id;
@@ -1175,7 +1179,8 @@ __global__ void __launch_bounds__(256) k_slide_accumulate(const __grid_constant_
 					int64_t o = A.entry[row];
 					while (o < hi) {
 						ngs_hdr h; mem.hdr_lite(o, h);
-						if (h.ref_id >= 0 && !(h.flag & 4u)) {
+						const CigReader<DevMem> cig = { mem, o + 36 + (int64_t)h.l_qname };
+						if (h.ref_id >= 0 && !(h.flag & 4u) && ngs_region_pass(A.cfg, h.ref_id, h.pos, h.n_cigar, cig)) {
 							const uint32_t gc = ngs_seq_gc(mem, o + 36 + (int64_t)h.l_qname + 4ll * h.n_cigar, h.l_seq) & 0xFFFFu;
 							slide_add(S, (uint32_t)h.ref_id, h.pos, gc, (uint32_t)h.l_seq);
 							++n_count;

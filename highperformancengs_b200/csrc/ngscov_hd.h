@@ -445,7 +445,29 @@ typedef struct {
 	const ngs_seg *seg;
 	int32_t  end_ctg;            /* region shard: a record of this contig at or beyond end_pos lies behind the slice */
 	uint32_t end_pos;            /* (end_ctg = -2: no slice).  Such a record counts as "the next contig has begun" */
+	int32_t  reg_ref;            /* NGSCOV_MODE_SLIDE, `-r` of bam_sliding_count: only records bam_fetch(reg_ref, reg_beg, reg_end) */
+	int32_t  reg_beg, reg_end;   /* hands out are counted; reg_ref < 0: no region */
 } ngs_walk_cfg;
+
+/* The record test of bam_fetch (samtools-0.1.19 bam_index.c: bam_iter_read stops at another refID or POS >= end,
+ * is_overlap wants the record's end > beg in unsigned arithmetic; the end is bam_calend over the reference-consuming
+ * CIGAR operations M D N = X, or POS + 1 without a CIGAR).  cig(i) = CIGAR word i.  The 'B' operation of bam_calend is
+ * not restated (no aligner writes it). */
+template <class Cig>
+NGS_HD bool ngs_region_pass(const ngs_walk_cfg &cfg, int32_t ref_id, int32_t pos, uint32_t n_cigar, const Cig &cig)
+{
+	if (cfg.reg_ref < 0) return true;
+	if (ref_id != cfg.reg_ref) return false;
+	const uint32_t rbeg = (uint32_t)pos, beg = (uint32_t)cfg.reg_beg;
+	if (rbeg >= (uint32_t)cfg.reg_end) return false;
+	if (rbeg > beg) return true;                    /* its end is at least POS */
+	uint32_t rend = rbeg + 1u;
+	if (n_cigar) {
+		rend = rbeg;
+		for (uint32_t k = 0; k < n_cigar; ++k) { const uint32_t w = cig(k); if ((0x3C1A7u >> ((w & 15u) << 1)) & 2u) rend += w >> 4; }
+	}
+	return rend > beg;
+}
 
 /* ---- compact record table (K1 -> owner tiles) ---------------------------------------------------
  * K1 (k_chain_classify) frames AND decodes: every record that contributes at least one M interval leaves one

@@ -16,90 +16,100 @@
 #define NGSCOV_INFLATE_H
 #include "ngscov_hd.h"
 
+#ifndef NGS_INF_LBITS
 #define NGS_INF_LBITS 10                 /* primary lookup width, literal/length code */
+#endif
+#ifndef NGS_INF_DBITS
 #define NGS_INF_DBITS 8                  /* primary lookup width, distance code */
+#endif
 
-/* Primary-table entry (32 bit): bits 3..0 code length (0: the code is longer than the primary width), 7..4 number of
- * extra bits, 9..8 kind (0 literal, 1 length or distance, 2 end of block), 31..16 value: the literal, or the BASE of
- * the length / distance (RFC 1951 3.2.5), so the hot loop does no arithmetic on symbols.  Plain tables (the
- * code-length code) carry the symbol in 31..16. */
-#define NGS_INF_KIND_LIT 0u
-#define NGS_INF_KIND_VAL 1u
-#define NGS_INF_KIND_EOB 2u
-#define NGS_INF_KIND_BAD 3u
-
-/* table memory of one decoder (device: one slice of shared memory per warp) */
+/* Primary-table entry (16 bit): bits 3..0 code length (0: the code is longer than the primary width), 15..4 the
+ * symbol.  Base value and extra-bit count of a length / distance symbol (RFC 1951 3.2.5) come from two 32-entry
+ * tables the output policy hands out (lentry / dentry: value in bits 23..0, number of extra bits in 31..24) -- on the
+ * device they sit in shared memory once per CTA.  Two-byte entries keep one decoder's tables at 3.5 KB: 48 decoders per SM
+ * (k_bgzf_inflate), or two per warp (k_bgzf_inflate_ls). */
 typedef struct {
-	uint32_t lfast[1 << NGS_INF_LBITS];
-	uint32_t dfast[1 << NGS_INF_DBITS];
+	uint16_t lfast[1 << NGS_INF_LBITS];
+	uint16_t dfast[1 << NGS_INF_DBITS];
 	uint16_t lsym[288], dsym[32];        /* symbols in canonical order, for the bit-by-bit slow path */
 	uint16_t lcount[16], dcount[16];     /* codes per length */
 	uint32_t lslow[2], dslow[2];         /* slow path restart behind the primary width: first code, symbol index */
 	uint8_t  lens[320];                  /* code lengths of the block header (literal/length then distance) */
 } ngs_inf_tables;
 
+/* Bit reader, LSB first.  The stream is read as ALIGNED 32-bit words starting at the word that holds its first byte
+ * (`lead` = the bits of that word that lie before the stream): w0 holds the next unread bit at position bp, w1 and w2
+ * are the two words after it.  A field of up to 32 bits is one funnel shift of (w0, w1); when bp passes 32 the words
+ * move down and the word after w2 is fetched -- two word-advances before anything needs it, so the load latency is
+ * off the decode chain.  The reader may touch up to 15 bytes past the end of the stream and up to 3 before its start
+ * (the caller guarantees that much readable memory); what it reads there only matters to a malformed stream, which
+ * the consumed-bytes check at the end of every block rejects. */
 typedef struct {
-	const uint8_t *in; uint32_t in_len, in_pos;
-	uint64_t buf; uint32_t cnt;          /* bit buffer, LSB first */
+	const uint32_t *wbase;               /* aligned word holding the first byte read by this reader */
+	uint32_t w0, w1, w2, bp, nw;         /* nw: words left behind so far */
+	uint32_t lead, start;                /* start: stream offset (bytes) this reader was opened at */
 } ngs_inf_bits;
 
-/* 32 more bits into the buffer (requires cnt <= 32).  Away from the end of the input the four bytes come from two
- * aligned 32-bit loads and a funnel shift (they may read up to seven bytes past in_len: the caller guarantees that
- * much readable memory); near the end byte by byte, zero bits past the end. */
-NGS_HD void ngs_inf_refill32(ngs_inf_bits &b)
+NGS_HD uint32_t ngs_inf_word(const uint32_t *p)
 {
-	uint32_t v = 0;
-	if (b.in_pos + 8u <= b.in_len) {
-		const uintptr_t p = (uintptr_t)(b.in + b.in_pos);
-		const uint32_t *w = (const uint32_t *)(p & ~(uintptr_t)3);
-		const uint32_t sh = (uint32_t)(p & 3u) * 8u, lo = w[0], hi = w[1];
 #if defined(__CUDA_ARCH__)
-		v = __funnelshift_r(lo, hi, sh);
+	return __ldg(p);
 #else
-		v = sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+	uint32_t v; memcpy(&v, p, 4); return v;
 #endif
-	} else {
-		for (uint32_t k = 0; k < 4u; ++k) if (b.in_pos + k < b.in_len) v |= (uint32_t)b.in[b.in_pos + k] << (8u * k);
-	}
-	b.in_pos += 4u;                      /* may run past in_len: only zero bits come from there, and that is an error below */
-	b.buf |= (uint64_t)v << b.cnt; b.cnt += 32u;
+}
+NGS_HD void ngs_inf_open(ngs_inf_bits &b, const uint8_t *in, uint32_t start)
+{
+	const uintptr_t a = (uintptr_t)(in + start);
+	b.wbase = (const uint32_t *)(a & ~(uintptr_t)3);
+	b.lead = (uint32_t)(a & 3u) * 8u; b.bp = b.lead; b.nw = 0; b.start = start;
+	b.w0 = ngs_inf_word(b.wbase); b.w1 = ngs_inf_word(b.wbase + 1); b.w2 = ngs_inf_word(b.wbase + 2);
+}
+/* the next 32 bits of the stream */
+NGS_HD uint32_t ngs_inf_peek(const ngs_inf_bits &b)
+{
+#if defined(__CUDA_ARCH__)
+	return __funnelshift_r(b.w0, b.w1, b.bp);
+#else
+	return b.bp ? (b.w0 >> b.bp) | (b.w1 << (32u - b.bp)) : b.w0;
+#endif
+}
+NGS_HD void ngs_inf_skip(ngs_inf_bits &b, uint32_t n)        /* n <= 32 */
+{
+	b.bp += n;
+	if (b.bp >= 32u) { b.bp -= 32u; ++b.nw; b.w0 = b.w1; b.w1 = b.w2; b.w2 = ngs_inf_word(b.wbase + b.nw + 2u); }
 }
 NGS_HD uint32_t ngs_inf_get(ngs_inf_bits &b, uint32_t n)     /* n <= 16 */
 {
-	if (b.cnt < n) ngs_inf_refill32(b);
-	const uint32_t v = (uint32_t)b.buf & ((1u << n) - 1u);
-	b.buf >>= n; b.cnt -= n;
+	const uint32_t v = ngs_inf_peek(b) & ((1u << n) - 1u);
+	ngs_inf_skip(b, n);
 	return v;
 }
-/* bytes really consumed so far (the buffer may hold look-ahead) */
-NGS_HD uint32_t ngs_inf_consumed(const ngs_inf_bits &b) { return b.in_pos - (b.cnt >> 3); }
+/* bytes consumed so far, counted from the start of the stream (a partly used byte counts) */
+NGS_HD uint32_t ngs_inf_consumed(const ngs_inf_bits &b) { return b.start + ((b.nw * 32u + b.bp - b.lead + 7u) >> 3); }
 
-/* symbol -> entry bits above the code length */
-NGS_HD uint32_t ngs_inf_ll_entry(uint32_t s)       /* literal/length alphabet */
+/* length symbol 257 + i and distance symbol j -> base value | extra bits << 24 (RFC 1951 3.2.5).  Symbols that must
+ * not occur (length 286/287, distance 30/31) get a value no block can satisfy, so the range check of the match
+ * rejects them without a test of their own. */
+NGS_HD uint32_t ngs_inf_len_entry(uint32_t i)
 {
-	if (s < 256u) return (s << 16) | (NGS_INF_KIND_LIT << 8);
-	if (s == 256u) return NGS_INF_KIND_EOB << 8;
-	if (s > 285u) return NGS_INF_KIND_BAD << 8;
-	const uint32_t i = s - 257u;
-	uint32_t base, ext;
-	if (i < 8u) { base = 3u + i; ext = 0; }
-	else if (i >= 28u) { base = 258u; ext = 0; }
-	else { ext = (i >> 2) - 1u; base = 3u + ((4u + (i & 3u)) << ext); }
-	return (base << 16) | (NGS_INF_KIND_VAL << 8) | (ext << 4);
+	if (i > 28u) return 0xffffffu;
+	if (i < 8u) return 3u + i;
+	if (i == 28u) return 258u;
+	const uint32_t ext = (i >> 2) - 1u;
+	return (3u + ((4u + (i & 3u)) << ext)) | (ext << 24);
 }
-NGS_HD uint32_t ngs_inf_d_entry(uint32_t j)        /* distance alphabet */
+NGS_HD uint32_t ngs_inf_dist_entry(uint32_t j)
 {
-	if (j > 29u) return NGS_INF_KIND_BAD << 8;
-	uint32_t base, ext;
-	if (j < 4u) { base = 1u + j; ext = 0; }
-	else { ext = (j >> 1) - 1u; base = 1u + ((2u + (j & 1u)) << ext); }
-	return (base << 16) | (NGS_INF_KIND_VAL << 8) | (ext << 4);
+	if (j > 29u) return 0xffffffu;
+	if (j < 4u) return 1u + j;
+	const uint32_t ext = (j >> 1) - 1u;
+	return (1u + ((2u + (j & 1u)) << ext)) | (ext << 24);
 }
 
 /* canonical Huffman tables from code lengths: symbols in canonical order, codes per length, and the primary lookup
- * (indexed by the next `bits` stream bits = the code reversed).  alphabet: 0 plain, 1 literal/length, 2 distance.
- * Returns 0, or -1 for an over-subscribed code. */
-NGS_HD int ngs_inf_build(const uint8_t *lens, uint32_t n, uint16_t *count, uint16_t *sym, uint32_t *fast, uint32_t bits, int alphabet, uint32_t *slow)
+ * (indexed by the next `bits` stream bits = the code reversed).  Returns 0, or -1 for an over-subscribed code. */
+NGS_HD int ngs_inf_build(const uint8_t *lens, uint32_t n, uint16_t *count, uint16_t *sym, uint16_t *fast, uint32_t bits, uint32_t *slow)
 {
 	uint16_t offs[16];
 	for (uint32_t l = 0; l < 16u; ++l) count[l] = 0;
@@ -121,8 +131,7 @@ NGS_HD int ngs_inf_build(const uint8_t *lens, uint32_t n, uint16_t *count, uint1
 			uint32_t r = 0;
 			for (uint32_t j = 0; j < l; ++j) r |= ((code >> j) & 1u) << (l - 1u - j);
 #endif
-			const uint32_t sy = sym[idx];
-			const uint32_t e = l | (alphabet == 1 ? ngs_inf_ll_entry(sy) : alphabet == 2 ? ngs_inf_d_entry(sy) : (sy << 16));
+			const uint16_t e = (uint16_t)(l | ((uint32_t)sym[idx] << 4));
 			for (uint32_t f = r; f < (1u << bits); f += 1u << l) fast[f] = e;
 		}
 	}
@@ -133,12 +142,12 @@ NGS_HD int ngs_inf_build(const uint8_t *lens, uint32_t n, uint16_t *count, uint1
 	return 0;
 }
 
-/* code longer than the primary width: bit by bit over the canonical order (RFC 1951 3.2.2); needs >= 15 bits in the
- * buffer.  Returns the symbol (bits consumed) or -1. */
-NGS_HD int ngs_inf_decode_slow(ngs_inf_bits &b, const uint16_t *count, const uint16_t *sym, uint32_t bits, const uint32_t *slow)
+/* code longer than the primary width, decoded bit by bit over the canonical order (RFC 1951 3.2.2) from the 32 peeked
+ * bits x.  Returns the symbol and its code length in *clen (nothing is consumed), or -1. */
+NGS_HD int ngs_inf_decode_slow(uint32_t x, const uint16_t *count, const uint16_t *sym, uint32_t bits, const uint32_t *slow, uint32_t *clen)
 {
 	/* the first `bits` stream bits are the code prefix, most significant bit first */
-	const uint32_t pre = (uint32_t)b.buf & ((1u << bits) - 1u);
+	const uint32_t pre = x & ((1u << bits) - 1u);
 #if defined(__CUDA_ARCH__)
 	int code = (int)((__brev(pre) >> (32u - bits)) << 1);
 #else
@@ -147,22 +156,25 @@ NGS_HD int ngs_inf_decode_slow(ngs_inf_bits &b, const uint16_t *count, const uin
 	int code = (int)(r << 1);
 #endif
 	int first = (int)slow[0], index = (int)slow[1];
-	uint64_t bb = b.buf >> bits;
+	uint32_t bb = x >> bits;
 	for (uint32_t l = bits + 1u; l < 16u; ++l) {
 		code |= (int)(bb & 1u); bb >>= 1;
 		const int c = (int)count[l];
-		if (code - c < first) { b.buf >>= l; b.cnt -= l; return (int)sym[index + (code - first)]; }
+		if (code - c < first) { *clen = l; return (int)sym[index + (code - first)]; }
 		index += c; first += c; first <<= 1; code <<= 1;
 	}
 	return -1;
 }
 /* one symbol of a plain table */
-NGS_HD int ngs_inf_decode(ngs_inf_bits &b, const uint16_t *count, const uint16_t *sym, const uint32_t *fast, uint32_t bits, const uint32_t *slow)
+NGS_HD int ngs_inf_decode(ngs_inf_bits &b, const uint16_t *count, const uint16_t *sym, const uint16_t *fast, uint32_t bits, const uint32_t *slow)
 {
-	if (b.cnt < 16u) ngs_inf_refill32(b);
-	const uint32_t e = fast[(uint32_t)b.buf & ((1u << bits) - 1u)];
-	if (e & 15u) { b.buf >>= (e & 15u); b.cnt -= (e & 15u); return (int)(e >> 16); }
-	return ngs_inf_decode_slow(b, count, sym, bits, slow);
+	const uint32_t x = ngs_inf_peek(b);
+	const uint32_t e = fast[x & ((1u << bits) - 1u)];
+	if (e & 15u) { ngs_inf_skip(b, e & 15u); return (int)(e >> 4); }
+	uint32_t cl = 0;
+	const int s = ngs_inf_decode_slow(x, count, sym, bits, slow, &cl);
+	if (s >= 0) ngs_inf_skip(b, cl);
+	return s;
 }
 
 /* header of a dynamic block (RFC 1951 3.2.7) or the fixed code (3.2.6) -> tables.  0 / -1. */
@@ -189,7 +201,7 @@ NGS_HD int ngs_inf_block_tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables 
 			T.lens[o] = (uint8_t)ngs_inf_get(b, 3);
 		}
 		/* the 19-symbol code borrows the distance tables for a moment */
-		if (ngs_inf_build(T.lens, 19u, T.dcount, T.dsym, T.dfast, 7u, 0, T.dslow)) return -1;
+		if (ngs_inf_build(T.lens, 19u, T.dcount, T.dsym, T.dfast, 7u, T.dslow)) return -1;
 		uint32_t i = 0;
 		while (i < nlen + ndist) {
 			const int s = ngs_inf_decode(b, T.dcount, T.dsym, T.dfast, 7u, T.dslow);
@@ -206,30 +218,31 @@ NGS_HD int ngs_inf_block_tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables 
 	}
 	/* the lengths sit at lens[0..nlen) and lens[nlen..nlen+ndist); the 19-symbol code that lived in the distance
 	 * tables is dead by now */
-	if (ngs_inf_build(T.lens + nlen, ndist, T.dcount, T.dsym, T.dfast, NGS_INF_DBITS, 2, T.dslow)) return -1;
-	if (ngs_inf_build(T.lens, nlen, T.lcount, T.lsym, T.lfast, NGS_INF_LBITS, 1, T.lslow)) return -1;
+	if (ngs_inf_build(T.lens + nlen, ndist, T.dcount, T.dsym, T.dfast, NGS_INF_DBITS, T.dslow)) return -1;
+	if (ngs_inf_build(T.lens, nlen, T.lcount, T.lsym, T.lfast, NGS_INF_LBITS, T.lslow)) return -1;
 	return 0;
 }
 
 /* Decoding loop with the output left to a policy:
  *   void literal(uint32_t pos, uint32_t byte); void match(uint32_t pos, uint32_t len, uint32_t dist);
  *   void stored(uint32_t pos, const uint8_t *src, uint32_t len); void finish();   (finish: nothing may stay pending)
+ *   uint32_t lentry(uint32_t i); uint32_t dentry(uint32_t j);   ngs_inf_len_entry / ngs_inf_dist_entry, or a table of them
  *   int tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables &T);   builds the block's tables, normally by calling
  *       ngs_inf_block_tables; the device policy lets ONE lane build them in the warp's shared-memory slice and hands the
  *       advanced bit reader to the other lanes
- * `in` must be readable up to in_len + 7.  Returns the number of bytes produced, or -1 (malformed stream / output
+ * `in` must be readable from 3 bytes before it up to in_len + 15.  Returns the number of bytes produced, or -1 (malformed stream / output
  * larger than out_len). */
 template <class Out>
 NGS_HD long ngs_inflate_stream(const uint8_t *in, uint32_t in_len, uint32_t out_len, ngs_inf_tables &T, Out &out)
 {
-	ngs_inf_bits b; b.in = in; b.in_len = in_len; b.in_pos = 0; b.buf = 0; b.cnt = 0;
-	uint32_t pos = 0, last;
+	ngs_inf_bits b; ngs_inf_open(b, in, 0u);
+	uint32_t pos = 0, last, bad = 0;
 	do {
-		last = ngs_inf_get(b, 1);
-		const uint32_t btype = ngs_inf_get(b, 2);
+		const uint32_t hdr = ngs_inf_get(b, 3);
+		last = hdr & 1u;
+		const uint32_t btype = hdr >> 1;
 		if (btype == 0u) {
-			const uint32_t drop = b.cnt & 7u;                      /* to the next byte boundary */
-			b.buf >>= drop; b.cnt -= drop;
+			ngs_inf_skip(b, (8u - (b.bp & 7u)) & 7u);            /* to the next byte boundary (lead is a multiple of 8) */
 			const uint32_t len = ngs_inf_get(b, 16), nlen = ngs_inf_get(b, 16);
 			if ((len ^ nlen) != 0xffffu) return -1;
 			const uint32_t at = ngs_inf_consumed(b);
@@ -237,35 +250,39 @@ NGS_HD long ngs_inflate_stream(const uint8_t *in, uint32_t in_len, uint32_t out_
 			out.finish();
 			out.stored(pos, in + at, len);
 			pos += len;
-			b.in_pos = at + len; b.buf = 0; b.cnt = 0;
+			ngs_inf_open(b, in, at + len);
 		} else if (btype == 3u) return -1;
 		else {
 			if (out.tables(b, btype, T)) return -1;
 			for (;;) {
-				/* literal/length: at most 15 code bits + 5 extra bits */
-				if (b.cnt < 32u) ngs_inf_refill32(b);
-				uint32_t e = T.lfast[(uint32_t)b.buf & ((1u << NGS_INF_LBITS) - 1u)];
-				if (e & 15u) { b.buf >>= (e & 15u); b.cnt -= (e & 15u); }
-				else { const int s = ngs_inf_decode_slow(b, T.lcount, T.lsym, NGS_INF_LBITS, T.lslow); if (s < 0) return -1; e = ngs_inf_ll_entry((uint32_t)s); }
-				const uint32_t kind = (e >> 8) & 3u;
-				if (kind == NGS_INF_KIND_LIT) { if (pos >= out_len) return -1; out.literal(pos, e >> 16); ++pos; continue; }
-				if (kind != NGS_INF_KIND_VAL) { if (kind == NGS_INF_KIND_EOB) break; return -1; }
-				const uint32_t le = (e >> 4) & 15u;
-				const uint32_t len = (e >> 16) + ((uint32_t)b.buf & ((1u << le) - 1u));
-				b.buf >>= le; b.cnt -= le;
+				/* literal/length: at most 15 code bits + 5 extra bits, all inside one 32-bit peek */
+				uint32_t x = ngs_inf_peek(b);
+				const uint32_t e = T.lfast[x & ((1u << NGS_INF_LBITS) - 1u)];
+				uint32_t cl = e & 15u, sym = e >> 4;
+				if (!cl) { const int s = ngs_inf_decode_slow(x, T.lcount, T.lsym, NGS_INF_LBITS, T.lslow, &cl); if (s < 0) { bad = 1; break; } sym = (uint32_t)s; }
+				if (sym < 256u) {
+					ngs_inf_skip(b, cl);
+					if (pos >= out_len) { bad = 1; break; }
+					out.literal(pos, sym); ++pos;
+					continue;
+				}
+				if (sym == 256u) { ngs_inf_skip(b, cl); break; }
+				const uint32_t le = out.lentry(sym - 257u);
+				const uint32_t len = (le & 0xffffffu) + ((x >> cl) & ((1u << (le >> 24)) - 1u));
+				ngs_inf_skip(b, cl + (le >> 24));
 				/* distance: at most 15 code bits + 13 extra bits */
-				if (b.cnt < 32u) ngs_inf_refill32(b);
-				uint32_t d = T.dfast[(uint32_t)b.buf & ((1u << NGS_INF_DBITS) - 1u)];
-				if (d & 15u) { b.buf >>= (d & 15u); b.cnt -= (d & 15u); }
-				else { const int s = ngs_inf_decode_slow(b, T.dcount, T.dsym, NGS_INF_DBITS, T.dslow); if (s < 0) return -1; d = ngs_inf_d_entry((uint32_t)s); }
-				if (((d >> 8) & 3u) != NGS_INF_KIND_VAL) return -1;
-				const uint32_t de = (d >> 4) & 15u;
-				const uint32_t dist = (d >> 16) + ((uint32_t)b.buf & ((1u << de) - 1u));
-				b.buf >>= de; b.cnt -= de;
-				if (dist > pos || pos + len > out_len) return -1;
+				x = ngs_inf_peek(b);
+				const uint32_t d = T.dfast[x & ((1u << NGS_INF_DBITS) - 1u)];
+				uint32_t cd = d & 15u, ds = d >> 4;
+				if (!cd) { const int s = ngs_inf_decode_slow(x, T.dcount, T.dsym, NGS_INF_DBITS, T.dslow, &cd); if (s < 0) { bad = 1; break; } ds = (uint32_t)s; }
+				const uint32_t de = out.dentry(ds);
+				const uint32_t dist = (de & 0xffffffu) + ((x >> cd) & ((1u << (de >> 24)) - 1u));
+				ngs_inf_skip(b, cd + (de >> 24));
+				if (dist > pos || pos + len > out_len) { bad = 1; break; }      /* also: symbols that must not occur */
 				out.match(pos, len, dist);
 				pos += len;
 			}
+			if (bad) return -1;
 		}
 		if (ngs_inf_consumed(b) > in_len) return -1;               /* ran past the compressed data */
 	} while (!last);

@@ -1662,60 +1662,182 @@ __global__ void __launch_bounds__(NGS_FMT_THREADS, MINB) k_format_bed(const __gr
  * after the literals and copies that produced its source. */
 struct ngs_bgzf_desc { unsigned long long src, dst; uint32_t clen, ulen; };
 
-struct WarpInflateOut {
-	uint8_t *o; int lane;
-	/* a short match is stored one symbol late: its load is issued, the next symbol is decoded while the byte travels,
-	 * and only then does the warp touch the loaded value (the load latency was 29 % of the stall samples) */
-	uint8_t *pend_dst; uint32_t pend_val; bool pend;
-	__device__ __forceinline__ void finish() { if (pend) { if (pend_dst) *pend_dst = (uint8_t)pend_val; pend = false; } }
-	/* the block's Huffman tables are built by lane 0 alone (32 lanes writing the same values to the same shared words is
-	 * harmless but is what compute-sanitizer's racecheck reports); the other lanes take over the bit reader it advanced */
+/* Output policy of one decoder = a group of W lanes (W = 32, 16 or 8: one, two or four decoders per warp).  The lanes
+ * of a group run the decode in lock step on identical values; the groups of a warp work on different BGZF blocks and
+ * share the warp's instruction stream wherever they happen to be at the same point (they reconverge at the head of
+ * the symbol loop), which is where the other lanes of the warp pay off: the decode is a chain of dependent
+ * instructions, and the table size, not the arithmetic, limits how many chains an SM can keep in flight. */
+template <int W>
+struct GroupInflateOut {
+	static constexpr int K = 32 / W;     /* bytes per lane of a deferred match */
+	uint8_t *o; int lane; unsigned gmask; uint32_t ltab, dtab;   /* ltab, dtab: shared-window addresses of the length / distance tables */
+	/* a match of up to 32 bytes is stored one symbol late: its loads are issued, the next symbol is decoded while
+	 * the bytes travel, and only then does the group touch the loaded values */
+	uint32_t pend_pos, pend_len, pend_val;
+	__device__ __forceinline__ uint32_t lentry(uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ltab + 4u * i)); return v; }
+	__device__ __forceinline__ uint32_t dentry(uint32_t j) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(dtab + 4u * j)); return v; }
+	__device__ __forceinline__ void finish()
+	{
+		if (pend_len) {
+			#pragma unroll
+			for (int k = 0; k < K; ++k) { const uint32_t i = (uint32_t)(lane + k * W); if (i < pend_len) o[pend_pos + i] = (uint8_t)(pend_val >> (8 * k)); }
+			pend_len = 0;
+		}
+	}
+	/* the block's Huffman tables are built by the group's first lane alone (all lanes writing the same values to the
+	 * same shared words is harmless but is what compute-sanitizer's racecheck reports); the other lanes take over
+	 * the bit reader it advanced */
 	__device__ __forceinline__ int tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables &T)
 	{
 		int r = 0;
-		__syncwarp();
+		__syncwarp(gmask);
 		if (lane == 0) r = ngs_inf_block_tables(b, btype, T);
-		__syncwarp();
-		r = __shfl_sync(0xffffffffu, r, 0);
-		b.in_pos = __shfl_sync(0xffffffffu, b.in_pos, 0); b.cnt = __shfl_sync(0xffffffffu, b.cnt, 0);
-		b.buf = __shfl_sync(0xffffffffu, b.buf, 0);
+		__syncwarp(gmask);
+		r = __shfl_sync(gmask, r, 0, W);
+		b.w0 = __shfl_sync(gmask, b.w0, 0, W); b.w1 = __shfl_sync(gmask, b.w1, 0, W); b.w2 = __shfl_sync(gmask, b.w2, 0, W);
+		b.bp = __shfl_sync(gmask, b.bp, 0, W); b.nw = __shfl_sync(gmask, b.nw, 0, W);
 		return r;
 	}
 	__device__ __forceinline__ void literal(uint32_t pos, uint32_t b) { if (lane == 0) o[pos] = (uint8_t)b; }
 	__device__ __forceinline__ void match(uint32_t pos, uint32_t len, uint32_t dist)
 	{
 		finish();                       /* the previous match may be this one's source */
-		__syncwarp();
-		const uint8_t *src = o + pos - dist;
+		__syncwarp(gmask);
+		const uint32_t s0 = pos - dist;
 		if (dist >= len) {
-			uint8_t *dst = o + pos;
 			if (len <= 32u) {
-				pend = true; pend_dst = (uint32_t)lane < len ? dst + lane : nullptr;
-				if ((uint32_t)lane < len) pend_val = src[lane];
+				uint32_t v = 0;
+				#pragma unroll
+				for (int k = 0; k < K; ++k) { const uint32_t i = (uint32_t)(lane + k * W); if (i < len) v |= (uint32_t)o[s0 + i] << (8 * k); }
+				pend_val = v; pend_pos = pos; pend_len = len;
 				return;
 			}
-			for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+			for (uint32_t i = lane; i < len; i += W) o[pos + i] = o[s0 + i];
 		}
-		else if (dist == 1u) { const uint8_t v = src[0]; for (uint32_t i = lane; i < len; i += 32) o[pos + i] = v; }
-		else { for (uint32_t i = lane; i < len; i += 32) o[pos + i] = src[i % dist]; }
+		else if (dist == 1u) { const uint8_t v = o[s0]; for (uint32_t i = lane; i < len; i += W) o[pos + i] = v; }
+		else { for (uint32_t i = lane; i < len; i += W) o[pos + i] = o[s0 + i % dist]; }
 	}
 	__device__ __forceinline__ void stored(uint32_t pos, const uint8_t *src, uint32_t len)
 	{
-		for (uint32_t i = lane; i < len; i += 32) o[pos + i] = src[i];
+		for (uint32_t i = lane; i < len; i += W) o[pos + i] = src[i];
 	}
 };
 
-#define NGS_INF_WARPS 4                /* 6.3 KB of tables per warp */
-__global__ void __launch_bounds__(NGS_INF_WARPS * 32) k_bgzf_inflate(const uint8_t *comp, const ngs_bgzf_desc *desc, uint32_t n_blk, uint8_t *out, ngs_dev_state *st)
+#define NGS_INF_WARPS 4
+#ifndef NGS_INF_MINB
+#define NGS_INF_MINB 12                  /* 40 registers: 48 warps per SM (measured best of 1 / 12 / 16) */
+#endif
+#ifndef NGS_INF_LS_MINB
+#define NGS_INF_LS_MINB(S) ((S) == 2 ? 8 : 4)
+#endif
+/* one decoder per group of 32 / S lanes (the library uses S = 1: a warp per BGZF block), NGS_INF_WARPS warps per CTA */
+template <int S>
+__global__ void __launch_bounds__(NGS_INF_WARPS * 32, NGS_INF_MINB) k_bgzf_inflate(const uint8_t *comp, const ngs_bgzf_desc *desc, uint32_t n_blk, uint8_t *out, ngs_dev_state *st)
 {
-	__shared__ ngs_inf_tables s_T[NGS_INF_WARPS];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	for (uint32_t b = blockIdx.x * NGS_INF_WARPS + warp; b < n_blk; b += gridDim.x * NGS_INF_WARPS) {
+	constexpr int W = 32 / S;
+	__shared__ ngs_inf_tables s_T[NGS_INF_WARPS * S];
+	__shared__ uint32_t s_ltab[32], s_dtab[32];
+	if (threadIdx.x < 32) { s_ltab[threadIdx.x] = ngs_inf_len_entry(threadIdx.x); s_dtab[threadIdx.x] = ngs_inf_dist_entry(threadIdx.x); }
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / W;
+	const unsigned gmask = S == 1 ? 0xffffffffu : ((1u << W) - 1u) << (grp * W);
+	const uint32_t first = (blockIdx.x * NGS_INF_WARPS + warp) * S + grp, stride = gridDim.x * NGS_INF_WARPS * S;
+	const uint32_t ltab = (uint32_t)__cvta_generic_to_shared(s_ltab), dtab = (uint32_t)__cvta_generic_to_shared(s_dtab);
+	for (uint32_t b = first; b < n_blk; b += stride) {
 		const ngs_bgzf_desc d = desc[b];
-		WarpInflateOut o = { out + d.dst, lane, nullptr, 0u, false };
-		const long r = ngs_inflate_stream(comp + d.src, d.clen, d.ulen, s_T[warp], o);
-		if (r != (long)d.ulen && lane == 0) atomicOr(&st->flags, NGS_FLAG_EFORMAT);
+		GroupInflateOut<W> o = { out + d.dst, lane % W, gmask, ltab, dtab, 0u, 0u, 0u };
+		const long r = ngs_inflate_stream(comp + d.src, d.clen, d.ulen, s_T[warp * S + grp], o);
+		if (r != (long)d.ulen && o.lane == 0) atomicOr(&st->flags, NGS_FLAG_EFORMAT);
+		__syncwarp(gmask);
+	}
+}
+
+/* The same decoders as a warp-wide state machine: S groups of 32/S lanes, one BGZF block each, and ONE symbol per group
+ * and pass of the loop.  The __syncwarp at the head of the loop brings the groups back together, so the table lookup
+ * and whichever of the two paths (literal / match) the groups share are issued once for all of them: the decode is
+ * bound by instruction issue, and this is how the other lanes of the warp take part in it.  Block headers, table
+ * builds and block changes are passes of their own (rare: one per ~5000 symbols). */
+enum { NGS_LS_OPEN = 0, NGS_LS_HDR = 1, NGS_LS_SYM = 2, NGS_LS_END = 3, NGS_LS_FAIL = 4, NGS_LS_IDLE = 5 };
+template <int S>
+__global__ void __launch_bounds__(NGS_INF_WARPS * 32, NGS_INF_LS_MINB(S)) k_bgzf_inflate_ls(const uint8_t *comp, const ngs_bgzf_desc *desc, uint32_t n_blk, uint8_t *out, ngs_dev_state *st)
+{
+	constexpr int W = 32 / S;
+	__shared__ ngs_inf_tables s_T[NGS_INF_WARPS * S];
+	__shared__ uint32_t s_ltab[32], s_dtab[32];
+	if (threadIdx.x < 32) { s_ltab[threadIdx.x] = ngs_inf_len_entry(threadIdx.x); s_dtab[threadIdx.x] = ngs_inf_dist_entry(threadIdx.x); }
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / W;
+	const unsigned gmask = ((1u << (W - 1)) | ((1u << (W - 1)) - 1u)) << (grp * W);
+	const uint32_t stride = gridDim.x * NGS_INF_WARPS * S;
+	uint32_t blk = (blockIdx.x * NGS_INF_WARPS + warp) * S + grp;
+	ngs_inf_tables &T = s_T[warp * S + grp];
+	GroupInflateOut<W> o = { out, lane % W, gmask, (uint32_t)__cvta_generic_to_shared(s_ltab), (uint32_t)__cvta_generic_to_shared(s_dtab), 0u, 0u, 0u };
+	ngs_inf_bits b; b.wbase = nullptr; b.w0 = b.w1 = b.w2 = b.bp = b.nw = b.lead = b.start = 0;
+	const uint8_t *in = comp;
+	uint32_t in_len = 0, out_len = 0, pos = 0, last = 0;
+	int state = blk < n_blk ? NGS_LS_OPEN : NGS_LS_IDLE;
+	for (;;) {
 		__syncwarp();
+		if (__all_sync(0xffffffffu, state == NGS_LS_IDLE)) break;
+		if (state == NGS_LS_SYM) {
+			uint32_t x = ngs_inf_peek(b);
+			const uint32_t e = T.lfast[x & ((1u << NGS_INF_LBITS) - 1u)];
+			uint32_t cl = e & 15u, sym = e >> 4;
+			if (!cl) { const int s = ngs_inf_decode_slow(x, T.lcount, T.lsym, NGS_INF_LBITS, T.lslow, &cl); if (s < 0) { sym = 256u; cl = 0; state = NGS_LS_FAIL; } else sym = (uint32_t)s; }
+			if (sym < 256u) {
+				ngs_inf_skip(b, cl);
+				if (pos >= out_len) state = NGS_LS_FAIL;
+				else { o.literal(pos, sym); ++pos; }
+			} else if (sym == 256u) {
+				if (state != NGS_LS_FAIL) {
+					ngs_inf_skip(b, cl);
+					state = ngs_inf_consumed(b) > in_len ? NGS_LS_FAIL : (last ? NGS_LS_END : NGS_LS_HDR);
+				}
+			} else {
+				const uint32_t le = o.lentry(sym - 257u);
+				const uint32_t len = (le & 0xffffffu) + ((x >> cl) & ((1u << (le >> 24)) - 1u));
+				ngs_inf_skip(b, cl + (le >> 24));
+				x = ngs_inf_peek(b);
+				const uint32_t d = T.dfast[x & ((1u << NGS_INF_DBITS) - 1u)];
+				uint32_t cd = d & 15u, ds = d >> 4;
+				if (!cd) { const int s = ngs_inf_decode_slow(x, T.dcount, T.dsym, NGS_INF_DBITS, T.dslow, &cd); if (s < 0) { ds = 31u; cd = 0; } else ds = (uint32_t)s; }
+				const uint32_t de = o.dentry(ds);
+				const uint32_t dist = (de & 0xffffffu) + ((x >> cd) & ((1u << (de >> 24)) - 1u));
+				ngs_inf_skip(b, cd + (de >> 24));
+				if (dist > pos || pos + len > out_len) state = NGS_LS_FAIL;    /* also: symbols that must not occur */
+				else { o.match(pos, len, dist); pos += len; }
+			}
+		} else if (state == NGS_LS_HDR) {
+			const uint32_t hdr = ngs_inf_get(b, 3);
+			last = hdr & 1u;
+			const uint32_t btype = hdr >> 1;
+			if (btype == 0u) {
+				ngs_inf_skip(b, (8u - (b.bp & 7u)) & 7u);
+				const uint32_t len = ngs_inf_get(b, 16), nlen = ngs_inf_get(b, 16);
+				const uint32_t at = ngs_inf_consumed(b);
+				if ((len ^ nlen) != 0xffffu || at + len > in_len || pos + len > out_len) state = NGS_LS_FAIL;
+				else {
+					o.finish();
+					__syncwarp(gmask);
+					o.stored(pos, in + at, len);
+					__syncwarp(gmask);
+					pos += len;
+					ngs_inf_open(b, in, at + len);
+					state = last ? NGS_LS_END : NGS_LS_HDR;
+				}
+			} else if (btype == 3u) state = NGS_LS_FAIL;
+			else state = o.tables(b, btype, T) ? NGS_LS_FAIL : NGS_LS_SYM;
+		} else if (state == NGS_LS_OPEN) {
+			const ngs_bgzf_desc d = desc[blk];
+			in = comp + d.src; in_len = d.clen; out_len = d.ulen; o.o = out + d.dst; o.pend_len = 0; pos = 0; last = 0;
+			ngs_inf_open(b, in, 0u);
+			state = NGS_LS_HDR;
+		} else if (state != NGS_LS_IDLE) {                       /* NGS_LS_END, NGS_LS_FAIL */
+			o.finish();
+			if ((state == NGS_LS_FAIL || pos != out_len) && o.lane == 0) atomicOr(&st->flags, NGS_FLAG_EFORMAT);
+			blk += stride;
+			state = blk < n_blk ? NGS_LS_OPEN : NGS_LS_IDLE;
+		}
 	}
 }
 

@@ -131,6 +131,10 @@ class CoverageEngine:
             return m
         return (1 << OUT_WIG) | (1 << OUT_CHROMSIZE)
 
+    def set_region(self, ref, beg, end):
+        """slide mode: count only what bam_fetch(ref, beg, end) hands out (`-r` of bam_sliding_count); ref < 0 clears"""
+        self._check(self.lib.ngscov_set_region(self.h, int(ref), int(beg), int(end)), "ngscov_set_region")
+
     def reset(self):
         self._check(self.lib.ngscov_reset(self.h), "ngscov_reset")
 
@@ -145,6 +149,8 @@ class CoverageEngine:
     def output(self, which):
         p, n = C.c_void_p(), C.c_size_t()
         self._check(self.lib.ngscov_output(self.h, which, C.byref(p), C.byref(n)), "ngscov_output")
+        if n.value >= 1 << 31:                 # ctypes.string_at takes a C int
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,)).tobytes()
         return C.string_at(p, n.value) if n.value else b""
 
     def output_view(self, which):

@@ -2,8 +2,10 @@
  *
  * Kept from the reference main (reference bam_sliding_count.c:333-435): getopt string "o:w:r:s:h?", defaults
  * (-o "out", -w 20000), atoi parsing, the table <outfile>.txt (output_count_GC, :140-165: first input file only, as the
- * reference prints `databuf`, not `databuf + i`), the progress lines on stderr including the read count.  Not produced:
- * <bam>_hits.png (draw_hits needs libgd, :276-331) and the -r region mode (:393-409), which exits with a message.
+ * reference prints `databuf`, not `databuf + i`), the progress lines on stderr including the read count, and the -r
+ * region mode (:393-409: the region line on stdout, the .bai must exist, only what bam_fetch hands out is counted --
+ * here the whole file still goes through the GPU and ngscov_set_region filters on the device).  Not produced:
+ * <bam>_hits.png (draw_hits needs libgd, :276-331).
  * The BAM file goes to the device compressed (ngscov_push_bgzf); record framing, SEQ GC counting and the per-window
  * sums run on the GPU, the O(windows) float post-processing of calc_winGC and the printing on the host. */
 #define _GNU_SOURCE
@@ -29,10 +31,67 @@ static void usage(const char *prog)
 	        "  B200-native drop-in for the HighPerformanceNGS bam_sliding_count tool: reads count and GC content per window.\n"
 	        "   [-o OUTPUT_FILE]  = output prefix (<prefix>.txt), default out.      [option]\n"
 	        "   [-w WINDOW_SIZE]  = window size, default 20000.                     [option]\n"
-	        "   [-r]              = region mode of the reference: not supported.     [option]\n"
+	        "   [-r]              = region, default is whole genome.(chr1:1-20000) [option]\n"
 	        "   [-s]              = accepted and ignored, like the reference.       [option]\n"
 	        "   Infiles           = BAM file(s); the table is that of the first.    [required]\n\n", prog);
 	exit(1);
+}
+
+/* bam_parse_region (samtools-0.1.19 bam_aux.c) restated: white space removed, the name ends at the last colon if what
+ * follows is digits, commas and at most one hyphen (otherwise the whole string is the name; a name that is not in the
+ * header is tried as the whole string as well); "beg-end" is 1-based inclusive -> beg - 1, end; no interval = the
+ * whole contig [0, 1<<29).  Returns the refID or -1. */
+static int find_ref(char **ref_name, int n_ref, const char *s)
+{
+	for (int i = 0; i < n_ref; ++i) if (!strcmp(ref_name[i], s)) return i;
+	return -1;
+}
+static int parse_region(char **ref_name, int n_ref, const char *str, int *beg, int *end)
+{
+	int l = (int)strlen(str), k = 0, i, name_end, ref;
+	char *s = (char *)malloc((size_t)l + 1);
+	*beg = *end = -1;
+	for (i = 0; i < l; ++i) if (!(str[i] == ' ' || (str[i] >= 9 && str[i] <= 13))) s[k++] = str[i];
+	s[k] = 0; l = k; name_end = l;
+	for (i = l - 1; i >= 0; --i) if (s[i] == ':') break;
+	if (i >= 0) name_end = i;
+	if (name_end < l) {
+		int n_hyphen = 0;
+		for (i = name_end + 1; i < l; ++i) {
+			if (s[i] == '-') ++n_hyphen;
+			else if (!(s[i] >= '0' && s[i] <= '9') && s[i] != ',') break;
+		}
+		if (i < l || n_hyphen > 1) name_end = l;
+		s[name_end] = 0;
+		ref = find_ref(ref_name, n_ref, s);
+		if (ref < 0) {
+			ref = find_ref(ref_name, n_ref, str);
+			if (ref < 0) { free(s); return -1; }
+			s[name_end] = ':'; name_end = l;
+		}
+	} else ref = find_ref(ref_name, n_ref, str);
+	if (ref < 0) { free(s); return -1; }
+	if (name_end < l) {
+		for (i = k = name_end + 1; i < l; ++i) if (s[i] != ',') s[k++] = s[i];
+		s[k] = 0;
+		*beg = atoi(s + name_end + 1);
+		for (i = name_end + 1; i != k; ++i) if (s[i] == '-') break;
+		*end = i < k ? atoi(s + i + 1) : 1 << 29;
+		if (*beg > 0) --*beg;
+	} else { *beg = 0; *end = 1 << 29; }
+	free(s);
+	return ref;
+}
+static int have_index(const char *fn)
+{
+	/* bam_index_load_local (samtools bam_index.c): fn.bai, else fn with its "bam" ending turned into "bai" */
+	char *p = (char *)malloc(strlen(fn) + 8);
+	int ok;
+	sprintf(p, "%s.bai", fn);
+	ok = access(p, R_OK) == 0;
+	if (!ok) { const size_t l = strlen(fn); if (l > 3 && !strcmp(fn + l - 3, "bam")) { strcpy(p, fn); strcpy(p + l - 3, "bai"); ok = access(p, R_OK) == 0; } }
+	free(p);
+	return ok;
 }
 
 int main(int argc, char *argv[])
@@ -49,7 +108,6 @@ int main(int argc, char *argv[])
 		default: fprintf(stderr, "error parameter!\n"); break;
 		}
 	}
-	if (strncmp(region, "-", 6) != 0) DIE("bam_sliding_count: the -r region mode is not supported by the GPU build\n");
 	if (optind >= argc) usage(argv[0]);
 	if (window < 1) DIE("bam_sliding_count: bad window size\n");
 	const long long begin = usec();
@@ -110,6 +168,15 @@ int main(int argc, char *argv[])
 	ngscov_t *h = NULL;
 	int rc = ngscov_create(&h, &cfg);
 	if (rc) DIE("bam2bed: GPU engine unavailable: %s\n", ngscov_strerror(rc));
+	if (strncmp(region, "-", 6) != 0) {                              /* the reference's test for "no region" (:389) */
+		int ref, rbeg, rend;
+		if (!have_index(fn)) { fprintf(stderr, "bam2bed: BAM indexing file is not available.\n"); return 1; }
+		ref = parse_region(ref_name, n_ref, region, &rbeg, &rend);
+		if (ref < 0) { fprintf(stderr, "bam2bed: Invalid region %s\n", region); return 1; }
+		fprintf(stdout, "%s\t%d\t%d\n", ref_name[ref], rbeg, rend);
+		fflush(stdout);
+		if ((rc = ngscov_set_region(h, ref, rbeg, rend))) DIE("bam2bed: %s\n", ngscov_strerror(rc));
+	}
 	if ((rc = ngscov_push_bgzf(h, file, end, hdr_len, NGSCOV_PUSH_LAST))) DIE("bam2bed: %s: %s (%s)\n", fn, ngscov_strerror(rc), ngscov_last_cuda_error(h));
 	if ((rc = ngscov_finish(h))) DIE("bam2bed: %s: %s (%s)\n", fn, ngscov_strerror(rc), ngscov_last_cuda_error(h));
 	fprintf(stderr, "Done load bam file %s at %.3f s\n", fn, (double)(usec() - begin) / 1e6);

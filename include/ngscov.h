@@ -173,6 +173,13 @@ int ngscov_slice_done(ngscov_t *h, int *done);
  * exist and the text is on its way to the host).  Non-blocking; used by the drivers for the reference's per-contig
  * progress line (bam2depth.c:338).  Equals n_ref after ngscov_finish_runs. */
 int ngscov_contigs_done(ngscov_t *h, uint32_t *n);
+
+/* NGSCOV_MODE_SLIDE only: the `-r chr:beg-end` mode of bam_sliding_count (bam_sliding_count.c:393-409).  Only the records
+ * bam_fetch(ref, beg, end) would hand to fetch_func are counted: refID == ref, POS < end and the alignment's end > beg
+ * (samtools-0.1.19 bam_index.c: bam_iter_read / is_overlap; beg is 0-based, end exclusive, as bam_parse_region yields
+ * them).  Call before the first push; ref < 0 clears the region; it survives ngscov_reset.  NGSCOV_EINVAL in the other
+ * modes or for a refID outside the header, NGSCOV_ESTATE once data has been pushed. */
+int ngscov_set_region(ngscov_t *h, int ref, int beg, int end);
 int ngscov_halo_get(ngscov_t *h, ngscov_halo *halo);
 int ngscov_halo_put(ngscov_t *h, int drop_first, uint32_t new_last_end);
 

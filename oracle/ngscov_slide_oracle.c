@@ -35,8 +35,20 @@ static void sb_printf(sbuf *b, const char *fmt, ...)
 
 /* records: the inflated BAM record stream.  out: malloc'ed text of <outfile>.txt.  n_count: reads counted (:107).
  * Returns 0, -1 on a malformed stream. */
+int ngscov_oracle_slide_region(const uint8_t *rec, size_t nbytes, int n_ref, const uint32_t *ref_len, const char *const *ref_name,
+                               int window, int reg_ref, int reg_beg, int reg_end, char **out, size_t *out_len, uint64_t *n_count);
 int ngscov_oracle_slide(const uint8_t *rec, size_t nbytes, int n_ref, const uint32_t *ref_len, const char *const *ref_name,
                         int window, char **out, size_t *out_len, uint64_t *n_count)
+{
+	return ngscov_oracle_slide_region(rec, nbytes, n_ref, ref_len, ref_name, window, -1, 0, 0, out, out_len, n_count);
+}
+
+/* The same with the `-r` mode (bam_sliding_count.c:393-409): only what bam_fetch(reg_ref, reg_beg, reg_end) hands to
+ * fetch_func is counted.  On a coordinate-sorted file that is every record with tid == reg_ref, (uint32) pos < end and
+ * (uint32) rend > beg, rend = bam_calend (reference-consuming CIGAR operations) or pos + 1 without a CIGAR
+ * (samtools-0.1.19 bam_index.c bam_iter_read / is_overlap).  reg_ref < 0: no region. */
+int ngscov_oracle_slide_region(const uint8_t *rec, size_t nbytes, int n_ref, const uint32_t *ref_len, const char *const *ref_name,
+                               int window, int reg_ref, int reg_beg, int reg_end, char **out, size_t *out_len, uint64_t *n_count)
 {
 	uint32_t *windows = (uint32_t *)calloc((size_t)n_ref + 1, sizeof(uint32_t));
 	unsigned int **bins = (unsigned int **)calloc((size_t)n_ref + 1, sizeof(*bins)), **len = (unsigned int **)calloc((size_t)n_ref + 1, sizeof(*len));
@@ -55,6 +67,19 @@ int ngscov_oracle_slide(const uint8_t *rec, size_t nbytes, int n_ref, const uint
 		memcpy(&tid, r, 4); memcpy(&pos, r + 4, 4); memcpy(&bin_mq_nl, r + 8, 4); memcpy(&flag_nc, r + 12, 4); memcpy(&l_qseq, r + 16, 4);
 		o += 4 + (size_t)bs;
 		const uint32_t l_qname = bin_mq_nl & 0xff, n_cigar = flag_nc & 0xffff, flag = flag_nc >> 16;
+		if (reg_ref >= 0) {
+			if (tid != reg_ref || (uint32_t)pos >= (uint32_t)reg_end) continue;
+			uint32_t rend = (uint32_t)pos + 1;
+			if (n_cigar) {
+				int end = pos;
+				for (uint32_t k = 0; k < n_cigar; ++k) {
+					uint32_t w; memcpy(&w, r + 32 + l_qname + 4 * (size_t)k, 4);
+					if ((0x3C1A7 >> ((w & 0xf) << 1)) & 2) end += (int)(w >> 4);
+				}
+				rend = (uint32_t)end;
+			}
+			if (!(rend > (uint32_t)reg_beg)) continue;
+		}
 		if (tid < 0) continue;                                        /* :96 */
 		if (flag & 4) continue;                                       /* :97 BAM_FUNMAP */
 		if (tid >= n_ref) { rc = -1; break; }

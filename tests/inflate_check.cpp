@@ -20,6 +20,8 @@ struct SeqOut {
 	void stored(uint32_t pos, const uint8_t *src, uint32_t len) { memcpy(o + pos, src, len); }
 	void finish() {}
 	int tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables &T) { return ngs_inf_block_tables(b, btype, T); }
+	uint32_t lentry(uint32_t i) { return ngs_inf_len_entry(i); }
+	uint32_t dentry(uint32_t j) { return ngs_inf_dist_entry(j); }
 };
 /* the lane-parallel copy rule of the kernel: byte i of a match comes from pos - dist + (i % dist), all old bytes */
 struct ParOut {
@@ -34,6 +36,8 @@ struct ParOut {
 	void stored(uint32_t pos, const uint8_t *src, uint32_t len) { memcpy(o + pos, src, len); }
 	void finish() {}
 	int tables(ngs_inf_bits &b, uint32_t btype, ngs_inf_tables &T) { return ngs_inf_block_tables(b, btype, T); }
+	uint32_t lentry(uint32_t i) { return ngs_inf_len_entry(i); }
+	uint32_t dentry(uint32_t j) { return ngs_inf_dist_entry(j); }
 };
 
 static std::vector<uint8_t> deflate_raw(const std::vector<uint8_t> &in, int level, int strategy)
@@ -53,7 +57,7 @@ static int check_stream(const uint8_t *comp, size_t clen, const uint8_t *exp, si
 	static ngs_inf_tables T;
 	std::vector<uint8_t> a(ulen + 8, 0xEE), b(ulen + 8, 0xEE);
 	SeqOut so = { a.data() }; ParOut po = { b.data() };
-	std::vector<uint8_t> padded(clen + 16, 0xA7);              /* the decoder may read up to 7 bytes past the stream */
+	std::vector<uint8_t> padded(clen + 20, 0xA7);              /* the decoder may read up to 15 bytes past the stream */
 	uint8_t *cp = padded.data() + (clen % 3);                  /* and must cope with any alignment */
 	memcpy(cp, comp, clen);
 	const long ra = ngs_inflate_stream(cp, (uint32_t)clen, (uint32_t)ulen, T, so);

@@ -25,6 +25,8 @@ def lib():
         l.ngscov_oracle_free.argtypes = [C.POINTER(Result)]
         l.ngscov_oracle_slide.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_char_p), C.c_int,
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
+        l.ngscov_oracle_slide_region.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_char_p), C.c_int,
+                                                 C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
         l.ngscov_oracle_slide_free.argtypes = [C.c_void_p]
         _lib = l
     return _lib
@@ -48,14 +50,17 @@ def run(records, names, lens, mode, window, emit_wig=True):
     return out
 
 
-def slide(records, names, lens, window):
-    """bam_sliding_count restated (oracle/ngscov_slide_oracle.c) -> dict(txt: bytes of <outfile>.txt, n_count)."""
+def slide(records, names, lens, window, region=None):
+    """bam_sliding_count restated (oracle/ngscov_slide_oracle.c) -> dict(txt: bytes of <outfile>.txt, n_count).
+    region = (refID, beg, end) as bam_parse_region yields them: the `-r` mode."""
     rec = np.ascontiguousarray(records, dtype=np.uint8)
     n = len(names)
     nm = (C.c_char_p * max(n, 1))(*[x if isinstance(x, bytes) else x.encode() for x in names])
     ln = (C.c_uint32 * max(n, 1))(*[int(x) for x in lens])
     p, m, cnt = C.c_void_p(), C.c_size_t(), C.c_uint64()
-    rc = lib().ngscov_oracle_slide(rec.ctypes.data, rec.size, n, ln, nm, int(window), C.byref(p), C.byref(m), C.byref(cnt))
+    rr = region if region is not None else (-1, 0, 0)
+    rc = lib().ngscov_oracle_slide_region(rec.ctypes.data, rec.size, n, ln, nm, int(window), int(rr[0]), int(rr[1]), int(rr[2]),
+                                          C.byref(p), C.byref(m), C.byref(cnt))
     if rc:
         raise RuntimeError(f"slide oracle failed: {rc}")
     out = C.string_at(p, m.value) if m.value else b""

@@ -14,6 +14,16 @@ CASES = [
     ("c5_s0.02_onewindow", "gen", (5, 0.02), [200000000, 20000]),
 ]
 
+# the `-r` mode: (case name, window, region string, (refID, beg, end) as bam_parse_region yields them)
+REGION_CASES = [
+    ("random1", 150, "c1:1000-5000", (0, 999, 5000)),
+    ("random1", 20000, "c3", (2, 0, 1 << 29)),
+    ("random3", 33, "c1:2,001-2,500", (0, 2000, 2500)),
+    ("random3", 1000, "c3:69000", (2, 68999, 1 << 29)),
+    ("c1_s0.05", 777, "chr1:1-20000", (0, 0, 20000)),
+    ("c2_s0.0005", 20000, "chr2:30000-90000", (1, 29999, 90000)),
+]
+
 
 def case_input(kind, params):
     """-> (names, lens, records uint8 array, generator or None), records WITH SEQ"""

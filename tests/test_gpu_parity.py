@@ -195,12 +195,15 @@ def test_nine_digit_positions_and_name_lengths(oracle, monkeypatch, fmt):
     assert b"\t100000" in got["bedgraph"] and b"\t99999" in got["bedgraph"]
 
 
+@pytest.mark.parametrize("decoders", [1, 2])
 @pytest.mark.parametrize("staging", [0, 300000])
 @pytest.mark.parametrize("case", ["random", "c2", "c4", "c5", "stored"])
-def test_device_bgzf_inflate(oracle, tmp_path, case, staging):
+def test_device_bgzf_inflate(oracle, tmp_path, monkeypatch, case, staging, decoders):
     """ngscov_push_bgzf: the BAM file's compressed blocks are inflated on the device (one warp per block) and feed the
     same pipeline; outputs must equal the oracle's on the host-inflated stream.  `stored` = level-0 BGZF (stored
-    deflate blocks), `random` = zlib level 6 from Python (dynamic blocks), generator files = level 1."""
+    deflate blocks), `random` = zlib level 6 from Python (dynamic blocks), generator files = level 1.  decoders = 2:
+    the opt-in kernel that runs two decoders per warp as a warp-wide state machine (NGSCOV_INF_S=2)."""
+    monkeypatch.setenv("NGSCOV_INF_S", str(decoders))
     from highperformancengs_b200 import CoverageEngine, bamio
     from highperformancengs_b200.gen import Generator
     bam = str(tmp_path / "x.bam")
@@ -240,8 +243,10 @@ def test_device_bgzf_inflate(oracle, tmp_path, case, staging):
     assert got["stats"]["ms_inflate"] > 0
 
 
-def test_device_bgzf_inflate_rejects_corrupt_block(tmp_path):
+@pytest.mark.parametrize("decoders", [1, 2])
+def test_device_bgzf_inflate_rejects_corrupt_block(tmp_path, monkeypatch, decoders):
     from highperformancengs_b200 import CoverageEngine, NgscovError, bamio
+    monkeypatch.setenv("NGSCOV_INF_S", str(decoders))
     names, lens, reads = bamutil.random_case(32, n_reads=3000)
     bam = str(tmp_path / "x.bam")
     bamutil.write_bam(bam, names, lens, bamutil.records(reads), index=False)

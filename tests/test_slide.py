@@ -14,7 +14,11 @@ from tests import bamutil, slide_cases
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "slide_outputs.json")))
+RGOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "slide_region_outputs.json")))
 PARAMS = [(n, k, p, w) for n, k, p, ws in slide_cases.CASES for w in ws]
+_BY_NAME = {c[0]: c for c in slide_cases.CASES}
+RPARAMS = [(n, _BY_NAME[n][1], _BY_NAME[n][2], w, r, parsed) for n, w, r, parsed in slide_cases.REGION_CASES]
+RIDS = [f"{p[0]}-{p[3]}-{p[4]}" for p in RPARAMS]
 IDS = [f"{p[0]}-{p[3]}" for p in PARAMS]
 _cache = {}
 
@@ -46,6 +50,19 @@ def test_oracle_matches_reference_outputs(oracle, name, kind, params, window):
     check_gold(got["txt"], got["n_count"], f"{name}|{window}")
 
 
+@pytest.mark.parametrize("name,kind,params,window,region,parsed", RPARAMS, ids=RIDS)
+def test_oracle_region_mode_matches_reference_outputs(oracle, name, kind, params, window, region, parsed):
+    """`-r`: only what bam_fetch hands out is counted (bam_sliding_count.c:393-409)"""
+    names, lens, recs, g = _input(name, kind, params)
+    got = oracle.slide(recs, names, lens, window, region=parsed)
+    g = RGOLD[f"{name}|{window}|{region}"]
+    assert (len(got["txt"]), hashlib.md5(got["txt"]).hexdigest(), got["n_count"]) == (g["size"], g["md5"], g["n_count"])
+
+
+def test_region_gold_covers_every_case():
+    assert set(RGOLD) == {f"{p[0]}|{p[3]}|{p[4]}" for p in RPARAMS}
+
+
 def test_oracle_vs_reference_binary(oracle, tmp_path):
     ref = os.path.join(ROOT, "oracle", "_ref", "bam_sliding_count")
     if not os.path.exists(ref):
@@ -59,9 +76,34 @@ def test_oracle_vs_reference_binary(oracle, tmp_path):
         assert open(str(tmp_path / "o.txt"), "rb").read() == oracle.slide(recs, names, lens, w)["txt"]
 
 
-def run_engine(names, lens, recs, window, staging_bytes=0):
+EDGE_READS = [(0, 100, 0, "50M"), (0, 900, 0, "100M"), (0, 901, 0, "100M"), (0, 950, 16, "10M2000N40M"), (0, 990, 0, "5S10M"), (0, 999, 0, "*"),
+              (0, 1000, 0, "*"), (0, 1000, 0, "20M"), (0, 1001, 4, "20M"), (0, 1200, 0, "70000M"), (0, 1499, 0, "30M"), (0, 1500, 0, "30M"),
+              (0, 400, 0, "66000M"), (1, 1100, 0, "50M")]
+
+
+def test_oracle_region_edges_vs_reference_binary(oracle, tmp_path):
+    """reads that start before the region and reach into it, end exactly at its first base, have no CIGAR"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "bam_sliding_count")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/bam_sliding_count not built (needs /root/reference)")
+    names, lens = [b"a", b"b"], [200000, 5000]
+    recs = bamutil.records(sorted(EDGE_READS, key=lambda r: (r[0], r[1])), seq=True, seq_seed=3)
+    bam = str(tmp_path / "t.bam")
+    bamutil.write_bam(bam, names, lens, recs, index=True)
+    for region, parsed in [("a:1001-1500", (0, 1000, 1500)), ("a:1000-1001", (0, 999, 1001)), ("a", (0, 0, 1 << 29)), ("b:2001-3000", (1, 2000, 3000)),
+                           ("a:951-951", (0, 950, 951)), ("a:70401", (0, 70400, 1 << 29))]:
+        r = subprocess.run([ref, "-o", str(tmp_path / "o"), "-w", "100", "-r", region, bam], capture_output=True, text=True, cwd=str(tmp_path))
+        assert r.returncode == 0
+        exp = oracle.slide(recs, names, lens, 100, region=parsed)
+        assert open(str(tmp_path / "o.txt"), "rb").read() == exp["txt"], region
+        assert int([ln for ln in r.stderr.splitlines() if ln.strip().isdigit()][0]) == exp["n_count"], region
+
+
+def run_engine(names, lens, recs, window, staging_bytes=0, region=None):
     from highperformancengs_b200 import CoverageEngine
     with CoverageEngine(names, lens, mode=2, window=window, staging_bytes=staging_bytes) as eng:
+        if region is not None:
+            eng.set_region(*region)
         eng.push_host(recs, last=True)
         eng.finish()
         return eng.output(4), eng.stats()
@@ -73,6 +115,35 @@ def test_engine_matches_reference_outputs(name, kind, params, window):
     names, lens, recs, g = _input(name, kind, params)
     txt, st = run_engine(names, lens, recs, window)
     check_gold(txt, st["kept"], f"{name}|{window}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kind,params,window,region,parsed", RPARAMS, ids=RIDS)
+def test_engine_region_mode_matches_reference_outputs(name, kind, params, window, region, parsed):
+    names, lens, recs, g = _input(name, kind, params)
+    txt, st = run_engine(names, lens, recs, window, region=parsed)
+    g = RGOLD[f"{name}|{window}|{region}"]
+    assert (len(txt), hashlib.md5(txt).hexdigest(), st["kept"]) == (g["size"], g["md5"], g["n_count"])
+
+
+@pytest.mark.gpu
+def test_engine_region_mode_edges(oracle):
+    """reads that start before the region and reach into it, end exactly at its first base, have no CIGAR, are too long
+    for a table entry (sequential path), and set_region after a push"""
+    from highperformancengs_b200 import CoverageEngine, NgscovError
+    names, lens = [b"a", b"b"], [200000, 5000]
+    recs = bamutil.records(sorted(EDGE_READS, key=lambda r: (r[0], r[1])), seq=True, seq_seed=3)
+    for region in [(0, 1000, 1500), (0, 999, 1001), (0, 0, 1 << 29), (1, 0, 1 << 29), (1, 2000, 3000), (0, 950, 951), (0, 70400, 1 << 29)]:
+        exp = oracle.slide(recs, names, lens, 100, region=region)
+        txt, st = run_engine(names, lens, recs, 100, region=region)
+        assert txt == exp["txt"] and st["kept"] == exp["n_count"], region
+    with CoverageEngine(names, lens, mode=2, window=100) as eng:
+        eng.push_host(recs, last=False)
+        with pytest.raises(NgscovError):
+            eng.set_region(0, 0, 10)
+    with CoverageEngine(names, lens, mode=0, window=100) as eng:
+        with pytest.raises(NgscovError):
+            eng.set_region(0, 0, 10)
 
 
 @pytest.mark.gpu
@@ -107,5 +178,16 @@ def test_c_driver_bam_sliding_count(tmp_path):
         assert r.returncode == 0, r.stderr
         n_count = int([ln for ln in r.stderr.splitlines() if ln.strip().isdigit()][0])
         check_gold(open(str(tmp_path / "o.txt"), "rb").read(), n_count, f"{name}|{w}")
+    # -r: the reference insists on the index, prints the parsed region on stdout and counts what bam_fetch hands out
     r = subprocess.run([exe, "-o", "o", "-r", "chr1:1-100", bam], cwd=str(tmp_path), capture_output=True, text=True)
-    assert r.returncode == 1 and "not supported" in r.stderr
+    assert r.returncode == 1 and "BAM indexing file is not available" in r.stderr
+    bamutil.write_bam(bam, names, lens, recs, index=True)
+    rn, rw, region, parsed = [c for c in slide_cases.REGION_CASES if c[0] == name][0]
+    r = subprocess.run([exe, "-o", "o", "-w", str(rw), "-r", region, bam], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    g = RGOLD[f"{name}|{rw}|{region}"]
+    txt = open(str(tmp_path / "o.txt"), "rb").read()
+    assert r.stdout == g["stdout"] and hashlib.md5(txt).hexdigest() == g["md5"]
+    assert int([ln for ln in r.stderr.splitlines() if ln.strip().isdigit()][0]) == g["n_count"]
+    r = subprocess.run([exe, "-o", "o", "-r", "nosuchcontig:5-9", bam], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 1 and "Invalid region" in r.stderr
