@@ -23,7 +23,7 @@ struct ngscov {
 	std::vector<std::string> ref_name;
 	int device;
 	cudaStream_t s_main, s_copy;
-	cudaEvent_t ev_h2d[2], ev_verified, ev_finalized, ev_t0, ev_t1;
+	cudaEvent_t ev_h2d[2], ev_verified, ev_finalized, ev_t0, ev_t1, ev_cov0, ev_cov1;
 	char cuda_err[256];
 
 	/* geometry */
@@ -104,6 +104,7 @@ struct ngscov {
 	bool bed_patched;
 	/* NGSCOV_MODE_SLIDE (bam_sliding_count) */
 	int reg_ref, reg_beg, reg_end;     /* ngscov_set_region (slide mode); reg_ref < 0: none */
+	bool cov_pending; uint64_t cov_t0, cov_t1;   /* a cover launch whose counters have not been read back yet (cover_harvest) */
 	bool slide; unsigned int *d_sl_cnt, *d_sl_len, *d_sl_ctg; unsigned long long *d_sl_gc, *d_sl_ncount; uint32_t *d_sl_nwin;
 	std::string slide_text; unsigned long long slide_ncount;
 	long long *d_halo;                       /* the shard's running halo record (device), see k_halo_gather */
@@ -114,7 +115,7 @@ struct ngscov {
 	int sm_count;
 	/* per-push timing events (start/end pairs), reused across inputs */
 	std::vector<cudaEvent_t> ev_ing, ev_cp, ev_inf, ev_k2; size_t n_ing, n_cp, n_inf, n_k2;
-	uint8_t *d_comp[2]; size_t comp_cap[2]; ngs_bgzf_desc *d_desc[2]; size_t desc_cap[2];   /* BGZF blocks awaiting the device inflate */
+	uint8_t *d_comp[2]; size_t comp_cap[2]; ngs_bgzf_desc *d_desc[2], *h_desc[2];   /* BGZF blocks awaiting the device inflate (h_desc: pinned) */
 };
 
 static cudaEvent_t next_event(std::vector<cudaEvent_t> &pool, size_t &used)
@@ -252,7 +253,7 @@ static int create_impl(ngscov_t **out, const ngscov_cfg *cfg)
 	for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&h->ev_verified, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&h->ev_finalized, cudaEventDisableTiming));
-	CK(cudaEventCreate(&h->ev_t0)); CK(cudaEventCreate(&h->ev_t1));
+	CK(cudaEventCreate(&h->ev_t0)); CK(cudaEventCreate(&h->ev_t1)); CK(cudaEventCreate(&h->ev_cov0)); CK(cudaEventCreate(&h->ev_cov1));
 	CK(cudaFuncSetAttribute(k_ingest_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)NGS_TILE_THREADS << 10) + NGS_TILE_MARGIN)));
 	CK(cudaFuncSetAttribute(k_ingest_tiles2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)NGS_T2_SUB << 10) + NGS_TILE_MARGIN + ((size_t)NGS_T2_SUB << 5) * 2)));
 	build_geometry(h);
@@ -393,10 +394,12 @@ extern "C" void ngscov_destroy(ngscov_t *h)
 	if (h->ev_finalized) cudaEventDestroy(h->ev_finalized);
 	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
 	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+	if (h->ev_cov0) cudaEventDestroy(h->ev_cov0);
+	if (h->ev_cov1) cudaEventDestroy(h->ev_cov1);
 	for (cudaEvent_t e : h->ev_ing) cudaEventDestroy(e);
 	for (cudaEvent_t e : h->ev_inf) cudaEventDestroy(e);
 	for (cudaEvent_t e : h->ev_k2) cudaEventDestroy(e);
-	for (int i = 0; i < 2; ++i) { if (h->d_comp[i]) cudaFree(h->d_comp[i]); if (h->d_desc[i]) cudaFree(h->d_desc[i]); }
+	for (int i = 0; i < 2; ++i) { if (h->d_comp[i]) cudaFree(h->d_comp[i]); if (h->d_desc[i]) cudaFree(h->d_desc[i]); if (h->h_desc[i]) cudaFreeHost(h->h_desc[i]); }
 	for (cudaEvent_t e : h->ev_cp) cudaEventDestroy(e);
 	delete h;
 }
@@ -406,6 +409,7 @@ extern "C" int ngscov_reset(ngscov_t *h)
 	if (!h) return NGSCOV_EINVAL;
 	CK(cudaSetDevice(h->device));
 	CK(cudaStreamSynchronize(h->s_main)); CK(cudaStreamSynchronize(h->s_copy));
+	h->cov_pending = false;
 	if (h->diff_dirty) {            /* pushes were made but the scan (which re-zeroes) never ran */
 		tic(h);
 		if (h->d_far_flag) CK(cudaMemsetAsync(h->d_far_flag, 0, std::max<uint64_t>(1, h->n_tiles) * NGS_CPT * 4, h->s_main));
@@ -839,16 +843,27 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 	CK(cudaSetDevice(h->device));
 	int r;
 	if ((r = ensure_chunk(h, 0)) || (r = ensure_chunk(h, 1))) return r;
-	/* block table and chunk plan: whole blocks, at most stage_cap inflated bytes per chunk */
+	/* Chunk plan: whole blocks, at most stage_cap inflated bytes (and desc_blocks blocks) per chunk.  The host only reads
+	 * each block's BSIZE and ISIZE, but that is one dependent cache miss per block over the whole file: the plan of chunk
+	 * k+1 is therefore made while the GPU inflates chunk k (it used to be made for the whole file first: 60-100 ms
+	 * before the first kernel on the 30x BAM).  Descriptors are written straight into pinned memory. */
 	const uint8_t *src = (const uint8_t *)blocks;
 	const bool dbg = getenv("NGSCOV_DEBUG") != nullptr;
 	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-	double t_parse = now(), t_res = 0, t_stage = 0, t_launch = 0;
-	struct Chunk { size_t b0, b1, c0, c1; size_t ulen; };
-	std::vector<ngs_bgzf_desc> desc; std::vector<Chunk> chunks;
-	{
-		size_t off = 0; Chunk c = { 0, 0, 0, 0, 0 };
-		while (off < nbytes) {
+	double t_parse = 0, t_res = 0, t_stage = 0, t_launch = 0;
+	struct Chunk { size_t c0, c1, nb, ulen; };
+	const size_t desc_blocks = h->stage_cap / 16384 + 4096;
+	for (int i = 0; i < 2; ++i) if (!h->h_desc[i]) {
+		CK(cudaHostAlloc((void **)&h->h_desc[i], desc_blocks * sizeof(ngs_bgzf_desc), cudaHostAllocDefault));
+		CK(cudaMalloc((void **)&h->d_desc[i], desc_blocks * sizeof(ngs_bgzf_desc)));
+	}
+	size_t off = 0, n_blocks = 0, n_chunks = 0, total_u = 0;
+	auto plan = [&](int idx, Chunk &c) -> int {                   /* next chunk from `off`; c.nb == 0: end of input */
+		const double t0 = now();
+		CK(cudaEventSynchronize(h->ev_h2d[idx]));                 /* the copy that last read h_desc[idx] */
+		ngs_bgzf_desc *dd = h->h_desc[idx];
+		c.c0 = off; c.nb = 0; c.ulen = 0;
+		while (off < nbytes && c.nb < desc_blocks) {
 			if (off + 18 > nbytes) return NGSCOV_EFORMAT;
 			const uint8_t *p = src + off;
 			if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4) || p[12] != 'B' || p[13] != 'C') return NGSCOV_EFORMAT;
@@ -856,24 +871,16 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 			if (bsize < 26 || off + bsize > nbytes) return NGSCOV_EFORMAT;
 			uint32_t isize; memcpy(&isize, p + bsize - 4, 4);
 			if (isize > 65536 || isize > h->stage_cap) return NGSCOV_EFORMAT;
-			if (c.ulen + isize > h->stage_cap) { c.b1 = desc.size(); c.c1 = off; chunks.push_back(c); c.b0 = desc.size(); c.c0 = off; c.ulen = 0; }
+			if (c.ulen + isize > h->stage_cap) break;
 			ngs_bgzf_desc d; d.src = off + 18 - c.c0; d.dst = c.ulen; d.clen = (uint32_t)(bsize - 26); d.ulen = isize;
-			desc.push_back(d); c.ulen += isize; off += bsize;
+			dd[c.nb++] = d; c.ulen += isize; off += bsize;
 		}
-		c.b1 = desc.size(); c.c1 = off;
-		if (c.b1 > c.b0) chunks.push_back(c);
-	}
-	t_parse = now() - t_parse;
-	size_t total_u = 0;
-	for (const Chunk &c : chunks) total_u += c.ulen;
-	if (skip > total_u) return NGSCOV_EINVAL;
-	if (flags & NGSCOV_PUSH_LAST) { h->last_pushed = true; h->last_flags = flags; }
-	h->stats.stream_bytes += total_u - skip;
-	if ((r = resolve_pending(h))) return r;
-	if (chunks.empty()) return 0;
-	auto stage_in = [&](size_t k, int idx) -> int {               /* compressed bytes + descriptors of chunk k -> device */
-		const Chunk &c = chunks[k];
-		const size_t cb = c.c1 - c.c0, nb = c.b1 - c.b0;
+		c.c1 = off; n_blocks += c.nb; total_u += c.ulen;
+		t_parse += now() - t0;
+		return 0;
+	};
+	auto stage_in = [&](const Chunk &c, int idx) -> int {         /* compressed bytes + descriptors of a chunk -> device */
+		const size_t cb = c.c1 - c.c0;
 		if (cb + 16 > h->comp_cap[idx]) {
 			CK(cudaStreamSynchronize(h->s_main)); CK(cudaStreamSynchronize(h->s_copy));
 			if (h->d_comp[idx]) cudaFree(h->d_comp[idx]);
@@ -881,47 +888,47 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 			const size_t want = cb + cb / 8 + 4096;
 			CK(cudaMalloc((void **)&h->d_comp[idx], want)); h->comp_cap[idx] = want;
 		}
-		if (nb > h->desc_cap[idx]) {
-			CK(cudaStreamSynchronize(h->s_main)); CK(cudaStreamSynchronize(h->s_copy));
-			if (h->d_desc[idx]) cudaFree(h->d_desc[idx]);
-			h->d_desc[idx] = nullptr; h->desc_cap[idx] = 0;
-			const size_t want = nb + nb / 8 + 64;
-			CK(cudaMalloc((void **)&h->d_desc[idx], want * sizeof(ngs_bgzf_desc))); h->desc_cap[idx] = want;
-		}
 		/* no device-side wait: the inflate that last read these two buffers precedes a verification the host has
 		 * already waited for */
 		CK(cudaEventRecord(next_event(h->ev_cp, h->n_cp), h->s_copy));
 		CK(cudaMemcpyAsync(h->d_comp[idx], src + c.c0, cb, cudaMemcpyHostToDevice, h->s_copy));
-		CK(cudaMemcpyAsync(h->d_desc[idx], desc.data() + c.b0, nb * sizeof(ngs_bgzf_desc), cudaMemcpyHostToDevice, h->s_copy));
+		CK(cudaMemcpyAsync(h->d_desc[idx], h->h_desc[idx], c.nb * sizeof(ngs_bgzf_desc), cudaMemcpyHostToDevice, h->s_copy));
 		CK(cudaEventRecord(next_event(h->ev_cp, h->n_cp), h->s_copy));
 		CK(cudaEventRecord(h->ev_h2d[idx], h->s_copy));
 		return 0;
 	};
+	if (flags & NGSCOV_PUSH_LAST) { h->last_pushed = true; h->last_flags = flags; }
+	if ((r = resolve_pending(h))) return r;
+	Chunk cur, nxt;
 	int idx = 0;
-	if ((r = stage_in(0, idx))) return r;
+	if ((r = plan(idx, cur))) return h->sticky_err = r;
+	if (cur.nb && (r = stage_in(cur, idx))) return r;
 	int sm = 148;
 	cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->device);
-	for (size_t k = 0; k < chunks.size(); ++k, idx ^= 1) {
-		const Chunk &c = chunks[k];
+	for (; cur.nb; cur = nxt, idx ^= 1, ++n_chunks) {
+		const Chunk &c = cur;
 		/* the inflate of chunk k is queued BEFORE the host waits for the verification of chunk k-1: it depends on
 		 * nothing of it (other chunk buffer, no engine state), and it keeps the GPU busy while the host round trip --
-		 * wait, finalize k-1, copy k+1, frame k -- happens (measured: 4.5 ms of idle GPU per chunk otherwise) */
+		 * plan k+1, wait, finalize k-1, copy k+1, frame k -- happens (measured: 4.5 ms of idle GPU per chunk otherwise) */
 		double t0 = now();
 		uint8_t *data = h->d_chunk[idx] + NGS_HEADROOM;
 		CK(cudaStreamWaitEvent(h->s_main, h->ev_h2d[idx], 0));
-		const uint32_t nb = (uint32_t)(c.b1 - c.b0);
+		const uint32_t nb = (uint32_t)c.nb;
 		CK(cudaEventRecord(next_event(h->ev_inf, h->n_inf), h->s_main));
 		launch_inflate(h, idx, nb, data, sm);
 		CK(cudaEventRecord(next_event(h->ev_inf, h->n_inf), h->s_main));
 		h->stats.launches += 1;
 		CK(cudaGetLastError());
-		t_launch += now() - t0; t0 = now();
+		t_launch += now() - t0;
+		if ((r = plan(idx ^ 1, nxt))) return h->sticky_err = r;
+		t0 = now();
 		if ((r = resolve_pending(h, true))) return r;                /* chunk k-1 verified, its buffers are free */
 		t_res += now() - t0; t0 = now();
-		if (k + 1 < chunks.size() && (r = stage_in(k + 1, idx ^ 1))) return r;
+		if (nxt.nb && (r = stage_in(nxt, idx ^ 1))) return r;
 		t_stage += now() - t0; t0 = now();
 		const size_t sk = std::min(skip, c.ulen);
 		skip -= sk;
+		h->stats.stream_bytes += c.ulen - sk;
 		if (c.ulen == sk) {                                          /* header-only chunk: nothing is submitted, so nothing orders the
 		                                                                inflate that reads d_comp / d_desc[idx] before their reuse */
 			CK(cudaStreamSynchronize(h->s_main));
@@ -938,8 +945,9 @@ extern "C" int ngscov_push_bgzf(ngscov_t *h, const void *blocks, size_t nbytes, 
 		if ((r = submit_chunk(h, data + sk, (int64_t)(c.ulen - sk), true, 0))) return r;
 		t_launch += now() - t0;
 	}
-	if (dbg) fprintf(stderr, "ngscov_push_bgzf: %zu blocks, %zu chunks; host seconds: parse %.4f resolve %.4f stage_in %.4f launch %.4f\n",
-	                 desc.size(), chunks.size(), t_parse, t_res, t_stage, t_launch);
+	if (dbg) fprintf(stderr, "ngscov_push_bgzf: %zu blocks, %zu chunks; host seconds: plan %.4f resolve %.4f stage_in %.4f launch %.4f\n",
+	                 n_blocks, n_chunks, t_parse, t_res, t_stage, t_launch);
+	if (skip) return h->sticky_err = NGSCOV_EINVAL;                  /* skip beyond the inflated size of the blocks */
 	return 0;
 }
 
@@ -1036,7 +1044,8 @@ static int scan_range(ngscov *h, size_t s0, size_t s1, unsigned long long mops_b
 
 static int format_bed_range(ngscov *h, size_t s0, size_t s1);
 static int grow_host_text(ngscov *h, int which, size_t need, size_t keep);
-static int cover_tiles(ngscov *h, uint64_t t0, uint64_t t1, unsigned long long mops_bound);
+static int cover_tiles(ngscov *h, uint64_t t0, uint64_t t1, unsigned long long mops_bound, bool defer = false);
+static int cover_harvest(ngscov *h);
 static int stream_finalize_cover(ngscov *h);
 
 /* Finalize segments [next_fin_seg, seg_end) while the rest of the stream is still arriving. */
@@ -1175,6 +1184,7 @@ extern "C" int ngscov_finish_runs(ngscov_t *h)
 	}
 	if (h->cover && !h->red_mode) {
 		if (!h->seg.empty() && h->fin_tile < h->n_tiles * NGS_CPT && (r = cover_tiles(h, h->fin_tile, h->n_tiles * NGS_CPT, st.m_ops - h->mops_fin))) return r;
+		if ((r = cover_harvest(h))) return r;
 		if (h->cfg.mode == NGSCOV_MODE_DEPTH) { h->text_ready[NGSCOV_OUT_BEDGRAPH] = true; h->text_len[NGSCOV_OUT_BEDGRAPH] = h->bed_off; }
 		h->next_fin_seg = h->seg.size();
 		h->diff_dirty = false;
@@ -1463,11 +1473,15 @@ static uint32_t dig(uint64_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n
 /* Cover pipeline: owner tiles [t0, t1) (global owner-tile indices, any range: a launch may start and end inside a
  * contig) -- accumulate, scan, window bins and (DEPTH mode) the bedGraph text appended at bed_off, one kernel.
  * h_st2 receives the counters. */
-static int cover_tiles(ngscov *h, uint64_t t0, uint64_t t1, unsigned long long mops_bound)
+/* A streamed finalize (defer) does not wait for its kernels: the counters they leave (bytes of text, runs, halo) are
+ * read back by cover_harvest at the next launch, one chunk later, when they have long arrived -- the host never blocks
+ * on a finalize and the next chunk's kernels are queued behind it at once (the wait used to idle the GPU for about a
+ * millisecond per 256 MiB chunk).  At most one launch is pending. */
+static int cover_tiles(ngscov *h, uint64_t t0, uint64_t t1, unsigned long long mops_bound, bool defer)
 {
 	int r;
+	if ((r = cover_harvest(h))) return r;
 	const bool text = h->cfg.mode == NGSCOV_MODE_DEPTH;
-	const uint64_t total_tiles = h->n_tiles * NGS_CPT;
 	const uint64_t elems = (t1 - t0) * (uint64_t)NGS_CT;
 	/* segments the range touches */
 	size_t s0 = 0, s1 = h->seg.size();
@@ -1494,7 +1508,7 @@ static int cover_tiles(ngscov *h, uint64_t t0, uint64_t t1, unsigned long long m
 		if ((r = grow_text(h, NGSCOV_OUT_BEDGRAPH, h->bed_off + bound + 64, h->bed_off))) return r;
 		h->text_ready[NGSCOV_OUT_BEDGRAPH] = true; h->h_text_valid[NGSCOV_OUT_BEDGRAPH] = false;
 	}
-	tic(h);
+	CK(cudaEventRecord(h->ev_cov0, h->s_main));
 	if (!h->bins_zeroed) { CK(cudaMemsetAsync(h->d_bins, 0, h->n_bins * 8, h->s_main)); h->bins_zeroed = true; }
 	{	/* reset the per-launch fields of the device state block (the ingest fields stay live) */
 		const size_t o0 = offsetof(ngs_dev_state, scan_ticket), o1 = offsetof(ngs_dev_state, key_seed);
@@ -1544,10 +1558,27 @@ static int cover_tiles(ngscov *h, uint64_t t0, uint64_t t1, unsigned long long m
 		CK(cudaGetLastError());
 	}
 	if ((r = small_d2h(h, h->h_st2, h->d_st, sizeof(ngs_dev_state)))) return r;
-	h->stats.ms_scan += toc(h);
+	CK(cudaEventRecord(h->ev_cov1, h->s_main));
+	h->cov_pending = true; h->cov_t0 = t0; h->cov_t1 = t1;
+	h->fin_tile = t1;
+	return defer ? 0 : cover_harvest(h);
+}
+
+static int cover_harvest(ngscov *h)
+{
+	if (!h->cov_pending) return 0;
+	h->cov_pending = false;
+	int r;
+	const bool text = h->cfg.mode == NGSCOV_MODE_DEPTH;
+	const uint64_t total_tiles = h->n_tiles * NGS_CPT, t0 = h->cov_t0, t1 = h->cov_t1;
+	float ms = 0;
+	CK(cudaEventSynchronize(h->ev_cov1));
+	cudaEventElapsedTime(&ms, h->ev_cov0, h->ev_cov1);
+	h->stats.ms_scan += ms;
 	const ngs_dev_state &s2 = *h->h_st2;
 	if (s2.flags & NGS_FLAG_STALL) { snprintf(h->cuda_err, sizeof h->cuda_err, "look-back watchdog: a predecessor tile never published"); return h->sticky_err = NGSCOV_ECUDA; }
 	h->acc_boundaries += s2.n_boundaries; h->acc_runs += s2.n_runs;
+	h->mops_fin += s2.n_boundaries / 2;                         /* every interval makes at most two boundaries */
 	h->acc_max = std::max(h->acc_max, s2.max_depth); h->acc_min = std::min(h->acc_min, s2.min_depth);
 	h->stats.boundaries = h->acc_boundaries; h->stats.runs = h->acc_runs; h->stats.positions = h->n_elems;
 	if (s2.n_runs) {
@@ -1569,7 +1600,6 @@ static int cover_tiles(ngscov *h, uint64_t t0, uint64_t t1, unsigned long long m
 			h->bed_d2h = h->bed_off;
 		}
 	}
-	h->fin_tile = t1;
 	size_t ns = 0;                                              /* segments entirely below the finalized tiles */
 	while (ns < h->seg.size() && (ns + 1 < h->seg.size() ? h->seg[ns + 1].tile0 : h->n_tiles) * NGS_CPT <= t1) ++ns;
 	if (t1 >= total_tiles) ns = h->seg.size();
@@ -1599,8 +1629,7 @@ static int stream_finalize_cover(ngscov *h)
 	const auto t0 = std::chrono::steady_clock::now();
 	/* the interval counters lag one chunk behind the keys: allow for every record the pending chunk can hold */
 	const unsigned long long mops = h->h_st->m_ops - h->mops_fin + (unsigned long long)(h->p_n / 36 + 1) * 2;
-	int r = cover_tiles(h, h->fin_tile, upto, mops);
-	if (!r) h->mops_fin += h->h_st2->n_boundaries / 2;
+	int r = cover_tiles(h, h->fin_tile, upto, mops, true);
 	h->fin_wall += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++h->fin_calls;
 	return r;
 }
@@ -1699,6 +1728,7 @@ extern "C" int ngscov_output_device(ngscov_t *h, int which, const void **dev_buf
 {
 	if (!h || which < 0 || which > 2 || !dev_buf || !len) return NGSCOV_EINVAL;
 	if (!h->text_ready[which]) return NGSCOV_ESTATE;
+	{ const int rh = cover_harvest(h); if (rh) return rh; }
 	if (which == NGSCOV_OUT_BEDGRAPH && h->dev_stitched) {
 		CK(cudaSetDevice(h->device));
 		CK(cudaStreamSynchronize(h->s_main));
@@ -1734,6 +1764,7 @@ extern "C" int ngscov_output(ngscov_t *h, int which, const char **buf, size_t *l
 	if (!h->text_ready[which]) return NGSCOV_ESTATE;
 	if (which == NGSCOV_OUT_CHROMSIZE) { *buf = h->chromsize.data(); *len = h->chromsize.size(); return 0; }
 	CK(cudaSetDevice(h->device));
+	{ const int rh = cover_harvest(h); if (rh) return rh; }      /* a streamed finalize still in flight (only before ngscov_finish) */
 	if (which == NGSCOV_OUT_BEDGRAPH && h->bed_d2h && h->bed_d2h == h->text_len[which] && !h->h_text_valid[which]) {
 		tic(h);
 		CK(cudaStreamSynchronize(h->s_out));               /* streamed finalize: the copy has been in flight since the scan */
