@@ -528,6 +528,18 @@ def main():
                       "aux_output": ".depth" if job.mode == 0 else "wig",
                       "bedgraph_bytes": int(sum(int(x.item()) for x in alll)),
                       "rule": "sum_j byte_j * ((j + 1) * 0x9E3779B97F4A7C15 mod 2^64) mod 2^64 over the rank-ordered concatenation"}
+    # the full-size config-2 job is pinned against the UNMODIFIED reference binary run on the same generated BAM
+    # (tests/golden/config2_full_reference.json, made by tests/golden/make_config2_full_golden.py): same bytes, same hash
+    gold_path = os.path.join(ROOT, "tests", "golden", "config2_full_reference.json")
+    if rank == 0 and cfg == 2 and args.scale == 1.0 and args.window == 20000 and os.path.exists(gold_path):
+        gold = json.load(open(gold_path))
+        ph = parity["hash"]
+        ok = (int(gold["reads"]) == int(g.n_reads) and gold["bedgraph"]["hash"] == ph["bedgraph"] and gold["bedgraph"]["bytes"] == ph["bedgraph_bytes"]
+              and gold["depth"]["hash"] == ph["aux"])
+        parity["reference_full_size"] = {"match": bool(ok), "bedgraph_md5": gold["bedgraph"]["md5"], "reference_seconds": gold.get("reference_seconds"),
+                                         "what": "bedGraph and .depth of oracle/_ref/bam2depth (unmodified reference) on the same 618 M-read BAM: size and hash"}
+        if not ok:
+            print("bench: PARITY FAILURE: the output of the measured job differs from the reference's (tests/golden/config2_full_reference.json)", file=sys.stderr)
 
     # ---- end-to-end timing (host buffers, H2D + D2H inside)
     def time_e2e(step_fn, h2d_bytes):
@@ -634,6 +646,8 @@ def main():
     job.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity.get("reference_full_size", {}).get("match") is False:
+        sys.exit(1)                                   # a fast wrong answer is not a benchmark result
 
 
 def bind_to_gpu_numa(local):

@@ -123,3 +123,31 @@ def test_default_prefix_and_missing_index(exe, tmp_path):
     os.remove(bam + ".bai")
     p = subprocess.run([exe, bam], stderr=subprocess.PIPE)
     assert p.returncode == 1 and b"BAM indexing file is not available" in p.stderr   # bamSplitChr.c:63-70
+
+
+def test_records_with_a_contig_but_no_position_are_left_out(exe, tmp_path):
+    """refID >= 0 with POS -1 (placed-unmapped mates written that way by some aligners): bam_fetch never hands them out
+    (is_overlap compares the position as uint32), so they are in none of the per-contig files"""
+    sam2bam = os.path.join(ROOT, "oracle", "_ref", "sam2bam")
+    names, lens, reads = bamutil.random_case(9, n_reads=2000)
+    extra = [(0, -1, 4, "*"), (0, -1, 4, "*"), (2, -1, 69, "*")]
+    reads = sorted([r for r in reads if r[0] >= 0] + extra, key=lambda r: (r[0], r[1])) + [r for r in reads if r[0] < 0]
+    recs = bamutil.records(reads, seq_seed=1)
+    bam = str(tmp_path / "t.bam")
+    bamutil.write_bam(bam, names, lens, recs, index=False)
+    if os.path.exists(sam2bam):
+        subprocess.check_call([sam2bam, "--index-only", bam])
+    else:
+        open(bam + ".bai", "wb").write(b"BAI\1")          # the splitter only insists that the file exists
+    outs = split_both(exe, tmp_path, bam)
+    hdr = bamutil.header_bytes(names, lens)
+    raw, o, per = bytes(recs), 0, {i: b"" for i in range(len(names))}
+    for r in reads:
+        (bs,) = struct.unpack_from("<i", raw, o)
+        if r[0] >= 0 and r[1] >= 0:
+            per[r[0]] += raw[o:o + 4 + bs]
+        o += 4 + bs
+    for i, nm in enumerate(names):
+        assert inflate(outs[0][0]["x_%s.bam" % nm.decode()]) == hdr + per[i]
+    if len(outs) == 2:
+        assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]

@@ -124,3 +124,31 @@ def test_c_drivers_usage_and_missing_index(tmp_path):
         assert r.returncode == 1 and "BAM indexing file is not available" in r.stderr   # reference bam2depth.c:112-119
         r = subprocess.run([exe, "-o", str(tmp_path / "o"), str(tmp_path / "missing.bam")], capture_output=True, text=True, cwd=str(tmp_path))
         assert r.returncode == 1 and "Fail to open BAM file" in r.stderr
+
+
+def test_file_hash_tool_matches_the_bench_definition(tmp_path):
+    """tools/file_hash.py (CPU, used to pin device hashes against files the reference wrote) = the rule bench.py states:
+    sum_j byte_j * ((j + 1) * 0x9E3779B97F4A7C15 mod 2^64) mod 2^64"""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from file_hash import file_hash
+    b = np.random.RandomState(4).randint(0, 256, size=300007, dtype=np.uint8)
+    p = str(tmp_path / "x.bin")
+    b.tofile(p)
+    M, mask = 0x9E3779B97F4A7C15, (1 << 64) - 1
+    exp = 0
+    for j in range(0, b.size, 997):               # a strided sample of terms in Python integers, the rest by linearity
+        exp = (exp + int(b[j]) * (((j + 1) * M) & mask)) & mask
+    sub = np.zeros_like(b)
+    sub[::997] = b[::997]
+    q = str(tmp_path / "y.bin")
+    sub.tofile(q)
+    assert file_hash(q, step=4096)["hash"] == "%016x" % exp
+    whole = file_hash(p, step=65536)
+    assert whole["bytes"] == b.size and whole["hash"] == file_hash(p, step=1 << 20)["hash"]
+    gold = os.path.join(ROOT, "tests", "golden", "config2_full_reference.json")
+    if os.path.exists(gold):
+        import json
+        g = json.load(open(gold))
+        assert g["reads"] == 618271620 and len(g["bedgraph"]["hash"]) == 16 and g["bedgraph"]["bytes"] > 2e10
