@@ -21,7 +21,9 @@ One JSON line is printed by rank 0:
             with the already-inflated record stream (ngscov_push_host)
   roofline  the slowest kernel's algorithmic bytes / its device time vs the measured HBM copy peak
   parity    a check of THIS arm before the timed region: the same sharded job at a small scale compared byte for byte with
-            the CPU oracle, plus a 64-bit position-weighted hash of the full-size rank-ordered output (equal for every N)
+            the CPU oracle, plus a 64-bit position-weighted hash of the full-size rank-ordered output (equal for every N);
+            for the full-size config-2 job that hash is compared with the one of the files the UNMODIFIED reference wrote
+            for the same BAM (parity.reference_full_size, tests/golden/config2_full_reference.json): a mismatch exits 1
   cpu_baseline  the unmodified reference tool (oracle/_ref) timed on one core: a bounded sample for config 2, the full input
             for configs 1/4/5
   cli_wall  (config 1, and config 2 at --cli-scale) wall seconds of the drop-in C driver host/bam2depth and of the reference
@@ -192,6 +194,20 @@ def reference_arm(args):
                              "sample": f"{n_tot} reads per step: {cores} processes (the tool is single-threaded)"},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def full_size_gate(ph, n_reads, gold_path=None):
+    """The full-size config-2 job is pinned against the UNMODIFIED reference binary run on the same generated BAM
+    (tests/golden/config2_full_reference.json, made by tests/golden/make_config2_full_golden.py): the hash bench.py
+    computes on the device over the engine's output must be the hash of the files the reference wrote.  ph = parity["hash"]."""
+    gold_path = gold_path or os.path.join(ROOT, "tests", "golden", "config2_full_reference.json")
+    if not os.path.exists(gold_path):
+        return None
+    gold = json.load(open(gold_path))
+    ok = (int(gold["reads"]) == int(n_reads) and gold["bedgraph"]["hash"] == ph["bedgraph"] and int(gold["bedgraph"]["bytes"]) == int(ph["bedgraph_bytes"])
+          and gold["depth"]["hash"] == ph["aux"])
+    return {"match": bool(ok), "bedgraph_md5": gold["bedgraph"]["md5"], "reference_seconds": gold.get("reference_seconds"),
+            "what": "bedGraph and .depth of oracle/_ref/bam2depth (unmodified reference) on the same 618 M-read BAM: size and hash"}
 
 
 # --------------------------------------------------------------------------------------- our arm
@@ -528,18 +544,12 @@ def main():
                       "aux_output": ".depth" if job.mode == 0 else "wig",
                       "bedgraph_bytes": int(sum(int(x.item()) for x in alll)),
                       "rule": "sum_j byte_j * ((j + 1) * 0x9E3779B97F4A7C15 mod 2^64) mod 2^64 over the rank-ordered concatenation"}
-    # the full-size config-2 job is pinned against the UNMODIFIED reference binary run on the same generated BAM
-    # (tests/golden/config2_full_reference.json, made by tests/golden/make_config2_full_golden.py): same bytes, same hash
-    gold_path = os.path.join(ROOT, "tests", "golden", "config2_full_reference.json")
-    if rank == 0 and cfg == 2 and args.scale == 1.0 and args.window == 20000 and os.path.exists(gold_path):
-        gold = json.load(open(gold_path))
-        ph = parity["hash"]
-        ok = (int(gold["reads"]) == int(g.n_reads) and gold["bedgraph"]["hash"] == ph["bedgraph"] and gold["bedgraph"]["bytes"] == ph["bedgraph_bytes"]
-              and gold["depth"]["hash"] == ph["aux"])
-        parity["reference_full_size"] = {"match": bool(ok), "bedgraph_md5": gold["bedgraph"]["md5"], "reference_seconds": gold.get("reference_seconds"),
-                                         "what": "bedGraph and .depth of oracle/_ref/bam2depth (unmodified reference) on the same 618 M-read BAM: size and hash"}
-        if not ok:
-            print("bench: PARITY FAILURE: the output of the measured job differs from the reference's (tests/golden/config2_full_reference.json)", file=sys.stderr)
+    if rank == 0 and cfg == 2 and args.scale == 1.0 and args.window == 20000:
+        gate = full_size_gate(parity["hash"], g.n_reads)
+        if gate is not None:
+            parity["reference_full_size"] = gate
+            if not gate["match"]:
+                print("bench: PARITY FAILURE: the output of the measured job differs from the reference's (tests/golden/config2_full_reference.json)", file=sys.stderr)
 
     # ---- end-to-end timing (host buffers, H2D + D2H inside)
     def time_e2e(step_fn, h2d_bytes):

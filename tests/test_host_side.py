@@ -152,3 +152,23 @@ def test_file_hash_tool_matches_the_bench_definition(tmp_path):
         import json
         g = json.load(open(gold))
         assert g["reads"] == 618271620 and len(g["bedgraph"]["hash"]) == 16 and g["bedgraph"]["bytes"] > 2e10
+
+
+def test_full_size_gate_of_the_bench(tmp_path):
+    """bench.py compares the device hash of the full-size config-2 output with the hash of the files the unmodified
+    reference wrote (tests/golden/config2_full_reference.json).  The line saved from the B200 run must pass the gate, and
+    a different hash must not."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("ngscov_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    gold = os.path.join(ROOT, "tests", "golden", "config2_full_reference.json")
+    if not os.path.exists(gold):
+        pytest.skip("golden not made yet")
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r2_bench_config2.json")).read().strip().splitlines()[-1])
+    ph = line["parity"]["hash"]
+    assert bench.full_size_gate(ph, line["config"]["reads"])["match"] is True
+    bad = dict(ph, bedgraph="0" * 16)
+    assert bench.full_size_gate(bad, line["config"]["reads"])["match"] is False
+    assert bench.full_size_gate(ph, line["config"]["reads"], gold_path=str(tmp_path / "none.json")) is None
