@@ -37,48 +37,48 @@ static void usage(const char *prog)
 	exit(1);
 }
 
-/* bam_parse_region (samtools-0.1.19 bam_aux.c) restated: white space removed, the name ends at the last colon if what
- * follows is digits, commas and at most one hyphen (otherwise the whole string is the name; a name that is not in the
- * header is tried as the whole string as well); "beg-end" is 1-based inclusive -> beg - 1, end; no interval = the
- * whole contig [0, 1<<29).  Returns the refID or -1. */
+/* Region strings as bam_parse_region reads them (samtools-0.1.19 bam_aux.c, called at bam_sliding_count.c:401):
+ * white space is dropped; what follows the LAST colon is an interval if it consists of digits, commas and at most one
+ * hyphen, otherwise the colon belongs to the contig name; a name the header does not know is retried as the whole
+ * string; "beg-end" is 1-based inclusive and becomes [beg - 1, end), a lone "beg" runs to 1 << 29, no interval means
+ * the whole contig [0, 1 << 29).  Returns the refID or -1. */
 static int find_ref(char **ref_name, int n_ref, const char *s)
 {
 	for (int i = 0; i < n_ref; ++i) if (!strcmp(ref_name[i], s)) return i;
 	return -1;
 }
+static int interval_like(const char *t)
+{
+	int hyphens = 0;
+	for (; *t; ++t) {
+		if (*t == '-') { if (++hyphens > 1) return 0; }
+		else if (*t != ',' && (*t < '0' || *t > '9')) return 0;
+	}
+	return 1;
+}
 static int parse_region(char **ref_name, int n_ref, const char *str, int *beg, int *end)
 {
-	int l = (int)strlen(str), k = 0, i, name_end, ref;
-	char *s = (char *)malloc((size_t)l + 1);
-	*beg = *end = -1;
-	for (i = 0; i < l; ++i) if (!(str[i] == ' ' || (str[i] >= 9 && str[i] <= 13))) s[k++] = str[i];
-	s[k] = 0; l = k; name_end = l;
-	for (i = l - 1; i >= 0; --i) if (s[i] == ':') break;
-	if (i >= 0) name_end = i;
-	if (name_end < l) {
-		int n_hyphen = 0;
-		for (i = name_end + 1; i < l; ++i) {
-			if (s[i] == '-') ++n_hyphen;
-			else if (!(s[i] >= '0' && s[i] <= '9') && s[i] != ',') break;
-		}
-		if (i < l || n_hyphen > 1) name_end = l;
-		s[name_end] = 0;
+	char *s = (char *)malloc(strlen(str) + 1), *w = s, *colon, *num = NULL;
+	int ref;
+	for (const char *p = str; *p; ++p) if (*p != ' ' && !(*p >= 9 && *p <= 13)) *w++ = *p;
+	*w = 0;
+	*beg = 0; *end = 1 << 29;
+	colon = strrchr(s, ':');
+	if (colon && interval_like(colon + 1)) {
+		*colon = 0;
 		ref = find_ref(ref_name, n_ref, s);
-		if (ref < 0) {
-			ref = find_ref(ref_name, n_ref, str);
-			if (ref < 0) { free(s); return -1; }
-			s[name_end] = ':'; name_end = l;
-		}
+		if (ref >= 0) num = colon + 1;
+		else ref = find_ref(ref_name, n_ref, str);               /* the name itself may end in ":digits" */
 	} else ref = find_ref(ref_name, n_ref, str);
-	if (ref < 0) { free(s); return -1; }
-	if (name_end < l) {
-		for (i = k = name_end + 1; i < l; ++i) if (s[i] != ',') s[k++] = s[i];
-		s[k] = 0;
-		*beg = atoi(s + name_end + 1);
-		for (i = name_end + 1; i != k; ++i) if (s[i] == '-') break;
-		*end = i < k ? atoi(s + i + 1) : 1 << 29;
+	if (ref >= 0 && num) {
+		char *d = num, *hy;
+		for (char *p = num; *p; ++p) if (*p != ',') *d++ = *p;      /* thousands separators */
+		*d = 0;
+		*beg = atoi(num);
+		hy = strchr(num, '-');
+		if (hy) *end = atoi(hy + 1);
 		if (*beg > 0) --*beg;
-	} else { *beg = 0; *end = 1 << 29; }
+	}
 	free(s);
 	return ref;
 }

@@ -191,3 +191,26 @@ def test_c_driver_bam_sliding_count(tmp_path):
     assert int([ln for ln in r.stderr.splitlines() if ln.strip().isdigit()][0]) == g["n_count"]
     r = subprocess.run([exe, "-o", "o", "-r", "nosuchcontig:5-9", bam], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 1 and "Invalid region" in r.stderr
+
+
+def test_region_strings_parse_like_samtools(tmp_path):
+    """parse_region of the C driver against what samtools-0.1.19 bam_parse_region returned for the same strings
+    (table recorded from oracle/_ref/libbam.a; refID -1 = "Invalid region")"""
+    table = [("c1", 0, 0, 1 << 29), ("c1:1000-5000", 0, 999, 5000), ("c1:2,001-2,500", 0, 2000, 2500), ("chr2:69000", 1, 68999, 1 << 29),
+             (" chr2 : 10 - 20 ", 1, 9, 20), ("HLA:01-2", 2, 0, 1 << 29), ("HLA:01-2:5-9", 2, 4, 9), ("x:y", 3, 0, 1 << 29), ("x:y:7", 3, 6, 1 << 29),
+             ("nope:1-2", -1, None, None), ("c1:", 0, 0, 1 << 29), ("c1:-5", 0, -5, 5), ("c1:5-", 0, 4, 0), ("c1:1-2-3", -1, None, None),
+             ("c1:0-10", 0, 0, 10), ("c1:abc", -1, None, None)]
+    src = tmp_path / "h.c"
+    cli = os.path.join(ROOT, "highperformancengs_b200", "host", "ngscov_slide_cli.c")
+    src.write_text('#include <stdio.h>\n#define main slide_main\n#include "%s"\n#undef main\n' % cli +
+                   'int main(int argc, char **argv) { char *names[] = { "c1", "chr2", "HLA:01-2", "x:y" }; int b, e;\n'
+                   '  for (int i = 1; i < argc; ++i) { int r = parse_region(names, 4, argv[i], &b, &e); printf("%d %d %d\\n", r, b, e); } return 0; }\n')
+    exe = str(tmp_path / "h")
+    lib = os.path.join(ROOT, "highperformancengs_b200")
+    subprocess.check_call(["gcc", "-O1", "-w", str(src), "-o", exe, "-L" + lib, "-lngscov_cuda", "-Wl,-rpath," + lib, "-lz"])
+    out = subprocess.run([exe] + [t[0] for t in table], capture_output=True, text=True, check=True).stdout.split("\n")
+    for (q, r, b, e), line in zip(table, out):
+        gr, gb, ge = (int(x) for x in line.split())
+        assert gr == r, q
+        if r >= 0:
+            assert (gb, ge) == (b, e), q
