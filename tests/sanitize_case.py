@@ -46,10 +46,13 @@ def main():
             data = open(bam, "rb").read()
         hdr_len = bamio.parse_header(bamio.bgzf_inflate(data))[2]
         exp = oracle_py.run(recs, names, lens, 0, 500)
-        with CoverageEngine(names, lens, mode=0, window=500, emit_wig=True) as eng:
-            eng.push_bgzf(data, skip=hdr_len, last=True)
-            eng.finish()
-            assert eng.output(0) == exp["bedgraph"] and eng.output(1) == exp["depth"]
+        for decoders in ("1", "2"):                    # one decoder per warp, and the opt-in two-per-warp state machine
+            os.environ["NGSCOV_INF_S"] = decoders
+            with CoverageEngine(names, lens, mode=0, window=500, emit_wig=True) as eng:
+                eng.push_bgzf(data, skip=hdr_len, last=True)
+                eng.finish()
+                assert eng.output(0) == exp["bedgraph"] and eng.output(1) == exp["depth"]
+        del os.environ["NGSCOV_INF_S"]
     print("sanitize_case ok:", what)
 
 
